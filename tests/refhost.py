@@ -27,6 +27,10 @@ class RefHost:
         L.srt_ref_sellmeier.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
         L.srt_ref_spectrum_interp.restype = C.c_float
         L.srt_ref_spectrum_interp.argtypes = [C.c_void_p, C.c_float]
+        L.srt_ref_spectrum_to_xyz.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.srt_ref_tonemap.argtypes = [C.c_void_p, C.c_void_p]
+        L.srt_ref_color_spectrum.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]
+        L.srt_ref_prepare_color.argtypes = [C.c_float, C.c_float, C.c_float]
 
     def open(self, *args):
         argv = (C.c_char_p * len(args))(*[str(a).encode() for a in args])
