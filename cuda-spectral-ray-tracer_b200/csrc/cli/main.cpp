@@ -1,0 +1,52 @@
+// srt_cli: drop-in for the reference executable (main.cpp:135-167) on top of the C-ABI.
+// Same flags (io/params.h:236-304); --no-show is implied (there is no display window), --save
+// writes renders/<title>.bmp like main.cpp:113-118, plus a .ppm next to it.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cctype>
+#include <string>
+#include <vector>
+#include <sys/stat.h>
+#include "srt.h"
+
+int main(int argc, char** argv) {
+    srt_params* pm = srt_params_instance();
+    srt_params_parse(pm, argc, argv);
+    std::printf("Image Title: %s\nScene ID: %u\nX res: %u\nY res: %u\nAR: %g\nX chunk size: %u\nY chunk size: %u\n# samples: %u\n# max bounces: %u\n",
+                srt_params_img_title(pm), srt_params_scene_id(pm), srt_params_xres(pm), srt_params_yres(pm), srt_params_ar(pm),
+                srt_params_xcsize(pm), srt_params_ycsize(pm), srt_params_nsamples(pm), srt_params_bounce_limit(pm));
+    srt_scene* scene = srt_scene_create(srt_params_scene_id(pm));
+    const char* msg = nullptr;
+    if (!srt_scene_result(scene, &msg)) { std::fprintf(stderr, "%s\n", msg); return 1; }
+    std::printf("%s\n", msg);
+    srt_camera cam;
+    srt_scene_camera(scene, &cam);
+    const size_t n = (size_t)cam.width * cam.height;
+    std::vector<float> r(n), g(n), b(n);
+    srt_render_manager* rm = srt_render_manager_create(scene, &cam, r.data(), g.data(), b.data());
+    if (srt_rm_init_renderer(rm, srt_params_bounce_limit(pm), srt_params_nsamples(pm)) != SRT_OK ||
+        srt_rm_init_device_params(rm, srt_params_xcsize(pm), srt_params_ycsize(pm)) != SRT_OK) {
+        std::fprintf(stderr, "%s\n", srt_last_error());
+        return 1;
+    }
+    std::fprintf(stderr, "Rendering... ");
+    const auto t0 = std::chrono::steady_clock::now();
+    if (srt_rm_render_all(rm) != SRT_OK) { std::fprintf(stderr, "%s\n", srt_last_error()); return 1; }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    srt_stats st;
+    srt_rm_get_stats(rm, &st);
+    std::fprintf(stderr, "done, took %g seconds.\n", sec);
+    std::printf("total rendering time (seconds): %g\nkernel time (ms): %g\nsamples/s: %g\nrays: %llu\n", sec, st.render_ms,
+                st.samples / (st.render_ms * 1e-3), (unsigned long long)st.rays);
+    if (srt_params_do_save(pm)) {
+        std::string name = srt_params_img_title(pm);
+        for (char& c : name) c = c == ' ' ? '_' : (char)std::tolower((unsigned char)c);  // utils/utility.h:30-39
+        mkdir("renders", 0755);
+        srt_write_bmp(("renders/" + name + ".bmp").c_str(), r.data(), g.data(), b.data(), cam.width, cam.height);
+        srt_write_ppm(("renders/" + name + ".ppm").c_str(), r.data(), g.data(), b.data(), cam.width, cam.height);
+    }
+    srt_render_manager_destroy(rm);
+    srt_scene_destroy(scene);
+    return 0;
+}

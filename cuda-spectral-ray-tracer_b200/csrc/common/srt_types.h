@@ -1,0 +1,62 @@
+// Shared host/device plain-old-data layouts of the B200 path tracer (see DESIGN.md "HBM layout").
+#ifndef SRT_TYPES_H
+#define SRT_TYPES_H
+#include <stdint.h>
+
+#define SRT_N_WL 7           // hero + 6 rotations (reference ray/ray.cuh:12)
+#define SRT_NS 95            // spectrum samples, 360..830 nm @ 5 nm (utils/cie_const.cuh:8)
+#define SRT_EPSILON 0.0001f  // self-intersection offset (materials/material.cuh:14)
+
+// material type tags (reference materials/material.cuh:16-22)
+#define SRT_LAMBERTIAN 0u
+#define SRT_METALLIC 1u
+#define SRT_DIELECTRIC 2u
+#define SRT_EMISSIVE 4u
+
+// ---- device triangle, 48 B = 3 x 16-B vectors ------------------------------------------
+// q0 = plane (nx, ny, nz, D)
+// q1 = (w0, h0, w1, h1)   projected vertices on the triangle's 2-D test plane
+// q2 = (w2, h2, bits, 0)  bits: [15:0] material index, [16] clockwise, [18:17] w axis,
+//                         [20:19] h axis, [23:21] material type
+struct alignas(16) SrtTri {
+    float nx, ny, nz, D;
+    float w0, h0, w1, h1;
+    float w2, h2;
+    uint32_t bits;
+    uint32_t pad;
+};
+#define SRT_TRI_MAT(bits) ((bits) & 0xFFFFu)
+#define SRT_TRI_CW(bits) (((bits) >> 16) & 1u)
+#define SRT_TRI_WAX(bits) (((bits) >> 17) & 3u)
+#define SRT_TRI_HAX(bits) (((bits) >> 19) & 3u)
+#define SRT_TRI_MTYPE(bits) (((bits) >> 21) & 7u)
+
+// ---- device BVH node, 64 B = 4 x 16-B vectors (both child boxes in the parent) -----------
+// q0 = (c0.xmin, c0.xmax, c0.ymin, c0.ymax)   q1 = (c1.xmin, c1.xmax, c1.ymin, c1.ymax)
+// q2 = (c0.zmin, c0.zmax, c1.zmin, c1.zmax)   q3 = (child0, child1, -, -)
+// child >= 0: internal node index; child < 0: leaf, triangle index = ~child
+struct alignas(16) SrtNode {
+    float c0xmin, c0xmax, c0ymin, c0ymax;
+    float c1xmin, c1xmax, c1ymin, c1ymax;
+    float c0zmin, c0zmax, c1zmin, c1zmax;
+    int32_t child0, child1;
+    int32_t pad0, pad1;
+};
+
+// ---- device material, 400 B: 95-sample spectrum + parameters ------------------------------
+struct alignas(16) SrtMaterial {
+    float spec[SRT_NS];
+    float fuzz;
+    float sellB[3];
+    float sellC[3];
+    uint32_t type;
+};
+
+struct SrtCamera {
+    uint32_t width, height;
+    float du[3], dv[3], p00[3];
+    float defocus_angle;
+    float center[3], disk_u[3], disk_v[3];
+};
+
+#endif

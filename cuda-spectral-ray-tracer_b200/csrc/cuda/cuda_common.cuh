@@ -1,0 +1,18 @@
+// Small CUDA host helpers shared by the .cu files of libsrt.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <string>
+#include "../host/srt_host.hpp"
+
+namespace srt {
+extern std::atomic<uint64_t> g_kernel_launches;
+inline void count_launch(uint64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+bool cuda_ok(cudaError_t e, const char* what, const char* file, int line);
+}  // namespace srt
+
+#define SRT_CUDA(call)                                                   \
+    do {                                                                 \
+        if (!::srt::cuda_ok((call), #call, __FILE__, __LINE__)) return false; \
+    } while (0)
+#define SRT_CUDA_LAST() SRT_CUDA(cudaGetLastError())

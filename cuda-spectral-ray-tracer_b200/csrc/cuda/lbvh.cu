@@ -1,0 +1,536 @@
+// LBVH construction on the device (Karras 2012) + the standalone closest-hit query kernel.
+//
+//   bounds   : leaf box = padded triangle box, centroid, scene box (float atomics on ordered ints)
+//   morton   : 30-bit code per triangle (10 bits per axis, x highest)
+//   sort     : hand-written ONESWEEP least-significant-digit radix sort, 4 passes of 8 bits,
+//              one global histogram pre-pass, decoupled look-back, warp match/ballot ranking,
+//              stable => equal codes stay in triangle-index order
+//   hierarchy: one thread per internal node, clz(key_i ^ key_j) prefix lengths, ties broken by index
+//   refit    : bottom-up, one thread per leaf, second arrival at a node does the union
+//   emit     : 64-B traversal nodes carrying both child boxes + triangles permuted to leaf order
+//
+// Specification and bit-exactness oracle: oracle/lbvh_oracle.c.  The reference
+// itself builds its BVH serially in one thread (bvh/bvh.cu:206-345, scene/scene.cu:9-20); this
+// file replaces that step.  Compiled with -fmad=false: everything here is bandwidth bound and
+// the Morton quantisation must round exactly like the CPU specification.
+#include "cuda_common.cuh"
+#include <cfloat>
+#include <cstdio>
+#include <vector>
+
+namespace srt {
+
+std::atomic<uint64_t> g_kernel_launches{0};
+uint64_t kernel_launches() { return g_kernel_launches.load(); }
+
+bool cuda_ok(cudaError_t e, const char* what, const char* file, int line) {
+    if (e == cudaSuccess) return true;
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d '%s'", (int)e, cudaGetErrorString(e), file, line, what);
+    set_error(buf);
+    return false;
+}
+int cuda_device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+bool cuda_select_device(int dev) { SRT_CUDA(cudaSetDevice(dev)); return true; }
+
+// ------------------------------------------------------------------------------------------
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_PASSES = 4;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per tile
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+
+struct DeviceScene {
+    uint32_t n = 0, n_mats = 0;
+    // inputs
+    float* verts = nullptr;       // n x 9
+    SrtTri* tris_in = nullptr;    // n, original order
+    SrtMaterial* mats = nullptr;
+    // build products
+    float* leaf_boxes = nullptr;  // n x 6 (xmin xmax ymin ymax zmin zmax), original order
+    float* centroids = nullptr;   // n x 3
+    float* scene_box = nullptr;   // 6 floats (as ordered ints during the reduction)
+    uint32_t* codes = nullptr;    // n, original order
+    uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+    uint32_t* hist = nullptr;     // SORT_PASSES x RADIX global digit counts -> exclusive bases
+    uint32_t* lookback = nullptr; // SORT_PASSES x tiles x RADIX status words
+    uint32_t* tile_counter = nullptr;  // SORT_PASSES dynamic tile ids
+    int32_t *left = nullptr, *right = nullptr, *parent = nullptr;
+    float* node_boxes = nullptr;  // (2n-1) x 6
+    uint32_t* visit = nullptr;    // n-1 refit arrival flags
+    SrtNode* nodes = nullptr;     // n-1 traversal nodes
+    SrtTri* tris = nullptr;       // n, LEAF order
+    uint32_t tiles = 0;
+    cudaEvent_t ev[6];
+    double last_build_ms = 0;
+    cudaStream_t stream = nullptr;
+};
+
+// ---- float <-> order-preserving uint for atomic min/max ----
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+__global__ void k_init_scene_box(uint32_t* box) {
+    if (threadIdx.x < 6) box[threadIdx.x] = (threadIdx.x & 1) ? f2ord(-INFINITY) : f2ord(INFINITY);
+}
+
+// leaf box (bvh/aabb.cuh:49-57 + pad :93-102), centroid (primitives/tri.cuh:73-77), scene box
+__global__ void __launch_bounds__(256) k_bounds(const float* __restrict__ verts, uint32_t n, float* __restrict__ leaf_boxes,
+                                                float* __restrict__ centroids, uint32_t* __restrict__ scene_box) {
+    __shared__ uint32_t sbox[6];
+    if (threadIdx.x < 6) sbox[threadIdx.x] = (threadIdx.x & 1) ? f2ord(-INFINITY) : f2ord(INFINITY);
+    __syncthreads();
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float v[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) v[k] = verts[9ull * i + k];
+        const float third = 1 / 3.f;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            float mn = fminf(v[a], fminf(v[3 + a], v[6 + a]));
+            float mx = fmaxf(v[a], fmaxf(v[3 + a], v[6 + a]));
+            if (!((mx - mn) >= 0.0001f)) {
+                const float padding = 0.0001f / 2;
+                mn = mn - padding;
+                mx = mx + padding;
+            }
+            leaf_boxes[6ull * i + 2 * a] = mn;
+            leaf_boxes[6ull * i + 2 * a + 1] = mx;
+            centroids[3ull * i + a] = third * ((v[a] + v[3 + a]) + v[6 + a]);
+            lo[a] = fminf(lo[a], mn);
+            hi[a] = fmaxf(hi[a], mx);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&sbox[2 * a], f2ord(lo[a]));
+            atomicMax(&sbox[2 * a + 1], f2ord(hi[a]));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        if (threadIdx.x & 1) atomicMax(&scene_box[threadIdx.x], sbox[threadIdx.x]);
+        else atomicMin(&scene_box[threadIdx.x], sbox[threadIdx.x]);
+    }
+}
+__global__ void k_decode_scene_box(uint32_t* box) {
+    if (threadIdx.x < 6) box[threadIdx.x] = __float_as_uint(ord2f(box[threadIdx.x]));
+}
+
+__device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t quant10(float c, float lo, float hi) {
+    float x = (c - lo) / (hi - lo);
+    x = fminf(fmaxf(x * 1024.0f, 0.0f), 1023.0f);
+    return (uint32_t)x;
+}
+// Morton code per triangle + identity payload + the global digit histogram of all 4 passes
+__global__ void __launch_bounds__(256) k_morton_hist(const float* __restrict__ centroids, const float* __restrict__ scene_box, uint32_t n,
+                                                     uint32_t* __restrict__ codes, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                     uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[SORT_PASSES * RADIX];
+    for (int i = threadIdx.x; i < SORT_PASSES * RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const float b0 = scene_box[0], b1 = scene_box[1], b2 = scene_box[2], b3 = scene_box[3], b4 = scene_box[4], b5 = scene_box[5];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t xx = expand_bits(quant10(centroids[3ull * i], b0, b1));
+        const uint32_t yy = expand_bits(quant10(centroids[3ull * i + 1], b2, b3));
+        const uint32_t zz = expand_bits(quant10(centroids[3ull * i + 2], b4, b5));
+        const uint32_t code = xx * 4 + yy * 2 + zz;
+        codes[i] = code;
+        keys[i] = code;
+        vals[i] = i;
+#pragma unroll
+        for (int p = 0; p < SORT_PASSES; p++) atomicAdd(&sh[p * RADIX + ((code >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SORT_PASSES * RADIX; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// exclusive scan of each pass' 256 digit counts (one block, one warp-scan per 32 digits)
+__global__ void k_scan_hist(uint32_t* hist) {
+    __shared__ uint32_t warp_tot[RADIX / 32];
+    for (int p = 0; p < SORT_PASSES; p++) {
+        const uint32_t v = hist[p * RADIX + threadIdx.x];
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((threadIdx.x & 31) >= o) inc += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += warp_tot[w];
+        hist[p * RADIX + threadIdx.x] = base + inc - v;
+        __syncthreads();
+    }
+}
+
+// ---- one onesweep pass --------------------------------------------------------------------
+// status word: [31:30] 0 = empty, 1 = tile-local count, 2 = inclusive prefix; [29:0] value
+constexpr uint32_t LB_LOCAL = 1u << 30, LB_INCL = 2u << 30, LB_MASK = (1u << 30) - 1;
+
+__global__ void __launch_bounds__(SORT_THREADS) k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                           uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+                                                           const uint32_t* __restrict__ digit_base, volatile uint32_t* lookback,
+                                                           uint32_t* tile_counter) {
+    __shared__ uint32_t s_warp_hist[SORT_WARPS][RADIX];  // per-warp digit counts -> per-warp exclusive offsets
+    __shared__ uint32_t s_tile_off[RADIX];               // exclusive offset of each digit inside the sorted tile
+    __shared__ uint32_t s_glob_off[RADIX];               // global position of the tile's first key of each digit
+    __shared__ uint32_t s_keys[SORT_TILE];
+    __shared__ uint32_t s_vals[SORT_TILE];
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);  // dynamic tile id: earlier tiles are always already running
+    for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t tile_base = tile * SORT_TILE;
+    // warp-striped load: warp w owns [w*512, (w+1)*512), item i of lane l = w*512 + i*32 + l
+    uint32_t key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        const uint32_t g = tile_base + warp * (SORT_ITEMS * 32) + i * 32 + lane;
+        key[i] = g < n ? keys_in[g] : 0xFFFFFFFFu;
+        val[i] = g < n ? vals_in[g] : 0u;
+    }
+    // stable rank of every key among equal digits of its warp (items in order, lanes in order)
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        const uint32_t g = tile_base + warp * (SORT_ITEMS * 32) + i * 32 + lane;
+        const bool valid = g < n;
+        const uint32_t digit = (key[i] >> shift) & (RADIX - 1);
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : (RADIX + lane));
+        const uint32_t before = __popc(peers & ((1u << lane) - 1));
+        uint32_t base = 0;
+        if (valid && before == 0) {  // leader of the peer group bumps the warp counter
+            base = s_warp_hist[warp][digit];
+            s_warp_hist[warp][digit] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+        rank[i] = base + before;
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive scan over warps (stability across warps) and the tile-local count
+    uint32_t local_count = 0;
+    {
+        const int d = tid;  // SORT_THREADS == RADIX
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            const uint32_t c = s_warp_hist[w][d];
+            s_warp_hist[w][d] = run;
+            run += c;
+        }
+        local_count = run;
+        // publish the local count, then look back over earlier tiles for the exclusive prefix
+        volatile uint32_t* lb = lookback + (size_t)tile * RADIX + d;
+        if (tile > 0) *lb = LB_LOCAL | local_count;
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            while (true) {
+                const uint32_t s = lookback[(size_t)t * RADIX + d];
+                const uint32_t flag = s & ~LB_MASK;
+                if (flag == LB_INCL) { excl += s & LB_MASK; break; }
+                if (flag == LB_LOCAL) { excl += s & LB_MASK; t--; }
+                // flag empty: the earlier tile has not published yet; poll again
+            }
+        }
+        __threadfence();
+        *lb = LB_INCL | (excl + local_count);
+        s_glob_off[d] = digit_base[d] + excl;
+    }
+    // exclusive scan of the tile-local digit counts -> position of each digit inside the sorted tile
+    {
+        uint32_t inc = local_count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        __shared__ uint32_t s_wtot[SORT_WARPS];
+        if (lane == 31) s_wtot[warp] = inc;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < warp; w++) base += s_wtot[w];
+        s_tile_off[tid] = base + inc - local_count;
+    }
+    __syncthreads();
+    // scatter into shared memory in sorted order
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        const uint32_t g = tile_base + warp * (SORT_ITEMS * 32) + i * 32 + lane;
+        if (g < n) {
+            const uint32_t digit = (key[i] >> shift) & (RADIX - 1);
+            const uint32_t pos = s_tile_off[digit] + s_warp_hist[warp][digit] + rank[i];
+            s_keys[pos] = key[i];
+            s_vals[pos] = val[i];
+        }
+    }
+    __syncthreads();
+    // coalesced write-out: consecutive threads write consecutive addresses inside each digit run
+    const uint32_t count = min((uint32_t)SORT_TILE, n - tile_base);
+    for (uint32_t j = tid; j < count; j += SORT_THREADS) {
+        const uint32_t k = s_keys[j];
+        const uint32_t digit = (k >> shift) & (RADIX - 1);
+        const uint32_t dst = s_glob_off[digit] + (j - s_tile_off[digit]);
+        keys_out[dst] = k;
+        vals_out[dst] = s_vals[j];
+    }
+}
+
+// ---- hierarchy ------------------------------------------------------------------------------
+__device__ __forceinline__ int lcp(const uint32_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint32_t a = keys[i], b = keys[j];
+    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clz(a ^ b);
+}
+__global__ void __launch_bounds__(256) k_hierarchy(const uint32_t* __restrict__ keys, int n, int32_t* __restrict__ left, int32_t* __restrict__ right,
+                                                   int32_t* __restrict__ parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) parent[0] = -1;
+    if (i >= n - 1) return;
+    const int d = (lcp(keys, n, i, i + 1) - lcp(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = lcp(keys, n, i, i - d);
+    int lmax = 2;
+    while (lcp(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (lcp(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = lcp(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (lcp(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int L = (lo == gamma) ? (n - 1 + gamma) : gamma;
+    const int R = (hi == gamma + 1) ? (n - 1 + gamma + 1) : gamma + 1;
+    left[i] = L;
+    right[i] = R;
+    parent[L] = i;
+    parent[R] = i;
+}
+
+// ---- refit ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_refit(int n, const uint32_t* __restrict__ sorted_idx, const float* __restrict__ leaf_boxes,
+                                               const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                               const int32_t* __restrict__ parent, float* node_boxes, uint32_t* visit) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float b[6];
+    const uint32_t src = sorted_idx[k];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        b[c] = leaf_boxes[6ull * src + c];
+        node_boxes[6ull * (n - 1 + k) + c] = b[c];
+    }
+    int node = parent[n - 1 + k];
+    int from = n - 1 + k;
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&visit[node], 1u) == 0) return;  // the sibling subtree finishes this node
+        const int other = left[node] == from ? right[node] : left[node];
+        const volatile float* ob = node_boxes + 6ull * other;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            b[2 * c] = fminf(b[2 * c], ob[2 * c]);
+            b[2 * c + 1] = fmaxf(b[2 * c + 1], ob[2 * c + 1]);
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) node_boxes[6ull * node + c] = b[c];
+        from = node;
+        node = parent[node];
+    }
+}
+
+// ---- emit traversal layout -------------------------------------------------------------------
+__device__ __forceinline__ float widen_lo(float v) { return v - fabsf(v) * 2.4e-7f; }
+__device__ __forceinline__ float widen_hi(float v) { return v + fabsf(v) * 2.4e-7f; }
+__global__ void __launch_bounds__(256) k_emit(int n, const uint32_t* __restrict__ sorted_idx, const int32_t* __restrict__ left,
+                                              const int32_t* __restrict__ right, const float* __restrict__ node_boxes,
+                                              const SrtTri* __restrict__ tris_in, SrtNode* __restrict__ nodes, SrtTri* __restrict__ tris) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tris[i] = tris_in[sorted_idx[i]];
+    if (i >= n - 1) return;
+    const int L = left[i], R = right[i];
+    const float* a = node_boxes + 6ull * L;
+    const float* b = node_boxes + 6ull * R;
+    SrtNode nd;
+    nd.c0xmin = widen_lo(a[0]); nd.c0xmax = widen_hi(a[1]); nd.c0ymin = widen_lo(a[2]); nd.c0ymax = widen_hi(a[3]);
+    nd.c1xmin = widen_lo(b[0]); nd.c1xmax = widen_hi(b[1]); nd.c1ymin = widen_lo(b[2]); nd.c1ymax = widen_hi(b[3]);
+    nd.c0zmin = widen_lo(a[4]); nd.c0zmax = widen_hi(a[5]); nd.c1zmin = widen_lo(b[4]); nd.c1zmax = widen_hi(b[5]);
+    nd.child0 = L >= n - 1 ? ~(L - (n - 1)) : L;
+    nd.child1 = R >= n - 1 ? ~(R - (n - 1)) : R;
+    nd.pad0 = nd.pad1 = 0;
+    nodes[i] = nd;
+}
+
+// ------------------------------------------------------------------------------------------ host
+template <class T> static bool dalloc(T*& p, size_t count) {
+    SRT_CUDA(cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T)));
+    return true;
+}
+
+DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::vector<HostMaterial>& mats) {
+    if (cuda_device_count() == 0) { set_error("libsrt: no CUDA device available (the product has no CPU fallback)"); return nullptr; }
+    auto* s = new DeviceScene();
+    s->n = (uint32_t)tris.size();
+    s->n_mats = (uint32_t)mats.size();
+    const uint32_t n = s->n;
+    std::vector<float> verts(9ull * n);
+    std::vector<SrtTri> packed(n);
+    std::vector<SrtMaterial> dm(mats.size());
+    for (size_t m = 0; m < mats.size(); m++) {
+        memcpy(dm[m].spec, mats[m].spec, sizeof dm[m].spec);
+        dm[m].fuzz = mats[m].fuzz;
+        for (int k = 0; k < 3; k++) { dm[m].sellB[k] = mats[m].B[k]; dm[m].sellC[k] = mats[m].C[k]; }
+        dm[m].type = mats[m].type;
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        for (int k = 0; k < 3; k++) { verts[9ull * i + 3 * k] = tris[i].v[k].x; verts[9ull * i + 3 * k + 1] = tris[i].v[k].y; verts[9ull * i + 3 * k + 2] = tris[i].v[k].z; }
+        const uint32_t mt = tris[i].mat < mats.size() ? mats[tris[i].mat].type : SRT_LAMBERTIAN;
+        packed[i] = tris[i].pack(mt);
+    }
+    s->tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    bool ok = dalloc(s->verts, 9ull * n) && dalloc(s->tris_in, n) && dalloc(s->mats, mats.size()) && dalloc(s->leaf_boxes, 6ull * n) &&
+              dalloc(s->centroids, 3ull * n) && dalloc(s->scene_box, 6) && dalloc(s->codes, n) && dalloc(s->keys[0], n) && dalloc(s->keys[1], n) &&
+              dalloc(s->vals[0], n) && dalloc(s->vals[1], n) && dalloc(s->hist, SORT_PASSES * RADIX) &&
+              dalloc(s->lookback, (size_t)SORT_PASSES * (s->tiles ? s->tiles : 1) * RADIX) && dalloc(s->tile_counter, SORT_PASSES) &&
+              dalloc(s->left, n) && dalloc(s->right, n) && dalloc(s->parent, 2ull * n) && dalloc(s->node_boxes, 12ull * n) && dalloc(s->visit, n) &&
+              dalloc(s->nodes, n) && dalloc(s->tris, n);
+    for (auto& e : s->ev) ok = ok && cuda_ok(cudaEventCreate(&e), "cudaEventCreate", __FILE__, __LINE__);
+    if (ok && n) {
+        ok = cuda_ok(cudaMemcpy(s->verts, verts.data(), verts.size() * sizeof(float), cudaMemcpyHostToDevice), "upload verts", __FILE__, __LINE__) &&
+             cuda_ok(cudaMemcpy(s->tris_in, packed.data(), packed.size() * sizeof(SrtTri), cudaMemcpyHostToDevice), "upload tris", __FILE__, __LINE__);
+    }
+    if (ok && !mats.empty())
+        ok = cuda_ok(cudaMemcpy(s->mats, dm.data(), dm.size() * sizeof(SrtMaterial), cudaMemcpyHostToDevice), "upload mats", __FILE__, __LINE__);
+    float ms[5];
+    if (ok) ok = device_scene_build_lbvh(s, 1, ms);
+    if (!ok) { device_scene_destroy(s); return nullptr; }
+    return s;
+}
+
+void device_scene_destroy(DeviceScene* s) {
+    if (!s) return;
+    cudaFree(s->verts); cudaFree(s->tris_in); cudaFree(s->mats); cudaFree(s->leaf_boxes); cudaFree(s->centroids); cudaFree(s->scene_box);
+    cudaFree(s->codes); cudaFree(s->keys[0]); cudaFree(s->keys[1]); cudaFree(s->vals[0]); cudaFree(s->vals[1]); cudaFree(s->hist);
+    cudaFree(s->lookback); cudaFree(s->tile_counter); cudaFree(s->left); cudaFree(s->right); cudaFree(s->parent); cudaFree(s->node_boxes);
+    cudaFree(s->visit); cudaFree(s->nodes); cudaFree(s->tris);
+    for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    delete s;
+}
+
+static int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
+    const uint32_t n = s->n;
+    for (int k = 0; k < 5; k++) ms_out[k] = 0.f;
+    if (n == 0) return true;
+    const int sms = sm_count();
+    const int grid_stride = (int)min((uint32_t)(sms * 8), (n + 255) / 256);
+    const int grid_n = (int)((n + 255) / 256);
+    for (int rep = 0; rep < repeats; rep++) {
+        cudaStream_t st = s->stream;
+        SRT_CUDA(cudaEventRecord(s->ev[0], st));
+        k_init_scene_box<<<1, 32, 0, st>>>((uint32_t*)s->scene_box);
+        k_bounds<<<grid_stride, 256, 0, st>>>(s->verts, n, s->leaf_boxes, s->centroids, (uint32_t*)s->scene_box);
+        k_decode_scene_box<<<1, 32, 0, st>>>((uint32_t*)s->scene_box);
+        SRT_CUDA(cudaMemsetAsync(s->hist, 0, SORT_PASSES * RADIX * sizeof(uint32_t), st));
+        SRT_CUDA(cudaMemsetAsync(s->lookback, 0, (size_t)SORT_PASSES * s->tiles * RADIX * sizeof(uint32_t), st));
+        SRT_CUDA(cudaMemsetAsync(s->tile_counter, 0, SORT_PASSES * sizeof(uint32_t), st));
+        SRT_CUDA(cudaMemsetAsync(s->visit, 0, n * sizeof(uint32_t), st));
+        k_morton_hist<<<grid_stride, 256, 0, st>>>(s->centroids, s->scene_box, n, s->codes, s->keys[0], s->vals[0], s->hist);
+        SRT_CUDA(cudaEventRecord(s->ev[1], st));
+        k_scan_hist<<<1, RADIX, 0, st>>>(s->hist);
+        for (int p = 0; p < SORT_PASSES; p++) {
+            k_onesweep<<<s->tiles, SORT_THREADS, 0, st>>>(s->keys[p & 1], s->vals[p & 1], s->keys[(p + 1) & 1], s->vals[(p + 1) & 1], n, p * RADIX_BITS,
+                                                         s->hist + p * RADIX, s->lookback + (size_t)p * s->tiles * RADIX, s->tile_counter + p);
+        }
+        SRT_CUDA(cudaEventRecord(s->ev[2], st));
+        if (n > 1) k_hierarchy<<<grid_n, 256, 0, st>>>(s->keys[0], (int)n, s->left, s->right, s->parent);
+        else SRT_CUDA(cudaMemsetAsync(s->parent, 0xFF, sizeof(int32_t), st));
+        SRT_CUDA(cudaEventRecord(s->ev[3], st));
+        k_refit<<<grid_n, 256, 0, st>>>((int)n, s->vals[0], s->leaf_boxes, s->left, s->right, s->parent, s->node_boxes, s->visit);
+        k_emit<<<grid_n, 256, 0, st>>>((int)n, s->vals[0], s->left, s->right, s->node_boxes, s->tris_in, s->nodes, s->tris);
+        SRT_CUDA(cudaEventRecord(s->ev[4], st));
+        count_launch(6 + SORT_PASSES + (n > 1 ? 1 : 0) + 1);
+        SRT_CUDA_LAST();
+    }
+    SRT_CUDA(cudaEventSynchronize(s->ev[4]));
+    float t;
+    SRT_CUDA(cudaEventElapsedTime(&t, s->ev[0], s->ev[4])); ms_out[0] = t;
+    SRT_CUDA(cudaEventElapsedTime(&t, s->ev[0], s->ev[1])); ms_out[1] = t;
+    SRT_CUDA(cudaEventElapsedTime(&t, s->ev[1], s->ev[2])); ms_out[2] = t;
+    SRT_CUDA(cudaEventElapsedTime(&t, s->ev[2], s->ev[3])); ms_out[3] = t;
+    SRT_CUDA(cudaEventElapsedTime(&t, s->ev[3], s->ev[4])); ms_out[4] = t;
+    s->last_build_ms = ms_out[0];
+    return true;
+}
+double device_scene_lbvh_ms(const DeviceScene* s) { return s->last_build_ms; }
+
+bool device_scene_download_lbvh(const DeviceScene* s, LbvhDump& o) {
+    const uint32_t n = s->n;
+    o.codes.resize(n); o.sorted_idx.resize(n); o.left.resize(n > 0 ? n - 1 : 0); o.right.resize(n > 0 ? n - 1 : 0);
+    o.parent.resize(n ? 2 * n - 1 : 0); o.node_boxes.resize(n ? 6ull * (2 * n - 1) : 0);
+    if (!n) return true;
+    SRT_CUDA(cudaMemcpy(o.codes.data(), s->codes, n * 4, cudaMemcpyDeviceToHost));
+    SRT_CUDA(cudaMemcpy(o.sorted_idx.data(), s->vals[0], n * 4, cudaMemcpyDeviceToHost));
+    if (n > 1) {
+        SRT_CUDA(cudaMemcpy(o.left.data(), s->left, (n - 1) * 4, cudaMemcpyDeviceToHost));
+        SRT_CUDA(cudaMemcpy(o.right.data(), s->right, (n - 1) * 4, cudaMemcpyDeviceToHost));
+    }
+    SRT_CUDA(cudaMemcpy(o.parent.data(), s->parent, (2 * n - 1) * 4, cudaMemcpyDeviceToHost));
+    SRT_CUDA(cudaMemcpy(o.node_boxes.data(), s->node_boxes, 6ull * (2 * n - 1) * 4, cudaMemcpyDeviceToHost));
+    SRT_CUDA(cudaMemcpy(o.scene_box, s->scene_box, 24, cudaMemcpyDeviceToHost));
+    return true;
+}
+
+// accessors for the renderer translation units
+const SrtNode* device_scene_nodes(const DeviceScene* s) { return s->nodes; }
+const SrtTri* device_scene_tris(const DeviceScene* s) { return s->tris; }
+const SrtMaterial* device_scene_mats(const DeviceScene* s) { return s->mats; }
+uint32_t device_scene_ntris(const DeviceScene* s) { return s->n; }
+uint32_t device_scene_nmats(const DeviceScene* s) { return s->n_mats; }
+const uint32_t* device_scene_sorted_idx(const DeviceScene* s) { return s->vals[0]; }
+
+}  // namespace srt

@@ -1,0 +1,66 @@
+// Kernel parameter block and the per-FP-mode launch table of the path tracer.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include "../common/srt_types.h"
+
+#define SRT_BLOCK 256
+
+namespace srt {
+
+struct WaveParams {
+    // scene (global memory; small scenes are staged into shared memory by every block)
+    const SrtNode* nodes;
+    const SrtTri* tris;  // leaf order
+    const SrtMaterial* mats;
+    const float* cie;    // x[95] y[95] z[95]
+    const float* bg;     // background spectrum [95]
+    int n_tris, n_mats, bg_is_zero;
+    // camera and chunk geometry
+    SrtCamera cam;
+    uint32_t off_x, off_y, cw, ch;   // current chunk (pixels)
+    uint32_t img_w, img_h;
+    uint32_t slot_w, nslots;         // slot = cj * slot_w + ci over the NOMINAL chunk size
+    uint32_t ref_grid_x;             // nominal_chunk_w / 28 + 1 (reference launch geometry -> seeds)
+    uint32_t spp, bounce_limit;
+    int regen_loop;
+    uint32_t tile_w, tile_h, tiles_x, rank, world;
+    // per-slot path state, 16-byte vectors
+    float4* R0;    // hit point xyz | triangle (leaf order)
+    float4* R1;    // incoming direction xyz | valid[2:0] + bounce
+    float4* P0;    // power 0..3
+    float4* P1;    // power 4..6 | hero wavelength
+    uint4* G0;     // XORWOW d v0 v1 v2
+    uint2* G1;     // XORWOW v3 v4
+    uint32_t* sidx;  // samples started
+    float* acc;      // film: XYZ sums, 3 planes of `plane` floats, full-image raster
+    size_t plane;
+    // queues (ping-pong): regenerate queue + 3 material segments of capacity nslots each
+    const uint32_t* qr_in;
+    const uint32_t* qm_in;
+    uint32_t* qr_out;
+    uint32_t* qm_out;
+    const uint32_t* cnt_in;  // [0] regen, [1] lambertian, [2] metallic, [3] dielectric
+    uint32_t* cnt_out;
+    unsigned long long* ray_counter;
+};
+
+struct LaunchTable {
+    size_t (*smem_bytes)(const WaveParams&);
+    cudaError_t (*configure)(size_t smem_bytes);
+    void (*init_slots)(const WaveParams&, cudaStream_t);
+    void (*begin_chunk)(const WaveParams&, cudaStream_t);
+    void (*generate)(const WaveParams&, int grid, size_t smem, cudaStream_t);
+    void (*shade)(const WaveParams&, int grid, size_t smem, cudaStream_t);
+    void (*megakernel)(const WaveParams&, int grid, size_t smem, cudaStream_t);
+    void (*resolve)(const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, float* rgb,
+                    float* xyz, cudaStream_t);
+    void (*trace_rays)(const WaveParams&, uint32_t n, const float* o, const float* d, const uint32_t* sorted_idx, float* t_out, int32_t* tri_out,
+                       int grid, cudaStream_t);
+};
+
+namespace fastfp { LaunchTable make_launch_table(); }
+namespace strictfp_ { LaunchTable make_launch_table(); }
+
+}  // namespace srt

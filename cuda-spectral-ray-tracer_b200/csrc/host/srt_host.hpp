@@ -1,0 +1,211 @@
+// Host side of libsrt.so: the mirror of the reference's L3-L5 objects (params, camera_builder,
+// scene_manager, render_manager) re-designed around flat arrays that upload in one copy.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <memory>
+#include <string>
+#include <vector>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+
+#include "../common/srt_types.h"
+#include "../../../include/srt.h"
+
+namespace srt {
+
+void set_error(const std::string& msg);
+const std::string& last_error();
+
+struct vec3f {
+    float x = 0, y = 0, z = 0;
+    vec3f() = default;
+    vec3f(float a, float b, float c) : x(a), y(b), z(c) {}
+    float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+};
+
+// ---------------------------------------------------------------- params (io/params.h)
+struct Params {
+    std::string image_title, log_subdir;
+    unsigned scene = 0, xres = 600, yres = 600;
+    float ar = 1.0f;
+    unsigned xcsize = 0, ycsize = 0, n_samples = 500, bounce_limit = 10;
+    bool do_log = false, show_render = true, do_save = false;
+    mutable std::string title_cache;
+
+    Params() { reset_yres(); }
+    void reset_yres();
+    unsigned get_xcsize() const;
+    unsigned get_ycsize() const;
+    const std::string& get_title() const;
+    void parse(int argc, char** argv);
+    static Params& instance();
+    static void reset_instance();
+};
+
+// ---------------------------------------------------------------- camera
+struct CameraBuilder {
+    float vfov = 90.0f;
+    vec3f lookfrom{0, 0, -1}, lookat{0, 0, 0}, vup{0, 1, 0};
+    float defocus_angle = 0, focus_dist = 10;
+    vec3f background{0, 0, 0};
+    srt_camera build(uint32_t w, uint32_t h) const;
+};
+
+// ---------------------------------------------------------------- geometry (host build, bit-faithful)
+enum AAPlane : int { AA_NONE = 0, AA_XY = 1, AA_YZ = 2, AA_XZ = 3 };
+struct HostTri {
+    vec3f v[3];
+    vec3f normal;
+    float D = 0;
+    int clockwise = 0;
+    int aa_plane = AA_NONE;
+    uint32_t mat = 0;
+    float bbox[6] = {0, 0, 0, 0, 0, 0};
+    void derive();  // normal, plane constant, winding, projection plane, padded box
+    SrtTri pack(uint32_t mat_type) const;
+};
+struct HostMaterial {
+    uint32_t type = SRT_LAMBERTIAN;
+    vec3f color;
+    float fuzz = 1.0f, power = 0.0f;
+    float B[3] = {0, 0, 0}, C[3] = {0, 0, 0};
+    float spec[SRT_NS];
+    void bake_spectrum();
+    static HostMaterial from_desc(const srt_material_desc& d, bool ref_compat);
+};
+
+class TriangleSoup {  // growing triangle list with the reference's composite builders
+public:
+    std::vector<HostTri> tris;
+    size_t add_tri(vec3f a, vec3f b, vec3f c, uint32_t mat, bool as_vectors);
+    size_t add_quad(vec3f Q, vec3f u, vec3f v, uint32_t mat);
+    size_t add_box(vec3f a, vec3f b, const uint32_t mats[6]);
+    size_t add_pyramid(vec3f Q, vec3f u, vec3f v, vec3f w, uint32_t mat);
+    size_t add_prism(vec3f Q, vec3f u, vec3f v, vec3f w, uint32_t mat);
+    vec3f quad_center(size_t first) const;
+    vec3f box_center(size_t first) const;
+    vec3f prism_centroid(size_t first) const;
+    void rotate_y_about(size_t first, size_t count, vec3f pivot, float theta);
+    void translate(size_t first, size_t count, vec3f d, bool rederive);
+    void rederive(size_t first, size_t count);
+};
+
+struct SceneDescription {
+    std::vector<HostTri> tris;
+    std::vector<HostMaterial> mats;
+    CameraBuilder camera;
+};
+SceneDescription make_reference_scene(unsigned scene_id, bool ref_compat);
+SceneDescription make_soup_scene(uint32_t n, uint64_t seed);
+bool load_obj(const char* path, std::vector<float>& verts9);
+
+// sRGB -> sigmoid-polynomial coefficients, computed on demand (replaces the 9.4 MB table)
+namespace rgb2spec {
+float scale(int k);                                          // Scale[k], res 64
+bool cell(int l, int k, int j, int i, float out[3]);         // Data[l][k][j][i][0..2], cached
+void coeffs_nearest(vec3f rgb, float out_c[3]);              // device-path lookup (nearest cell)
+void coeffs_trilinear(vec3f rgb, float out_c[3]);            // host-path lookup (background)
+}  // namespace rgb2spec
+const float* cie_table(int which);  // 0 x, 1 y, 2 z, 3 normalised D65 (95 floats each)
+float spectrum_interp_host(const float* table95, float lambda);
+void background_spectrum(vec3f rgb, float out95[SRT_NS]);
+
+// ---------------------------------------------------------------- device objects (defined in cuda/*.cu)
+struct DeviceScene;     // triangles, materials, LBVH
+struct DeviceRenderer;  // per-pixel state, queues, film
+
+struct LbvhDump {
+    std::vector<uint32_t> codes, sorted_idx;
+    std::vector<int32_t> left, right, parent;
+    std::vector<float> node_boxes;
+    float scene_box[6];
+};
+
+DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::vector<HostMaterial>& mats);
+void device_scene_destroy(DeviceScene*);
+bool device_scene_build_lbvh(DeviceScene*, int repeats, float ms_out[5]);
+bool device_scene_download_lbvh(const DeviceScene*, LbvhDump& out);
+bool device_scene_trace(const DeviceScene*, uint32_t n, const float* o, const float* d, float* t, int32_t* tri, float* ms);
+double device_scene_lbvh_ms(const DeviceScene*);
+
+struct RenderConfig {
+    srt_camera cam;
+    unsigned spp = 1, bounce_limit = 10;
+    unsigned chunk_w = 0, chunk_h = 0;   // nominal chunk geometry (seeds depend on it, reference Q15)
+    int fp_strict = 0, pipeline = 0, regen_loop = 4;
+    int tile_w = 32, tile_h = 32, rank = 0, world = 1;
+    float bg_spectrum[SRT_NS];
+    int bg_is_zero = 1;
+};
+DeviceRenderer* device_renderer_create(const DeviceScene*, const RenderConfig&);
+void device_renderer_destroy(DeviceRenderer*);
+// renders one chunk (offset/size in pixels) into the device film (XYZ sums, full-image raster)
+bool device_renderer_render_chunk(DeviceRenderer*, unsigned off_x, unsigned off_y, unsigned w, unsigned h);
+// tonemaps film region -> host planes (pinned staging inside); any pointer may be null
+bool device_renderer_resolve(DeviceRenderer*, unsigned off_x, unsigned off_y, unsigned w, unsigned h, float* r, float* g,
+                             float* b, float* xyz, unsigned img_w, unsigned img_h);
+float* device_renderer_film(DeviceRenderer*);
+void device_renderer_stats(const DeviceRenderer*, srt_stats* s);
+
+uint64_t kernel_launches();
+bool cuda_select_device(int dev);
+int cuda_device_count();
+
+// ---------------------------------------------------------------- scene + render manager
+struct Scene {
+    SceneDescription desc;
+    DeviceScene* dev = nullptr;
+    bool ok = false;
+    std::string msg;
+    ~Scene();
+};
+
+class RenderManager {  // rendering/render_manager.cuh:37-225
+public:
+    RenderManager(Scene* scene, const srt_camera& cam, float* r, float* g, float* b);
+    ~RenderManager();
+    int init_renderer(unsigned bounce_limit, unsigned spp);
+    int init_device_params(unsigned cw, unsigned ch);
+    bool ready() const { return device_inited_ && i_ < n_iterations_; }
+    bool done() const { return done_; }
+    int step();
+    int update_fb();
+    int render_cycle();
+    int end_render();
+    int set_option(int opt, int value);
+    int get_xyz(float* xyz);
+    float* device_film();
+    int resolve_film();
+    int stats(srt_stats* s) const;
+    unsigned width() const { return cam_.width; }
+    unsigned height() const { return cam_.height; }
+
+private:
+    struct Slot {  // render_step_data (render_manager.cuh:9-35) without host staging copies
+        unsigned off_x = 0, off_y = 0, w = 0, h = 0;
+        bool is_last = false;
+        bool full = false;
+    };
+    Scene* scene_;
+    srt_camera cam_;
+    float *fb_r_, *fb_g_, *fb_b_;
+    std::vector<float> xyz_;
+    bool scene_inited_ = false, renderer_inited_ = false, device_inited_ = false, done_ = true;
+    RenderConfig cfg_;
+    DeviceRenderer* dev_ = nullptr;
+    unsigned i_ = 0, n_iterations_ = 0, x_chunks_ = 0, chunk_w_ = 0, chunk_h_ = 0, off_x_ = 0, off_y_ = 0;
+    Slot slots_[2];
+    size_t next_write_ = 0, next_read_ = 0;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::thread worker_;
+    bool worker_started_ = false;
+    int worker_rc_ = 0;
+};
+
+bool write_ppm(const char* path, const float* r, const float* g, const float* b, uint32_t w, uint32_t h);
+bool write_bmp(const char* path, const float* r, const float* g, const float* b, uint32_t w, uint32_t h);
+
+}  // namespace srt

@@ -1,0 +1,341 @@
+"""ctypes binding of libsrt.so (include/srt.h) -- used by tests/, bench.py and __graft_entry__.py.
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible when a
+scene is created, this raises.  The Python classes mirror the reference's objects one to one
+(param_manager, camera_builder, scene_manager, render_manager, frame_buffer)."""
+import ctypes as C
+import os
+import pathlib
+
+import numpy as np
+
+PKG_DIR = pathlib.Path(__file__).resolve().parents[1]
+LIB_PATH = PKG_DIR / "libsrt.so"
+
+
+class SrtError(RuntimeError):
+    pass
+
+
+class Vec3(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("pixel_delta_u", Vec3), ("pixel_delta_v", Vec3),
+                ("pixel00_loc", Vec3), ("defocus_angle", C.c_float), ("camera_center", Vec3), ("defocus_disk_u", Vec3),
+                ("defocus_disk_v", Vec3), ("background", Vec3)]
+
+    def as_array(self):
+        v = lambda a: [a.x, a.y, a.z]
+        return np.array([self.width, self.height] + v(self.pixel_delta_u) + v(self.pixel_delta_v) + v(self.pixel00_loc)
+                        + [self.defocus_angle] + v(self.camera_center) + v(self.defocus_disk_u) + v(self.defocus_disk_v), np.float32)
+
+
+class MaterialDesc(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("color", C.c_float * 3), ("fuzz", C.c_float), ("emission_power", C.c_float),
+                ("sellmeier_b", C.c_float * 3), ("sellmeier_c", C.c_float * 3)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("wavefront_iterations", C.c_uint64), ("render_ms", C.c_double), ("lbvh_ms", C.c_double)]
+
+
+OPT_FP_MODE, OPT_PIPELINE, OPT_TILE_W, OPT_TILE_H, OPT_RANK, OPT_WORLD, OPT_REGEN_LOOP = 1, 2, 3, 4, 5, 6, 7
+MAT_LAMBERTIAN, MAT_METALLIC, MAT_DIELECTRIC, MAT_EMISSIVE = 0, 1, 2, 4
+
+# every symbol include/srt.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+_SIGS = [
+    ("srt_last_error", C.c_char_p, []),
+    ("srt_kernel_launch_count", C.c_uint64, []),
+    ("srt_device_count", C.c_int, []),
+    ("srt_set_device", C.c_int, [C.c_int]),
+    ("srt_params_instance", _P, []),
+    ("srt_params_reset", None, []),
+    ("srt_params_parse", None, [_P, C.c_int, C.POINTER(C.c_char_p)]),
+    ("srt_params_scene_id", C.c_uint, [_P]), ("srt_params_xres", C.c_uint, [_P]), ("srt_params_yres", C.c_uint, [_P]),
+    ("srt_params_ar", C.c_float, [_P]), ("srt_params_xcsize", C.c_uint, [_P]), ("srt_params_ycsize", C.c_uint, [_P]),
+    ("srt_params_nsamples", C.c_uint, [_P]), ("srt_params_bounce_limit", C.c_uint, [_P]),
+    ("srt_params_log_active", C.c_int, [_P]), ("srt_params_do_save", C.c_int, [_P]), ("srt_params_show_render", C.c_int, [_P]),
+    ("srt_params_img_title", C.c_char_p, [_P]), ("srt_params_log_subdir", C.c_char_p, [_P]),
+    ("srt_camera_builder_create", _P, []), ("srt_camera_builder_destroy", None, [_P]),
+    ("srt_camera_builder_set_vfov", None, [_P, C.c_float]),
+    ("srt_camera_builder_set_lookfrom", None, [_P, C.c_float, C.c_float, C.c_float]),
+    ("srt_camera_builder_set_lookat", None, [_P, C.c_float, C.c_float, C.c_float]),
+    ("srt_camera_builder_set_vup", None, [_P, C.c_float, C.c_float, C.c_float]),
+    ("srt_camera_builder_set_defocus_angle", None, [_P, C.c_float]),
+    ("srt_camera_builder_set_focus_dist", None, [_P, C.c_float]),
+    ("srt_camera_builder_set_background", None, [_P, C.c_float, C.c_float, C.c_float]),
+    ("srt_camera_builder_get_camera", C.c_int, [_P, C.POINTER(Camera)]),
+    ("srt_camera_builder_get_camera_res", C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(Camera)]),
+    ("srt_scene_create", _P, [C.c_uint]),
+    ("srt_scene_create_soup", _P, [C.c_uint32, C.c_uint64]),
+    ("srt_scene_create_mesh", _P, [_P, _P, C.c_uint32, C.POINTER(MaterialDesc), C.c_uint32]),
+    ("srt_scene_create_obj", _P, [C.c_char_p, C.POINTER(MaterialDesc), C.c_uint32]),
+    ("srt_scene_destroy", None, [_P]),
+    ("srt_scene_result", C.c_int, [_P, C.POINTER(C.c_char_p)]),
+    ("srt_scene_camera", C.c_int, [_P, C.POINTER(Camera)]),
+    ("srt_scene_camera_res", C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(Camera)]),
+    ("srt_scene_num_tris", C.c_uint32, [_P]), ("srt_scene_num_materials", C.c_uint32, [_P]),
+    ("srt_set_ref_compat", None, [C.c_int]),
+    ("srt_scene_get_tris", C.c_int, [_P, _P, _P]), ("srt_scene_get_materials", C.c_int, [_P, _P, _P]),
+    ("srt_scene_get_lbvh", C.c_int, [_P] * 8),
+    ("srt_scene_rebuild_lbvh", C.c_int, [_P, C.c_int, _P]),
+    ("srt_scene_trace_rays", C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, _P]),
+    ("srt_render_manager_create", _P, [_P, C.POINTER(Camera), _P, _P, _P]),
+    ("srt_render_manager_destroy", None, [_P]),
+    ("srt_rm_init_renderer", C.c_int, [_P, C.c_uint, C.c_uint]),
+    ("srt_rm_init_device_params", C.c_int, [_P, C.c_uint, C.c_uint]),
+    ("srt_rm_is_ready_to_render", C.c_int, [_P]), ("srt_rm_is_done", C.c_int, [_P]),
+    ("srt_rm_im_width", C.c_uint, [_P]), ("srt_rm_im_height", C.c_uint, [_P]),
+    ("srt_rm_step", C.c_int, [_P]), ("srt_rm_update_fb", C.c_int, [_P]),
+    ("srt_rm_render_cycle", C.c_int, [_P]), ("srt_rm_end_render", C.c_int, [_P]), ("srt_rm_render_all", C.c_int, [_P]),
+    ("srt_rm_set_option", C.c_int, [_P, C.c_int, C.c_int]),
+    ("srt_rm_get_xyz", C.c_int, [_P, _P]),
+    ("srt_rm_device_film", _P, [_P]),
+    ("srt_rm_resolve_film", C.c_int, [_P]),
+    ("srt_rm_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
+    ("srt_write_ppm", C.c_int, [C.c_char_p, _P, _P, _P, C.c_uint32, C.c_uint32]),
+    ("srt_write_bmp", C.c_int, [C.c_char_p, _P, _P, _P, C.c_uint32, C.c_uint32]),
+]
+SYMBOLS = [s[0] for s in _SIGS]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise SrtError("libsrt.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        L = C.CDLL(str(LIB_PATH))
+        for name, res, args in _SIGS:
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise SrtError(lib().srt_last_error().decode() or ("srt error %d" % rc))
+
+
+def kernel_launch_count():
+    return int(lib().srt_kernel_launch_count())
+
+
+class Params:
+    """param_manager singleton (reference io/params.h:226-315)."""
+
+    def __init__(self, *argv, reset=True):
+        L = lib()
+        if reset:
+            L.srt_params_reset()
+        self.h = L.srt_params_instance()
+        if argv:
+            self.parse(*argv)
+
+    def parse(self, *argv):
+        args = [b"srt"] + [str(a).encode() for a in argv]
+        arr = (C.c_char_p * len(args))(*args)
+        lib().srt_params_parse(self.h, len(args), arr)
+
+    def __getattr__(self, name):
+        f = getattr(lib(), "srt_params_" + name)
+        v = f(self.h)
+        return v.decode() if isinstance(v, bytes) else v
+
+
+class CameraBuilder:
+    """camera_builder (reference rendering/camera_builder.cuh)."""
+
+    def __init__(self):
+        self.h = lib().srt_camera_builder_create()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().srt_camera_builder_destroy(self.h)
+            self.h = None
+
+    def _set(self, name, *v):
+        getattr(lib(), "srt_camera_builder_set_" + name)(self.h, *v)
+        return self
+
+    def setVfov(self, v): return self._set("vfov", v)
+    def setLookfrom(self, x, y, z): return self._set("lookfrom", x, y, z)
+    def setLookat(self, x, y, z): return self._set("lookat", x, y, z)
+    def setVup(self, x, y, z): return self._set("vup", x, y, z)
+    def setDefocusAngle(self, v): return self._set("defocus_angle", v)
+    def setFocusDist(self, v): return self._set("focus_dist", v)
+    def setBackground(self, r, g, b): return self._set("background", r, g, b)
+
+    def getCamera(self, w=None, h=None):
+        cam = Camera()
+        if w is None:
+            _check(lib().srt_camera_builder_get_camera(self.h, C.byref(cam)))
+        else:
+            _check(lib().srt_camera_builder_get_camera_res(self.h, w, h, C.byref(cam)))
+        return cam
+
+
+class Scene:
+    """scene_manager (reference scene/scene.cuh:103-176): builds triangles, materials and the device LBVH."""
+
+    def __init__(self, scene_id=None, soup=None, seed=1984, mesh=None, obj=None, host_only=False):
+        """host_only=True keeps a scene whose device upload failed (no GPU): only the host-side
+        dumps (tris(), materials(), camera()) work on it; rendering raises."""
+        L = lib()
+        if soup is not None:
+            self.h = L.srt_scene_create_soup(soup, seed)
+        elif mesh is not None:
+            verts, mat_idx, mats = mesh
+            verts = np.ascontiguousarray(verts, np.float32)
+            mat_idx = np.ascontiguousarray(mat_idx, np.uint32)
+            arr = (MaterialDesc * len(mats))(*mats)
+            self.h = L.srt_scene_create_mesh(verts.ctypes.data, mat_idx.ctypes.data, len(mat_idx), arr, len(mats))
+        elif obj is not None:
+            path, mats = obj
+            arr = (MaterialDesc * len(mats))(*mats)
+            self.h = L.srt_scene_create_obj(str(path).encode(), arr, len(mats))
+        else:
+            self.h = L.srt_scene_create(scene_id)
+        if not self.h:
+            raise SrtError(L.srt_last_error().decode())
+        msg = C.c_char_p()
+        self.ok = bool(L.srt_scene_result(self.h, C.byref(msg)))
+        self.msg = (msg.value or b"").decode()
+        if not self.ok and not host_only:
+            raise SrtError(self.msg)
+        self.ntris = L.srt_scene_num_tris(self.h)
+        self.nmats = L.srt_scene_num_materials(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().srt_scene_destroy(self.h)
+            self.h = None
+
+    def camera(self, w=None, h=None):
+        cam = Camera()
+        if w is None:
+            _check(lib().srt_scene_camera(self.h, C.byref(cam)))
+        else:
+            _check(lib().srt_scene_camera_res(self.h, w, h, C.byref(cam)))
+        return cam
+
+    def tris(self):
+        f = np.zeros((self.ntris, 22), np.float32); iv = np.zeros((self.ntris, 3), np.int32)
+        _check(lib().srt_scene_get_tris(self.h, f.ctypes.data, iv.ctypes.data))
+        return f, iv
+
+    def materials(self):
+        f = np.zeros((self.nmats, 108), np.float32); iv = np.zeros(self.nmats, np.int32)
+        _check(lib().srt_scene_get_materials(self.h, f.ctypes.data, iv.ctypes.data))
+        return f, iv
+
+    def lbvh(self):
+        n = self.ntris
+        d = dict(scene_box=np.zeros(6, np.float32), codes=np.zeros(n, np.uint32), sorted_idx=np.zeros(n, np.uint32),
+                 left=np.zeros(max(n - 1, 1), np.int32), right=np.zeros(max(n - 1, 1), np.int32),
+                 parent=np.zeros(max(2 * n - 1, 1), np.int32), node_boxes=np.zeros((max(2 * n - 1, 1), 6), np.float32))
+        _check(lib().srt_scene_get_lbvh(self.h, d["codes"].ctypes.data, d["sorted_idx"].ctypes.data, d["left"].ctypes.data,
+                                        d["right"].ctypes.data, d["parent"].ctypes.data, d["node_boxes"].ctypes.data,
+                                        d["scene_box"].ctypes.data))
+        d["left"] = d["left"][:max(n - 1, 0)]; d["right"] = d["right"][:max(n - 1, 0)]
+        return d
+
+    def rebuild_lbvh(self, repeats=1):
+        ms = np.zeros(5, np.float32)
+        _check(lib().srt_scene_rebuild_lbvh(self.h, repeats, ms.ctypes.data))
+        return dict(total=float(ms[0]), bounds_morton=float(ms[1]), sort=float(ms[2]), hierarchy=float(ms[3]), refit_emit=float(ms[4]))
+
+    def trace_rays(self, o, d):
+        o = np.ascontiguousarray(o, np.float32); d = np.ascontiguousarray(d, np.float32)
+        n = o.shape[0]
+        t = np.zeros(n, np.float32); tri = np.zeros(n, np.int32); ms = C.c_float(0)
+        _check(lib().srt_scene_trace_rays(self.h, n, o.ctypes.data, d.ctypes.data, t.ctypes.data, tri.ctypes.data, C.byref(ms)))
+        return t, tri, ms.value
+
+
+class FrameBuffer:
+    """frame_buffer (reference rendering/frame_buffer.cuh): planar float32 R, G, B, raster order, 0..255."""
+
+    def __init__(self, w, h):
+        self.w, self.h = w, h
+        self.r = np.zeros(w * h, np.float32); self.g = np.zeros(w * h, np.float32); self.b = np.zeros(w * h, np.float32)
+
+    def rgb(self):
+        return np.stack([self.r, self.g, self.b]).reshape(3, self.h, self.w)
+
+
+class RenderManager:
+    """render_manager (reference rendering/render_manager.cuh:37-173)."""
+
+    def __init__(self, scene, cam, fb):
+        self.scene, self.cam, self.fb = scene, cam, fb  # borrowed, keep alive
+        self.h = lib().srt_render_manager_create(scene.h, C.byref(cam), fb.r.ctypes.data, fb.g.ctypes.data, fb.b.ctypes.data)
+        if not self.h:
+            raise SrtError(lib().srt_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().srt_render_manager_destroy(self.h)
+            self.h = None
+
+    def init_renderer(self, bounce_limit, spp): _check(lib().srt_rm_init_renderer(self.h, bounce_limit, spp))
+    def init_device_params(self, cw=0, ch=0): _check(lib().srt_rm_init_device_params(self.h, cw, ch))
+    def set_option(self, opt, value): _check(lib().srt_rm_set_option(self.h, opt, value))
+    def isReadyToRender(self): return bool(lib().srt_rm_is_ready_to_render(self.h))
+    def isDone(self): return bool(lib().srt_rm_is_done(self.h))
+    def getImWidth(self): return lib().srt_rm_im_width(self.h)
+    def getImHeight(self): return lib().srt_rm_im_height(self.h)
+
+    def step(self):
+        rc = lib().srt_rm_step(self.h)
+        if rc < 0:
+            raise SrtError(lib().srt_last_error().decode())
+        return bool(rc)
+
+    def update_fb(self):
+        rc = lib().srt_rm_update_fb(self.h)
+        if rc < 0:
+            raise SrtError(lib().srt_last_error().decode())
+        return bool(rc)
+
+    def render_cycle(self): _check(lib().srt_rm_render_cycle(self.h))
+    def end_render(self): _check(lib().srt_rm_end_render(self.h))
+    def render_all(self): _check(lib().srt_rm_render_all(self.h))
+    def device_film(self): return lib().srt_rm_device_film(self.h)
+    def resolve_film(self): _check(lib().srt_rm_resolve_film(self.h))
+
+    def xyz(self):
+        out = np.zeros(3 * self.cam.width * self.cam.height, np.float32)
+        _check(lib().srt_rm_get_xyz(self.h, out.ctypes.data))
+        return out.reshape(3, self.cam.height, self.cam.width)
+
+    def stats(self):
+        s = Stats()
+        _check(lib().srt_rm_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=False, pipeline=0, scene=None, tiles=None, regen_loop=None):
+    """One-call helper: returns (rgb[3,h,w] float32 0..255, xyz[3,h,w] float32, stats dict)."""
+    sc = scene if scene is not None else Scene(scene_id)
+    cam = sc.camera(w, h)
+    fb = FrameBuffer(w, h)
+    rm = RenderManager(sc, cam, fb)
+    rm.init_renderer(bounce, spp)
+    rm.set_option(OPT_FP_MODE, 1 if strict else 0)
+    rm.set_option(OPT_PIPELINE, pipeline)
+    if regen_loop is not None:
+        rm.set_option(OPT_REGEN_LOOP, regen_loop)
+    if tiles is not None:
+        tw, th, rank, world = tiles
+        rm.set_option(OPT_TILE_W, tw); rm.set_option(OPT_TILE_H, th); rm.set_option(OPT_RANK, rank); rm.set_option(OPT_WORLD, world)
+    rm.init_device_params(*chunk)
+    rm.render_all()
+    return fb.rgb().copy(), rm.xyz(), rm.stats()

@@ -778,14 +778,14 @@ oscene* srt_oracle_scene_soup(int n, uint64_t seed) {
     s->mats[1] = mat_emissive(V(1.f, 1.f, 1.f), 5.f);
     float sz = 555.0f * powf((float)n, -1.0f / 3.0f);
     uint64_t st = seed;
-    int nsoup = n >= 2 ? n - 2 : 0;
+    int nsoup = n >= 3 ? n - 2 : n; /* tiny soups: no light quad */
     for (int i = 0; i < nsoup; i++) {
         float c[3], p[9];
         for (int k = 0; k < 3; k++) c[k] = sm_uniform(&st) * 555.0f;
         for (int k = 0; k < 9; k++) p[k] = c[k % 3] + (sm_uniform(&st) * 2.0f - 1.0f) * sz;
         s->tris[i] = tri_new(V(p[0], p[1], p[2]), V(p[3], p[4], p[5]), V(p[6], p[7], p[8]), 0, 0);
     }
-    if (n >= 2) {
+    if (n >= 3) {
         ov3 center = V(555.f / 2.f, 554.f, 555.f / 2.f);
         quad_new(s->tris + nsoup, V(center.x + 50.f, center.y, center.z + 50.f), V(-100.f, 0, 0), V(0, 0, -100.f), 1);
     }
