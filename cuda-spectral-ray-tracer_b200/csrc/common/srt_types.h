@@ -31,6 +31,17 @@ struct alignas(16) SrtTri {
 #define SRT_TRI_HAX(bits) (((bits) >> 19) & 3u)
 #define SRT_TRI_MTYPE(bits) (((bits) >> 21) & 7u)
 
+// ---- conservative pre-test record, 64 B = 4 x 16-B vectors (leaf order, same index as SrtTri) ----
+// q0 = plane (nx, ny, nz, D); q1 = (A.xyz, a_w), q2 = (B.xyz, b_w): barycentrics u = A.p + a_w, v = B.p + b_w
+// q3 = (eps0, eps1, tol0, tol1): slack on u,v = eps0 + eps1*|o|_1, slack on the plane distance = tol0 + tol1*|o|_1
+struct alignas(16) SrtTriFast {
+    float nx, ny, nz, D;
+    float ax, ay, az, aw;
+    float bx, by, bz, bw;
+    float eps0, eps1, tol0, tol1;
+};
+#define SRT_FLAT_MAX_TRIS 64  // scenes up to this size are one wide leaf: no tree walk at all
+
 // ---- device BVH node, 64 B = 4 x 16-B vectors (both child boxes in the parent) -----------
 // q0 = (c0.xmin, c0.xmax, c0.ymin, c0.ymax)   q1 = (c1.xmin, c1.xmax, c1.ymin, c1.ymax)
 // q2 = (c0.zmin, c0.zmax, c1.zmin, c1.zmax)   q3 = (child0, child1, -, -)

@@ -1,0 +1,68 @@
+// Device micro-benchmarks that give the roofline denominators this library reports against:
+// FP32 FMA issue peak (the render kernels are instruction bound) and a plain
+// device-to-device copy (cross-check of MEASURED_PEAKS.json's HBM figure).
+#include "cuda_common.cuh"
+
+namespace srt {
+
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+double measure_fp32_tflops() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, iters = 4096;
+    float* d = nullptr;
+    if (cudaMalloc(&d, (size_t)blocks * 256 * sizeof(float)) != cudaSuccess) return 0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(e0);
+        k_fma_peak<<<blocks, 256>>>(d, iters, 0.999f, 0.001f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        count_launch();
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * iters * (double)blocks * 256;
+        if (rep > 0 && ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return best;
+}
+
+double measure_copy_gbs(uint32_t mbytes) {
+    const size_t bytes = (size_t)mbytes << 20;
+    char *a = nullptr, *b = nullptr;
+    if (cudaMalloc(&a, bytes) != cudaSuccess || cudaMalloc(&b, bytes) != cudaSuccess) { cudaFree(a); return 0; }
+    cudaMemset(a, 1, bytes);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(e0);
+        cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms > 0) best = std::max(best, 2.0 * bytes / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(a); cudaFree(b);
+    return best;
+}
+
+}  // namespace srt

@@ -11,6 +11,7 @@ namespace srt {
 
 const SrtNode* device_scene_nodes(const DeviceScene* s);
 const SrtTri* device_scene_tris(const DeviceScene* s);
+const SrtTriFast* device_scene_fast(const DeviceScene* s);
 const SrtMaterial* device_scene_mats(const DeviceScene* s);
 uint32_t device_scene_ntris(const DeviceScene* s);
 uint32_t device_scene_nmats(const DeviceScene* s);
@@ -36,34 +37,65 @@ struct DeviceRenderer {
     RenderConfig cfg;
     WaveParams P{};
     size_t smem = 0;
-    int grid = 0;
+    int grid = 0, mode = 0;  // 0 global LBVH, 1 shared-memory LBVH, 2 shared-memory wide leaf
     // owned device memory
     float* d_cie = nullptr;
     float* d_bg = nullptr;
-    uint32_t* d_queues = nullptr;   // 2 x (regen[nslots] + 3*nslots)
-    uint32_t* d_counters = nullptr; // 2 x 4
     unsigned long long* d_rays = nullptr;
     float* d_rgb = nullptr;         // resolve staging (device), 3 planes of max chunk
     float* d_xyz = nullptr;
     float* h_stage = nullptr;       // pinned, 6 planes of max chunk
-    uint32_t* h_counters = nullptr; // pinned
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // stats
     uint64_t launches = 0, iterations = 0, samples = 0, rays = 0;
     double render_ms = 0;
     bool slots_inited = false;
+    // optional per-kernel timing: event pairs tagged with a category (0 generate, 1 shade, 2 tail, 3 other)
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_tag;
+    size_t ev_used = 0;
+    double cat_ms[4] = {0, 0, 0, 0};
+    uint64_t cat_launches[4] = {0, 0, 0, 0};
 };
+
+namespace {
+struct KernelTimer {  // brackets one launch with two events when per-kernel timing is on
+    DeviceRenderer* r;
+    int tag;
+    KernelTimer(DeviceRenderer* rr, int t) : r(rr), tag(t) {
+        r->cat_launches[tag]++;
+        if (!r->cfg.kernel_timing) return;
+        if (r->ev_used + 2 > r->ev_pool.size()) {
+            for (int k = 0; k < 2; k++) { cudaEvent_t e; cudaEventCreate(&e); r->ev_pool.push_back(e); }
+            r->ev_tag.push_back(tag);
+        } else r->ev_tag[r->ev_used / 2] = tag;
+        cudaEventRecord(r->ev_pool[r->ev_used], r->stream);
+    }
+    ~KernelTimer() {
+        if (!r->cfg.kernel_timing) return;
+        cudaEventRecord(r->ev_pool[r->ev_used + 1], r->stream);
+        r->ev_used += 2;
+    }
+};
+void collect_kernel_times(DeviceRenderer* r) {
+    for (size_t k = 0; k + 1 < r->ev_used; k += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r->ev_pool[k], r->ev_pool[k + 1]) == cudaSuccess) r->cat_ms[r->ev_tag[k / 2]] += ms;
+    }
+    r->ev_used = 0;
+}
+}  // namespace
 
 void device_renderer_destroy(DeviceRenderer* r) {
     if (!r) return;
-    cudaFree(r->d_cie); cudaFree(r->d_bg); cudaFree(r->d_queues); cudaFree(r->d_counters); cudaFree(r->d_rays); cudaFree(r->d_rgb); cudaFree(r->d_xyz);
+    cudaFree(r->d_cie); cudaFree(r->d_bg); cudaFree(r->d_rays); cudaFree(r->d_rgb); cudaFree(r->d_xyz);
     cudaFree(r->P.R0); cudaFree(r->P.R1); cudaFree(r->P.P0); cudaFree(r->P.P1); cudaFree(r->P.G0); cudaFree(r->P.G1); cudaFree(r->P.sidx); cudaFree(r->P.acc);
     if (r->h_stage) cudaFreeHost(r->h_stage);
-    if (r->h_counters) cudaFreeHost(r->h_counters);
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
+    for (cudaEvent_t e : r->ev_pool) cudaEventDestroy(e);
     delete r;
 }
 
@@ -72,6 +104,7 @@ static bool renderer_setup(DeviceRenderer* r) {
     WaveParams& P = r->P;
     P.nodes = device_scene_nodes(r->scene);
     P.tris = device_scene_tris(r->scene);
+    P.fast = device_scene_fast(r->scene);
     P.mats = device_scene_mats(r->scene);
     P.n_tris = (int)device_scene_ntris(r->scene);
     P.n_mats = (int)device_scene_nmats(r->scene);
@@ -104,14 +137,11 @@ static bool renderer_setup(DeviceRenderer* r) {
     SRT_CUDA(cudaMalloc((void**)&P.sidx, ns * sizeof(uint32_t)));
     SRT_CUDA(cudaMalloc((void**)&P.acc, 3 * P.plane * sizeof(float)));
     SRT_CUDA(cudaMemsetAsync(P.acc, 0, 3 * P.plane * sizeof(float), r->stream));
-    SRT_CUDA(cudaMalloc((void**)&r->d_queues, 2 * 4 * ns * sizeof(uint32_t)));
-    SRT_CUDA(cudaMalloc((void**)&r->d_counters, 8 * sizeof(uint32_t)));
     SRT_CUDA(cudaMalloc((void**)&r->d_rays, sizeof(unsigned long long)));
     SRT_CUDA(cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), r->stream));
     SRT_CUDA(cudaMalloc((void**)&r->d_rgb, 3 * ns * sizeof(float)));
     SRT_CUDA(cudaMalloc((void**)&r->d_xyz, 3 * ns * sizeof(float)));
     SRT_CUDA(cudaMallocHost((void**)&r->h_stage, 6 * ns * sizeof(float)));
-    SRT_CUDA(cudaMallocHost((void**)&r->h_counters, 8 * sizeof(uint32_t)));
     std::vector<float> cie(3 * SRT_NS);
     for (int k = 0; k < 3; k++) memcpy(cie.data() + k * SRT_NS, cie_table(k), SRT_NS * sizeof(float));
     SRT_CUDA(cudaMalloc((void**)&r->d_cie, cie.size() * sizeof(float)));
@@ -122,9 +152,14 @@ static bool renderer_setup(DeviceRenderer* r) {
     P.bg = r->d_bg;
     P.ray_counter = r->d_rays;
     const LaunchTable& T = table(c.fp_strict);
-    const size_t need = T.smem_bytes(P);
-    r->smem = need <= kSmemSceneLimit ? need : 0;
-    if (r->smem) SRT_CUDA(T.configure(r->smem));
+    r->mode = P.n_tris <= SRT_FLAT_MAX_TRIS && c.traversal != 1 ? 2 : 1;
+    if (c.traversal == 0 && P.n_tris > SRT_FLAT_MAX_TRIS) r->mode = 1;
+    size_t need = T.smem_bytes(P, r->mode);
+    if (need > kSmemSceneLimit || c.traversal == 3) { r->mode = 0; need = 0; }
+    r->smem = need;
+    P.block_slots = (uint32_t)std::min(65536, std::max(32, c.block_slots));
+    P.queue_bytes = (2u * 4u * P.block_slots * (uint32_t)sizeof(uint16_t) + 15u) & ~15u;
+    SRT_CUDA(T.configure(r->smem + P.queue_bytes));
     // persistent grid: a multiple of the SM count, enough blocks to fill every SM's thread slots
     const int sms = sm_count();
     const int per_sm = r->smem ? std::max(1, std::min(8, (int)(200 * 1024 / (r->smem + 1024)))) : 8;
@@ -145,56 +180,33 @@ bool device_renderer_render_chunk(DeviceRenderer* r, unsigned off_x, unsigned of
     WaveParams P = r->P;
     const LaunchTable& T = table(r->cfg.fp_strict);
     cudaStream_t st = r->stream;
-    const size_t ns = P.nslots;
     P.off_x = off_x; P.off_y = off_y; P.cw = w; P.ch = h;
     SRT_CUDA(cudaEventRecord(r->ev0, st));
     if (!r->slots_inited) {  // RNG states are seeded once and carried across chunks (rendering.cu:209,232)
+        KernelTimer kt(r, 3);
         T.init_slots(P, st);
         r->launches++; count_launch();
         r->slots_inited = true;
     }
-    uint64_t owned = 0;
     if (r->cfg.pipeline == 1) {
-        T.megakernel(P, r->grid, r->smem, st);
-        r->launches++; count_launch();
-        SRT_CUDA_LAST();
-    } else {
-        uint32_t* q[2] = {r->d_queues, r->d_queues + 4 * ns};
-        uint32_t* cnt[2] = {r->d_counters, r->d_counters + 4};
-        SRT_CUDA(cudaMemsetAsync(r->d_counters, 0, 8 * sizeof(uint32_t), st));
-        P.qr_out = q[0]; P.qm_out = q[0] + ns; P.cnt_out = cnt[0];
-        T.begin_chunk(P, st);
-        r->launches++; count_launch();
-        int cur = 0;
-        // upper bound on iterations: every sample needs <= bounce_limit + 1 passes
-        const uint64_t max_iters = (uint64_t)P.spp * (P.bounce_limit + 2ull) + 2;
-        const int check_every = 8;
-        bool first = true;
-        for (uint64_t it = 0; it < max_iters;) {
-            for (int k = 0; k < check_every; k++, it++) {
-                const int nxt = cur ^ 1;
-                P.qr_in = q[cur]; P.qm_in = q[cur] + ns; P.cnt_in = cnt[cur];
-                P.qr_out = q[nxt]; P.qm_out = q[nxt] + ns; P.cnt_out = cnt[nxt];
-                SRT_CUDA(cudaMemsetAsync(cnt[nxt], 0, 4 * sizeof(uint32_t), st));
-                T.generate(P, r->grid, r->smem, st);
-                T.shade(P, r->grid, r->smem, st);
-                r->launches += 2; count_launch(2);
-                r->iterations++;
-                cur = nxt;
-            }
-            SRT_CUDA_LAST();
-            SRT_CUDA(cudaMemcpyAsync(r->h_counters, cnt[cur], 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            SRT_CUDA(cudaStreamSynchronize(st));
-            (void)first;
-            if (r->h_counters[0] + r->h_counters[1] + r->h_counters[2] + r->h_counters[3] == 0) break;
-        }
+        KernelTimer kt(r, 2);
+        T.megakernel(P, r->mode, r->grid, r->smem, st);
+    } else {  // one persistent-block launch renders the whole chunk
+        KernelTimer kt(r, 1);
+        const int blocks = (int)((P.nslots + P.block_slots - 1) / P.block_slots);
+        T.wavefront(P, r->mode, blocks, r->smem + P.queue_bytes, st);
+        r->iterations++;
     }
+    r->launches++; count_launch();
+    SRT_CUDA_LAST();
     SRT_CUDA(cudaEventRecord(r->ev1, st));
     SRT_CUDA(cudaEventSynchronize(r->ev1));
     float ms = 0;
     SRT_CUDA(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
     r->render_ms += ms;
+    collect_kernel_times(r);
     // owned pixels of this chunk (tile ownership) for the sample count
+    uint64_t owned = 0;
     for (unsigned y = off_y; y < off_y + h; y += 1) {
         const unsigned ty = y / P.tile_h;
         for (unsigned tx = off_x / P.tile_w; tx <= (off_x + w - 1) / P.tile_w; tx++) {
@@ -222,6 +234,7 @@ bool device_renderer_resolve(DeviceRenderer* r, unsigned off_x, unsigned off_y, 
     }
     T.resolve(r->P.acc, r->P.plane, r->P.img_w, off_x, off_y, w, h, r->P.spp, r->d_rgb, r->d_xyz, r->stream);
     r->launches++; count_launch();
+    r->cat_launches[3]++;
     SRT_CUDA_LAST();
     SRT_CUDA(cudaMemcpyAsync(r->h_stage, r->d_rgb, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
     SRT_CUDA(cudaMemcpyAsync(r->h_stage + 3 * n, r->d_xyz, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
@@ -245,11 +258,13 @@ void device_renderer_stats(const DeviceRenderer* r, srt_stats* s) {
     s->wavefront_iterations = r->iterations;
     s->render_ms = r->render_ms;
     s->lbvh_ms = device_scene_lbvh_ms(r->scene);
+    s->generate_ms = r->cat_ms[0]; s->shade_ms = r->cat_ms[1]; s->tail_ms = r->cat_ms[2]; s->other_ms = r->cat_ms[3];
+    s->generate_launches = r->cat_launches[0]; s->shade_launches = r->cat_launches[1]; s->tail_launches = r->cat_launches[2];
 }
 
 bool device_scene_trace(const DeviceScene* s, uint32_t n, const float* o, const float* d, float* t, int32_t* tri, float* ms) {
     WaveParams P{};
-    P.nodes = device_scene_nodes(s); P.tris = device_scene_tris(s); P.mats = device_scene_mats(s); P.n_tris = (int)device_scene_ntris(s);
+    P.nodes = device_scene_nodes(s); P.tris = device_scene_tris(s); P.fast = device_scene_fast(s); P.mats = device_scene_mats(s); P.n_tris = (int)device_scene_ntris(s);
     float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
     int32_t* d_tri = nullptr;
     cudaEvent_t e0, e1;

@@ -69,6 +69,7 @@ __device__ __forceinline__ float rng_range(Rng& s, float lo, float hi) {  // uti
 struct SceneRef {
     const SrtNode* nodes;
     const SrtTri* tris;
+    const SrtTriFast* fast;
     const SrtMaterial* mats;
     const float* cie;  // x[95] y[95] z[95]
     const float* bg;   // [95]
@@ -124,8 +125,51 @@ __device__ __forceinline__ bool tri_test(const SrtTri* __restrict__ tp, V3 o, V3
     return true;
 }
 
+// Wide-leaf closest hit for scenes of <= 64 triangles (all three reference scenes): the whole
+// LBVH collapses into ONE leaf, so there is no tree walk, no stack and no divergent descent.
+//   phase 1: every lane runs the same branch-free loop over all triangles (triangle data is a
+//            warp-uniform shared-memory broadcast) evaluating a CONSERVATIVE pre-test in explicit
+//            FMAs (plane distance with an approximate reciprocal + barycentrics with error slack)
+//            and records survivors in a 64-bit mask;
+//   phase 2: the few survivors (the triangles the ray really pierces, ~1-4) get the exact
+//            reference arithmetic (tri_test), nearest wins.
+// The pre-test only ever rejects pairs the exact test rejects too, so results are identical to
+// testing every triangle exactly -- which is what "closest hit" means in the reference (bvh.cu:98-166).
+__device__ __forceinline__ int closest_hit_flat(const SceneRef& sc, V3 o, V3 d, float& t_hit) {
+    const float o1 = fabsf(o.x) + fabsf(o.y) + fabsf(o.z);
+    uint32_t m0 = 0, m1 = 0;
+    const float4* __restrict__ fp = reinterpret_cast<const float4*>(sc.fast);
+    for (int i = 0; i < sc.n_tris; i++) {
+        const float4 pl = fp[4 * i], A = fp[4 * i + 1], B = fp[4 * i + 2], T = fp[4 * i + 3];
+        const float denom = __fmaf_rn(pl.z, d.z, __fmaf_rn(pl.y, d.y, pl.x * d.x));
+        const float num = pl.w - __fmaf_rn(pl.z, o.z, __fmaf_rn(pl.y, o.y, pl.x * o.x));
+        const float t = __fdividef(num, denom);
+        const float px = __fmaf_rn(t, d.x, o.x), py = __fmaf_rn(t, d.y, o.y), pz = __fmaf_rn(t, d.z, o.z);
+        const float u = __fmaf_rn(A.z, pz, __fmaf_rn(A.y, py, __fmaf_rn(A.x, px, A.w)));
+        const float v = __fmaf_rn(B.z, pz, __fmaf_rn(B.y, py, __fmaf_rn(B.x, px, B.w)));
+        const float eps = __fmaf_rn(T.y, o1, T.x), tol = __fmaf_rn(T.w, o1, T.z);
+        // written as "certainly outside" so that NaN/inf fall through to the exact test
+        const bool reject = (u < -eps) | (v < -eps) | (u + v > 1.0f + eps) | ((t < 0.0f) & (fabsf(num) > tol));
+        const uint32_t bit = reject ? 0u : 1u;
+        if (i < 32) m0 |= bit << i;
+        else m1 |= bit << (i - 32);
+    }
+    float closest = FLT_MAX;
+    int best = -1;
+    while (m0 | m1) {
+        int i;
+        if (m0) { i = __ffs(m0) - 1; m0 &= m0 - 1; }
+        else { i = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
+        float t;
+        if (tri_test(sc.tris + i, o, d, closest, t)) { closest = t; best = i; }
+    }
+    t_hit = closest;
+    return best;
+}
+
 // closest hit over the LBVH: both child boxes live in the parent node (4 x 16-B loads),
 // near child first, far child pushed.  Returns leaf-order triangle index or -1.
+template <bool FLAT>
 __device__ __forceinline__ int closest_hit(const SceneRef& sc, V3 o, V3 d, float& t_hit) {
     float closest = FLT_MAX;
     int best = -1;
@@ -133,6 +177,7 @@ __device__ __forceinline__ int closest_hit(const SceneRef& sc, V3 o, V3 d, float
     // A NaN ray (buggy-Sellmeier refraction, Q1) can never hit: every tri::hit computes a NaN t.
     // Answer "miss" up front instead of walking the whole tree.
     if (!(d.x == d.x && d.y == d.y && d.z == d.z && o.x == o.x && o.y == o.y && o.z == o.z)) return -1;
+    if (FLAT) return closest_hit_flat(sc, o, d, t_hit);
     if (sc.n_tris == 1) {
         float t;
         if (tri_test(sc.tris, o, d, closest, t)) { t_hit = t; return 0; }
@@ -225,7 +270,7 @@ __device__ __forceinline__ void camera_ray(const SrtCamera& c, uint32_t i, uint3
     p.bounce = 0;
 }
 
-__device__ __forceinline__ void mul_spectrum(Path& p, const float* __restrict__ spec) {  // ray/ray.cuh:60-69
+__device__ __noinline__ void mul_spectrum(Path& p, const float* __restrict__ spec) {  // ray/ray.cuh:60-69
     float wl[SRT_N_WL];
     hero_rotations(p.hero, wl);
 #pragma unroll
@@ -234,7 +279,7 @@ __device__ __forceinline__ void mul_spectrum(Path& p, const float* __restrict__ 
 }
 
 // dev_spectrum_to_XYZ (color/color.cu:88-104) added into the film accumulator of one pixel
-__device__ __forceinline__ void film_add(const SceneRef& sc, const Path& p, float* __restrict__ acc, size_t plane, size_t pix) {
+__device__ __noinline__ void film_add(const SceneRef& sc, const Path& p, float* __restrict__ acc, size_t plane, size_t pix) {
     if (p.valid == 0) return;  // contributes (0,0,0): x + 0 leaves the sum unchanged
     float wl[SRT_N_WL];
     hero_rotations(p.hero, wl);
@@ -274,9 +319,9 @@ __device__ __forceinline__ float sellmeier(const SrtMaterial* __restrict__ m, fl
 
 // material::scatter (materials/material.cu:55-100) for a non-emissive hit.
 // In: p.o = hit point, p.d = incoming direction, tri = the triangle hit.  Out: new ray in p.
-// Returns false when the path ends here (metal absorbed the ray).
-template <uint32_t MTYPE>
-__device__ __forceinline__ bool scatter(const SceneRef& sc, const SrtTri* __restrict__ tri, Path& p, Rng& rng) {
+// Returns false when the path ends here (metal absorbed the ray).  `mtype` is warp-uniform in the
+// wavefront (queues are sorted by material), so the branches below do not diverge there.
+__device__ __forceinline__ bool scatter(const SceneRef& sc, const SrtTri* __restrict__ tri, uint32_t mtype, Path& p, Rng& rng) {
     const float4 q0 = *reinterpret_cast<const float4*>(tri);
     const uint32_t bits = __float_as_uint((reinterpret_cast<const float4*>(tri) + 2)->z);
     const SrtMaterial* m = sc.mats + SRT_TRI_MAT(bits);
@@ -287,12 +332,7 @@ __device__ __forceinline__ bool scatter(const SceneRef& sc, const SrtTri* __rest
     V3 out;
     float eps_sign = 1.0f;
     bool alive = true;
-    if (MTYPE == SRT_METALLIC) {  // reflection_scatter :22-37
-        const V3 refl = reflect(uin, n);
-        out = refl + (m->fuzz * random_unit_vector(rng));
-        alive = dot(out, n) > 0;
-        if (!alive) p.valid = 0;
-    } else if (MTYPE == SRT_DIELECTRIC) {  // refraction_scatter :103-135, evaluated at the hero wavelength only
+    if (mtype == SRT_DIELECTRIC) {  // refraction_scatter :103-135, evaluated at the hero wavelength only
         const float ir = sellmeier(m, p.hero);
         const float ratio = front ? (1.0f / ir) : ir;
         const float cos_theta = fminf(dot(-uin, n), 1.0f);
@@ -313,10 +353,17 @@ __device__ __forceinline__ bool scatter(const SceneRef& sc, const SrtTri* __rest
             eps_sign = -1.0f;
             p.valid = 1;  // only the hero wavelength survives a refraction (Q5)
         }
-    } else {  // lambertian_scatter :9-19
-        out = n + random_unit_vector(rng);
-        const float s = 1e-8f;
-        if ((fabsf(out.x) < s) && (fabsf(out.y) < s) && (fabsf(out.z) < s)) out = n;
+    } else {
+        const V3 ruv = random_unit_vector(rng);  // both remaining materials draw one unit vector first
+        if (mtype == SRT_METALLIC) {  // reflection_scatter :22-37
+            out = reflect(uin, n) + (m->fuzz * ruv);
+            alive = dot(out, n) > 0;
+            if (!alive) p.valid = 0;
+        } else {  // lambertian_scatter :9-19
+            out = n + ruv;
+            const float s = 1e-8f;
+            if ((fabsf(out.x) < s) && (fabsf(out.y) < s) && (fabsf(out.z) < s)) out = n;
+        }
     }
     mul_spectrum(p, m->spec);
     p.o = p.o + ((eps_sign * SRT_EPSILON) * n);
@@ -329,9 +376,10 @@ enum : int { EV_DONE = -1 };  // sample finished; otherwise the value is the que
 
 // trace p's ray and either finish the sample or leave p at the hit (p.o = hit point).
 // Returns EV_DONE or the material queue (1 lambertian, 2 metallic, 3 dielectric); tri_out = leaf-order index.
+template <bool FLAT>
 __device__ __forceinline__ int extend(const SceneRef& sc, const WaveParams& P, Path& p, int& tri_out, float* acc, size_t pix) {
     float t = 0.f;
-    const int tri = closest_hit(sc, p.o, p.d, t);
+    const int tri = closest_hit<FLAT>(sc, p.o, p.d, t);
     if (tri < 0) {  // miss: ray_bounce, rendering.cu:24-27
         if (!P.bg_is_zero) {
             mul_spectrum(p, sc.bg);
@@ -353,28 +401,31 @@ __device__ __forceinline__ int extend(const SceneRef& sc, const WaveParams& P, P
 
 // ------------------------------------------------------------------------------ shared-memory scene
 // Small scenes (all three reference scenes) are staged once per block: nodes | tris | mats | cie | bg
-template <bool SMEM>
+template <bool SMEM, bool FLAT>
 __device__ __forceinline__ SceneRef load_scene(const WaveParams& P, unsigned char* smem) {
     SceneRef sc;
     sc.n_tris = P.n_tris;
     if (!SMEM) {
-        sc.nodes = P.nodes; sc.tris = P.tris; sc.mats = P.mats; sc.cie = P.cie; sc.bg = P.bg;
+        sc.nodes = P.nodes; sc.tris = P.tris; sc.fast = P.fast; sc.mats = P.mats; sc.cie = P.cie; sc.bg = P.bg;
         return sc;
     }
+    // layout: [nodes | pre-test records (flat scenes)] | tris | mats | cie | bg
     const int n_nodes = P.n_tris > 1 ? P.n_tris - 1 : 0;
     float4* dst = reinterpret_cast<float4*>(smem);
-    const int v_nodes = n_nodes * (int)(sizeof(SrtNode) / 16), v_tris = P.n_tris * (int)(sizeof(SrtTri) / 16),
-              v_mats = P.n_mats * (int)(sizeof(SrtMaterial) / 16);
-    for (int i = threadIdx.x; i < v_nodes; i += blockDim.x) dst[i] = reinterpret_cast<const float4*>(P.nodes)[i];
-    for (int i = threadIdx.x; i < v_tris; i += blockDim.x) dst[v_nodes + i] = reinterpret_cast<const float4*>(P.tris)[i];
-    for (int i = threadIdx.x; i < v_mats; i += blockDim.x) dst[v_nodes + v_tris + i] = reinterpret_cast<const float4*>(P.mats)[i];
-    float* f = reinterpret_cast<float*>(dst + v_nodes + v_tris + v_mats);
+    const int v_head = FLAT ? P.n_tris * (int)(sizeof(SrtTriFast) / 16) : n_nodes * (int)(sizeof(SrtNode) / 16);
+    const float4* head = FLAT ? reinterpret_cast<const float4*>(P.fast) : reinterpret_cast<const float4*>(P.nodes);
+    const int v_tris = P.n_tris * (int)(sizeof(SrtTri) / 16), v_mats = P.n_mats * (int)(sizeof(SrtMaterial) / 16);
+    for (int i = threadIdx.x; i < v_head; i += blockDim.x) dst[i] = head[i];
+    for (int i = threadIdx.x; i < v_tris; i += blockDim.x) dst[v_head + i] = reinterpret_cast<const float4*>(P.tris)[i];
+    for (int i = threadIdx.x; i < v_mats; i += blockDim.x) dst[v_head + v_tris + i] = reinterpret_cast<const float4*>(P.mats)[i];
+    float* f = reinterpret_cast<float*>(dst + v_head + v_tris + v_mats);
     for (int i = threadIdx.x; i < 3 * SRT_NS; i += blockDim.x) f[i] = P.cie[i];
     for (int i = threadIdx.x; i < SRT_NS; i += blockDim.x) f[3 * SRT_NS + i] = P.bg[i];
     __syncthreads();
-    sc.nodes = reinterpret_cast<const SrtNode*>(dst);
-    sc.tris = reinterpret_cast<const SrtTri*>(dst + v_nodes);
-    sc.mats = reinterpret_cast<const SrtMaterial*>(dst + v_nodes + v_tris);
+    sc.nodes = FLAT ? nullptr : reinterpret_cast<const SrtNode*>(dst);
+    sc.fast = FLAT ? reinterpret_cast<const SrtTriFast*>(dst) : nullptr;
+    sc.tris = reinterpret_cast<const SrtTri*>(dst + v_head);
+    sc.mats = reinterpret_cast<const SrtMaterial*>(dst + v_head + v_tris);
     sc.cie = f;
     sc.bg = f + 3 * SRT_NS;
     return sc;
@@ -390,15 +441,16 @@ __device__ __forceinline__ uint32_t ref_thread_index(const WaveParams& P, uint32
     return (cj % 16u) * 28u + (ci % 28u) + 448u * ((cj / 16u) * P.ref_grid_x + ci / 28u);
 }
 
-// warp-aggregated queue push: one atomicAdd per warp per queue
-__device__ __forceinline__ void queue_push(uint32_t* __restrict__ q, uint32_t* counter, bool pred, uint32_t slot) {
+// warp-aggregated push into a block-local (shared memory) queue of local slot ids:
+// ballot + one shared-memory atomicAdd per warp, lanes write at base + rank-in-ballot
+__device__ __forceinline__ void queue_push(uint16_t* __restrict__ q, int* counter, bool pred, uint32_t local_slot) {
     const uint32_t mask = __ballot_sync(0xffffffffu, pred);
     if (mask == 0) return;
     const int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == __ffs(mask) - 1) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    int base = 0;
+    if (lane == __ffs(mask) - 1) base = atomicAdd(counter, __popc(mask));
     base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
-    if (pred) q[base + __popc(mask & ((1u << lane) - 1))] = slot;
+    if (pred) q[base + __popc(mask & ((1u << lane) - 1))] = (uint16_t)local_slot;
 }
 
 __device__ __forceinline__ void store_hit_state(const WaveParams& P, uint32_t slot, const Path& p, int tri) {
@@ -406,6 +458,18 @@ __device__ __forceinline__ void store_hit_state(const WaveParams& P, uint32_t sl
     P.R1[slot] = make_float4(p.d.x, p.d.y, p.d.z, __uint_as_float(p.valid | (p.bounce << 3)));
     P.P0[slot] = make_float4(p.pw[0], p.pw[1], p.pw[2], p.pw[3]);
     P.P1[slot] = make_float4(p.pw[4], p.pw[5], p.pw[6], p.hero);
+}
+__device__ __forceinline__ void load_hit_state(const WaveParams& P, uint32_t slot, Path& p, int& tri) {
+    const float4 r0 = P.R0[slot], r1 = P.R1[slot], p0 = P.P0[slot], p1 = P.P1[slot];
+    p.o = mk(r0.x, r0.y, r0.z);
+    p.d = mk(r1.x, r1.y, r1.z);
+    const uint32_t meta = __float_as_uint(r1.w);
+    p.valid = meta & 7u;
+    p.bounce = meta >> 3;
+    p.pw[0] = p0.x; p.pw[1] = p0.y; p.pw[2] = p0.z; p.pw[3] = p0.w;
+    p.pw[4] = p1.x; p.pw[5] = p1.y; p.pw[6] = p1.z;
+    p.hero = p1.w;
+    tri = __float_as_int(r0.w);
 }
 __device__ __forceinline__ void store_rng(const WaveParams& P, uint32_t slot, const Rng& r) {
     P.G0[slot] = make_uint4(r.d, r.v0, r.v1, r.v2);
@@ -418,6 +482,13 @@ __device__ __forceinline__ Rng load_rng(const WaveParams& P, uint32_t slot) {
     r.d = a.x; r.v0 = a.y; r.v1 = a.z; r.v2 = a.w; r.v3 = b.x; r.v4 = b.y;
     return r;
 }
+__device__ __forceinline__ bool slot_owned(const WaveParams& P, uint32_t slot, uint32_t& ci, uint32_t& cj) {
+    if (slot >= P.nslots) return false;
+    slot_pixel(P, slot, ci, cj);
+    if (ci >= P.cw || cj >= P.ch) return false;
+    const uint32_t x = P.off_x + ci, y = P.off_y + cj;
+    return ((x / P.tile_w) + (y / P.tile_h) * P.tiles_x) % P.world == P.rank;
+}
 
 // ------------------------------------------------------------------------------ kernels
 __global__ void k_init_slots(WaveParams P) {  // init_random_states (rendering.cu:120-138), one state per reference thread slot
@@ -428,137 +499,120 @@ __global__ void k_init_slots(WaveParams P) {  // init_random_states (rendering.c
     store_rng(P, slot, rng_seed(1984u + ref_thread_index(P, ci, cj)));
 }
 
-// first regenerate queue of a chunk: every pixel of the chunk this rank owns, samples reset
-__global__ void k_begin_chunk(WaveParams P) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    bool mine = false;
-    if (slot < P.nslots) {
+// Persistent-block wavefront.  A block owns P.block_slots consecutive pixel slots for the whole
+// render of a chunk and runs its own bounce loop: four queues of local slot ids in shared memory
+// (regenerate | lambertian | metallic | dielectric), double buffered.  Every pass lays the four
+// queues out back to back, each padded to a warp multiple, so a warp only ever executes one kind
+// of work; warps pull 32-item chunks from a shared counter (cheap items do not leave a warp idle);
+// results are pushed into the other buffer with warp-aggregated shared-memory atomics.  No global
+// atomics, no host round trips, one launch per chunk; blocks are scheduled dynamically, which
+// balances the uneven pixel costs over the SMs.  The ray trace (extend) has ONE call site so the
+// hot loop stays inside the instruction cache.
+template <bool SMEM, bool FLAT>
+__global__ void __launch_bounds__(SRT_BLOCK, 4) k_wavefront(WaveParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t S = P.block_slots;
+    uint16_t* qbuf = reinterpret_cast<uint16_t*>(smem);  // [2][4][S]
+    __shared__ int cnt[2][4];
+    __shared__ int next_chunk;
+    const SceneRef sc = load_scene<SMEM, FLAT>(P, smem + P.queue_bytes);
+    const uint32_t first = blockIdx.x * S;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 8) (&cnt[0][0])[threadIdx.x] = 0;
+    if (threadIdx.x == 0) next_chunk = 0;
+    __syncthreads();
+    // pass 0 input: every slot of the block that this rank owns, samples reset
+    for (uint32_t l = threadIdx.x; l < S; l += blockDim.x) {
         uint32_t ci, cj;
-        slot_pixel(P, slot, ci, cj);
-        if (ci < P.cw && cj < P.ch) {
-            const uint32_t x = P.off_x + ci, y = P.off_y + cj;
-            const uint32_t tile = (x / P.tile_w) + (y / P.tile_h) * P.tiles_x;
-            mine = (tile % P.world) == P.rank;
-            if (mine) P.sidx[slot] = 0;
-        }
+        const bool mine = slot_owned(P, first + l, ci, cj);
+        if (mine) P.sidx[first + l] = 0;
+        queue_push(qbuf, &cnt[0][0], mine, l);
     }
-    queue_push(P.qr_out, P.cnt_out + 0, mine, slot);
-}
-
-template <bool SMEM>
-__global__ void __launch_bounds__(SRT_BLOCK) k_generate(WaveParams P) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const SceneRef sc = load_scene<SMEM>(P, smem);
-    const uint32_t n = P.cnt_in[0];
+    __syncthreads();
     unsigned long long rays = 0;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t idx = base + threadIdx.x;
-        const bool active = idx < n;
-        int ev = EV_DONE;
-        bool requeue = false;
-        uint32_t slot = 0;
-        if (active) {
-            slot = P.qr_in[idx];
-            uint32_t ci, cj;
-            slot_pixel(P, slot, ci, cj);
-            const size_t pix = (size_t)(P.off_y + cj) * P.img_w + (P.off_x + ci);
-            Rng rng = load_rng(P, slot);
-            uint32_t s = P.sidx[slot];
+    int cur = 0;
+    while (true) {
+        const int nR = cnt[cur][0], nL = cnt[cur][1], nM = cnt[cur][2], nD = cnt[cur][3];
+        if ((nR | nL | nM | nD) == 0) break;
+        const int eR = (nR + 31) & ~31, eL = eR + ((nL + 31) & ~31), eM = eL + ((nM + 31) & ~31), eD = eM + ((nD + 31) & ~31);
+        const uint16_t* qi = qbuf + (size_t)cur * 4 * S;
+        uint16_t* qo = qbuf + (size_t)(cur ^ 1) * 4 * S;
+        int* co = cnt[cur ^ 1];
+        while (true) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&next_chunk, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= eD) break;
+            const int v = base + lane;
+            // which queue does this warp serve (uniform), and does this lane have an item?
+            int kind, k;
+            if (base < eR) { kind = 0; k = v; }
+            else if (base < eL) { kind = 1; k = v - eR; }
+            else if (base < eM) { kind = 2; k = v - eL; }
+            else { kind = 3; k = v - eM; }
+            const int have_n = kind == 0 ? nR : (kind == 1 ? nL : (kind == 2 ? nM : nD));
+            const bool have = k < have_n;
+            const uint32_t l = have ? qi[kind * S + k] : 0u;
+            const uint32_t slot = first + l;
+            uint32_t ci = 0, cj = 0;
+            size_t pix = 0;
             Path p;
-            int tri = -1;
-            int loops = 0;
-            while (s < P.spp) {
-                if (loops == P.regen_loop) { requeue = true; break; }
-                loops++;
-                camera_ray(P.cam, P.off_x + ci, P.off_y + cj, rng, p);
-                s++;
-                if (P.bounce_limit == 0) { continue; }  // loop body of ray_bounce never runs: valid = 0
-                rays++;
-                ev = extend(sc, P, p, tri, P.acc, pix);
-                if (ev != EV_DONE) break;
+            Rng rng;
+            int tri = -1, ev = EV_DONE;
+            uint32_t s = 0;
+            bool trace = false;
+            if (have) {
+                slot_pixel(P, slot, ci, cj);
+                pix = (size_t)(P.off_y + cj) * P.img_w + (P.off_x + ci);
+                rng = load_rng(P, slot);
+                s = P.sidx[slot];
+                if (kind == 0) {  // next sample of this pixel (rendering.cu:215-228)
+                    if (s < P.spp) {
+                        camera_ray(P.cam, P.off_x + ci, P.off_y + cj, rng, p);
+                        s++;
+                        P.sidx[slot] = s;
+                        trace = P.bounce_limit != 0;  // limit 0: the bounce loop never runs, valid = 0
+                    }
+                } else {  // scatter at the stored hit (warp-uniform material)
+                    load_hit_state(P, slot, p, tri);
+                    const uint32_t mtype = kind == 2 ? SRT_METALLIC : (kind == 3 ? SRT_DIELECTRIC : SRT_LAMBERTIAN);
+                    const bool alive = scatter(sc, sc.tris + tri, mtype, p, rng);
+                    p.bounce++;
+                    trace = alive && p.bounce < P.bounce_limit;  // absorbed, or bounce limit: valid = 0 (rendering.cu:38)
+                }
             }
-            P.sidx[slot] = s;
-            store_rng(P, slot, rng);
-            if (ev != EV_DONE) store_hit_state(P, slot, p, tri);
+            if (trace) {
+                rays++;
+                ev = extend<FLAT>(sc, P, p, tri, P.acc, pix);
+            }
+            if (have) {
+                store_rng(P, slot, rng);
+                if (ev != EV_DONE) store_hit_state(P, slot, p, tri);
+            }
+            queue_push(qo, co + 0, have && ev == EV_DONE && s < P.spp, l);  // sample over, pixel not finished
+            queue_push(qo + S, co + 1, ev == 1, l);
+            queue_push(qo + 2 * S, co + 2, ev == 2, l);
+            queue_push(qo + 3 * S, co + 3, ev == 3, l);
         }
-        queue_push(P.qr_out, P.cnt_out + 0, requeue, slot);
-        queue_push(P.qm_out, P.cnt_out + 1, ev == 1, slot);
-        queue_push(P.qm_out + P.nslots, P.cnt_out + 2, ev == 2, slot);
-        queue_push(P.qm_out + 2 * (size_t)P.nslots, P.cnt_out + 3, ev == 3, slot);
-    }
-    if (P.ray_counter && rays) atomicAdd(P.ray_counter, rays);
-}
-
-template <uint32_t MTYPE>
-__device__ __forceinline__ int shade_one(const SceneRef& sc, const WaveParams& P, uint32_t slot, unsigned long long& rays) {
-    uint32_t ci, cj;
-    slot_pixel(P, slot, ci, cj);
-    const size_t pix = (size_t)(P.off_y + cj) * P.img_w + (P.off_x + ci);
-    const float4 r0 = P.R0[slot], r1 = P.R1[slot], p0 = P.P0[slot], p1 = P.P1[slot];
-    Path p;
-    p.o = mk(r0.x, r0.y, r0.z);
-    p.d = mk(r1.x, r1.y, r1.z);
-    const uint32_t meta = __float_as_uint(r1.w);
-    p.valid = meta & 7u;
-    p.bounce = meta >> 3;
-    p.pw[0] = p0.x; p.pw[1] = p0.y; p.pw[2] = p0.z; p.pw[3] = p0.w;
-    p.pw[4] = p1.x; p.pw[5] = p1.y; p.pw[6] = p1.z;
-    p.hero = p1.w;
-    int tri = __float_as_int(r0.w);
-    Rng rng = load_rng(P, slot);
-    const bool alive = scatter<MTYPE>(sc, sc.tris + tri, p, rng);
-    store_rng(P, slot, rng);
-    p.bounce++;
-    if (!alive || p.bounce >= P.bounce_limit) return EV_DONE;  // absorbed, or bounce limit: valid = 0 (rendering.cu:38)
-    rays++;
-    const int ev = extend(sc, P, p, tri, P.acc, pix);
-    if (ev != EV_DONE) store_hit_state(P, slot, p, tri);
-    return ev;
-}
-
-// one launch covers the three material segments; each segment is padded to a warp multiple so a
-// warp never mixes materials
-template <bool SMEM>
-__global__ void __launch_bounds__(SRT_BLOCK) k_shade(WaveParams P) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const SceneRef sc = load_scene<SMEM>(P, smem);
-    const uint32_t nL = P.cnt_in[1], nM = P.cnt_in[2], nD = P.cnt_in[3];
-    const uint32_t eL = (nL + 31u) & ~31u, eM = eL + ((nM + 31u) & ~31u), eD = eM + ((nD + 31u) & ~31u);
-    unsigned long long rays = 0;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < eD; base += gridDim.x * blockDim.x) {
-        const uint32_t v = base + threadIdx.x;
-        int ev = EV_DONE;
-        bool done = false;
-        uint32_t slot = 0;
-        if (v < eL) {
-            if (v < nL) { slot = P.qm_in[v]; ev = shade_one<SRT_LAMBERTIAN>(sc, P, slot, rays); done = ev == EV_DONE; }
-        } else if (v < eM) {
-            const uint32_t k = v - eL;
-            if (k < nM) { slot = P.qm_in[P.nslots + k]; ev = shade_one<SRT_METALLIC>(sc, P, slot, rays); done = ev == EV_DONE; }
-        } else if (v < eD) {
-            const uint32_t k = v - eM;
-            if (k < nD) { slot = P.qm_in[2 * (size_t)P.nslots + k]; ev = shade_one<SRT_DIELECTRIC>(sc, P, slot, rays); done = ev == EV_DONE; }
-        }
-        queue_push(P.qr_out, P.cnt_out + 0, done, slot);
-        queue_push(P.qm_out, P.cnt_out + 1, ev == 1, slot);
-        queue_push(P.qm_out + P.nslots, P.cnt_out + 2, ev == 2, slot);
-        queue_push(P.qm_out + 2 * (size_t)P.nslots, P.cnt_out + 3, ev == 3, slot);
+        __syncthreads();
+        if (threadIdx.x < 4) cnt[cur][threadIdx.x] = 0;  // becomes the output buffer of the next pass
+        if (threadIdx.x == 0) next_chunk = 0;
+        cur ^= 1;
+        __syncthreads();
     }
     if (P.ray_counter && rays) atomicAdd(P.ray_counter, rays);
 }
 
 // per-pixel persistent kernel: same device functions, no queues (cross-check / comparison)
-template <bool SMEM>
+template <bool SMEM, bool FLAT>
 __global__ void __launch_bounds__(SRT_BLOCK) k_megakernel(WaveParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const SceneRef sc = load_scene<SMEM>(P, smem);
+    const SceneRef sc = load_scene<SMEM, FLAT>(P, smem);
     unsigned long long rays = 0;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < P.nslots; slot += gridDim.x * blockDim.x) {
         uint32_t ci, cj;
-        slot_pixel(P, slot, ci, cj);
-        if (ci >= P.cw || cj >= P.ch) continue;
+        if (!slot_owned(P, slot, ci, cj)) continue;
         const uint32_t x = P.off_x + ci, y = P.off_y + cj;
-        if (((x / P.tile_w) + (y / P.tile_h) * P.tiles_x) % P.world != P.rank) continue;
         const size_t pix = (size_t)y * P.img_w + x;
         Rng rng = load_rng(P, slot);
         for (uint32_t s = 0; s < P.spp; s++) {
@@ -567,16 +621,13 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_megakernel(WaveParams P) {
             if (P.bounce_limit == 0) continue;
             int tri = -1;
             rays++;
-            int ev = extend(sc, P, p, tri, P.acc, pix);
+            int ev = extend<FLAT>(sc, P, p, tri, P.acc, pix);
             while (ev != EV_DONE) {
-                bool alive;
-                if (ev == 2) alive = scatter<SRT_METALLIC>(sc, sc.tris + tri, p, rng);
-                else if (ev == 3) alive = scatter<SRT_DIELECTRIC>(sc, sc.tris + tri, p, rng);
-                else alive = scatter<SRT_LAMBERTIAN>(sc, sc.tris + tri, p, rng);
+                const bool alive = scatter(sc, sc.tris + tri, ev == 2 ? SRT_METALLIC : (ev == 3 ? SRT_DIELECTRIC : SRT_LAMBERTIAN), p, rng);
                 p.bounce++;
                 if (!alive || p.bounce >= P.bounce_limit) break;
                 rays++;
-                ev = extend(sc, P, p, tri, P.acc, pix);
+                ev = extend<FLAT>(sc, P, p, tri, P.acc, pix);
             }
         }
         store_rng(P, slot, rng);
@@ -612,47 +663,54 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_trace_rays(WaveParams P, uint32_t
                                                           const uint32_t* __restrict__ sorted_idx, float* __restrict__ t_out,
                                                           int32_t* __restrict__ tri_out) {
     SceneRef sc;
-    sc.nodes = P.nodes; sc.tris = P.tris; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
+    sc.nodes = P.nodes; sc.tris = P.tris; sc.fast = P.fast; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float t = 0.f;
-        const int tri = closest_hit(sc, mk(o[3ull * i], o[3ull * i + 1], o[3ull * i + 2]), mk(d[3ull * i], d[3ull * i + 1], d[3ull * i + 2]), t);
+        const int tri = closest_hit<false>(sc, mk(o[3ull * i], o[3ull * i + 1], o[3ull * i + 2]), mk(d[3ull * i], d[3ull * i + 1], d[3ull * i + 2]), t);
         t_out[i] = tri >= 0 ? t : -1.0f;
         tri_out[i] = tri >= 0 ? (int32_t)sorted_idx[tri] : -1;
     }
 }
 
 // ------------------------------------------------------------------------------ launchers
-static size_t scene_smem_bytes(const WaveParams& P) {
+// mode 0: scene in global memory, LBVH walk; 1: scene staged in shared memory, LBVH walk;
+// 2: scene staged in shared memory, <= 64 triangles, wide-leaf closest hit (no tree walk)
+static size_t scene_smem_bytes(const WaveParams& P, int mode) {
     const size_t n_nodes = P.n_tris > 1 ? P.n_tris - 1 : 0;
-    return n_nodes * sizeof(SrtNode) + (size_t)P.n_tris * sizeof(SrtTri) + (size_t)P.n_mats * sizeof(SrtMaterial) + 4 * SRT_NS * sizeof(float);
+    const size_t head = mode == 2 ? (size_t)P.n_tris * sizeof(SrtTriFast) : n_nodes * sizeof(SrtNode);
+    return head + (size_t)P.n_tris * sizeof(SrtTri) + (size_t)P.n_mats * sizeof(SrtMaterial) + 4 * SRT_NS * sizeof(float);
 }
+#define SRT_DISPATCH(KERNEL, MODE, GRID, SMEMB, ST, ...)                                  \
+    do {                                                                                  \
+        if ((MODE) == 2) KERNEL<true, true><<<GRID, SRT_BLOCK, SMEMB, ST>>>(__VA_ARGS__); \
+        else if ((MODE) == 1) KERNEL<true, false><<<GRID, SRT_BLOCK, SMEMB, ST>>>(__VA_ARGS__); \
+        else KERNEL<false, false><<<GRID, SRT_BLOCK, 0, ST>>>(__VA_ARGS__);               \
+    } while (0)
 
 LaunchTable make_launch_table() {
     LaunchTable t;
-    t.smem_bytes = [](const WaveParams& P) { return scene_smem_bytes(P); };
+    t.smem_bytes = [](const WaveParams& P, int mode) { return scene_smem_bytes(P, mode); };
     t.configure = [](size_t bytes) {
         cudaError_t e = cudaSuccess;
-        if (bytes > 48 * 1024) {
-            e = cudaFuncSetAttribute(k_generate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_megakernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        {
+            const int b = (int)std::max<size_t>(bytes, 48 * 1024);
+            const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+            e = cudaFuncSetAttribute(k_wavefront<true, false>, attr, b);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wavefront<true, true>, attr, b);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wavefront<false, false>, attr, b);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_megakernel<true, false>, attr, b);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_megakernel<true, true>, attr, b);
         }
         return e;
     };
     t.init_slots = [](const WaveParams& P, cudaStream_t st) { k_init_slots<<<(P.nslots + 255) / 256, 256, 0, st>>>(P); };
-    t.begin_chunk = [](const WaveParams& P, cudaStream_t st) { k_begin_chunk<<<(P.nslots + 255) / 256, 256, 0, st>>>(P); };
-    t.generate = [](const WaveParams& P, int grid, size_t smem, cudaStream_t st) {
-        if (smem) k_generate<true><<<grid, SRT_BLOCK, smem, st>>>(P);
-        else k_generate<false><<<grid, SRT_BLOCK, 0, st>>>(P);
+    t.wavefront = [](const WaveParams& P, int mode, int grid, size_t smem, cudaStream_t st) {
+        // the queues always live in shared memory, also when the scene does not
+        if (mode == 2) k_wavefront<true, true><<<grid, SRT_BLOCK, smem, st>>>(P);
+        else if (mode == 1) k_wavefront<true, false><<<grid, SRT_BLOCK, smem, st>>>(P);
+        else k_wavefront<false, false><<<grid, SRT_BLOCK, smem, st>>>(P);
     };
-    t.shade = [](const WaveParams& P, int grid, size_t smem, cudaStream_t st) {
-        if (smem) k_shade<true><<<grid, SRT_BLOCK, smem, st>>>(P);
-        else k_shade<false><<<grid, SRT_BLOCK, 0, st>>>(P);
-    };
-    t.megakernel = [](const WaveParams& P, int grid, size_t smem, cudaStream_t st) {
-        if (smem) k_megakernel<true><<<grid, SRT_BLOCK, smem, st>>>(P);
-        else k_megakernel<false><<<grid, SRT_BLOCK, 0, st>>>(P);
-    };
+    t.megakernel = [](const WaveParams& P, int mode, int grid, size_t smem, cudaStream_t st) { SRT_DISPATCH(k_megakernel, mode, grid, smem, st, P); };
     t.resolve = [](const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, float* rgb,
                    float* xyz, cudaStream_t st) {
         k_resolve<<<(w * h + 255) / 256, 256, 0, st>>>(acc, plane, img_w, ox, oy, w, h, spp, rgb, xyz);

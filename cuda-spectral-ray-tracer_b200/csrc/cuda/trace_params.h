@@ -13,6 +13,7 @@ struct WaveParams {
     // scene (global memory; small scenes are staged into shared memory by every block)
     const SrtNode* nodes;
     const SrtTri* tris;  // leaf order
+    const SrtTriFast* fast;  // leaf order, conservative pre-test records
     const SrtMaterial* mats;
     const float* cie;    // x[95] y[95] z[95]
     const float* bg;     // background spectrum [95]
@@ -36,24 +37,17 @@ struct WaveParams {
     uint32_t* sidx;  // samples started
     float* acc;      // film: XYZ sums, 3 planes of `plane` floats, full-image raster
     size_t plane;
-    // queues (ping-pong): regenerate queue + 3 material segments of capacity nslots each
-    const uint32_t* qr_in;
-    const uint32_t* qm_in;
-    uint32_t* qr_out;
-    uint32_t* qm_out;
-    const uint32_t* cnt_in;  // [0] regen, [1] lambertian, [2] metallic, [3] dielectric
-    uint32_t* cnt_out;
+    // persistent-block wavefront: slots per block and the shared-memory bytes its queues take
+    uint32_t block_slots, queue_bytes;
     unsigned long long* ray_counter;
 };
 
 struct LaunchTable {
-    size_t (*smem_bytes)(const WaveParams&);
+    size_t (*smem_bytes)(const WaveParams&, int mode);
     cudaError_t (*configure)(size_t smem_bytes);
     void (*init_slots)(const WaveParams&, cudaStream_t);
-    void (*begin_chunk)(const WaveParams&, cudaStream_t);
-    void (*generate)(const WaveParams&, int grid, size_t smem, cudaStream_t);
-    void (*shade)(const WaveParams&, int grid, size_t smem, cudaStream_t);
-    void (*megakernel)(const WaveParams&, int grid, size_t smem, cudaStream_t);
+    void (*wavefront)(const WaveParams&, int mode, int grid, size_t smem, cudaStream_t);
+    void (*megakernel)(const WaveParams&, int mode, int grid, size_t smem, cudaStream_t);
     void (*resolve)(const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, float* rgb,
                     float* xyz, cudaStream_t);
     void (*trace_rays)(const WaveParams&, uint32_t n, const float* o, const float* d, const uint32_t* sorted_idx, float* t_out, int32_t* tri_out,

@@ -192,6 +192,9 @@ float* srt_rm_device_film(srt_render_manager* h) { return h->rm->device_film(); 
 int srt_rm_resolve_film(srt_render_manager* h) { return h->rm->resolve_film(); }
 int srt_rm_get_stats(const srt_render_manager* h, srt_stats* out) { return out ? h->rm->stats(out) : SRT_ERR_ARG; }
 
+double srt_measure_fp32_tflops(void) { return measure_fp32_tflops(); }
+double srt_measure_copy_gbs(uint32_t mbytes) { return measure_copy_gbs(mbytes); }
+
 int srt_write_ppm(const char* path, const float* r, const float* g, const float* b, uint32_t w, uint32_t h) { return write_ppm(path, r, g, b, w, h) ? SRT_OK : SRT_ERR_ARG; }
 int srt_write_bmp(const char* path, const float* r, const float* g, const float* b, uint32_t w, uint32_t h) { return write_bmp(path, r, g, b, w, h) ? SRT_OK : SRT_ERR_ARG; }
 

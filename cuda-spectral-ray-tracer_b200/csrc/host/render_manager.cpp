@@ -48,6 +48,10 @@ int RenderManager::set_option(int opt, int value) {
         case SRT_OPT_RANK: cfg_.rank = value; break;
         case SRT_OPT_WORLD: cfg_.world = value; break;
         case SRT_OPT_REGEN_LOOP: cfg_.regen_loop = value; break;
+        case SRT_OPT_KERNEL_TIMING: cfg_.kernel_timing = value ? 1 : 0; break;
+        case SRT_OPT_TAIL_THRESHOLD: cfg_.tail_threshold = value; break;
+        case SRT_OPT_TRAVERSAL: cfg_.traversal = value; break;
+        case SRT_OPT_BLOCK_SLOTS: cfg_.block_slots = value; break;
         default: set_error("unknown option"); return SRT_ERR_ARG;
     }
     return SRT_OK;

@@ -134,7 +134,9 @@ struct RenderConfig {
     srt_camera cam;
     unsigned spp = 1, bounce_limit = 10;
     unsigned chunk_w = 0, chunk_h = 0;   // nominal chunk geometry (seeds depend on it, reference Q15)
-    int fp_strict = 0, pipeline = 0, regen_loop = 4;
+    int fp_strict = 0, pipeline = 0, regen_loop = 4, kernel_timing = 0, tail_threshold = 0;
+    int block_slots = 1024;  // pixel slots owned by one persistent wavefront block
+    int traversal = 0;  // 0 auto (wide leaf when <= 64 triangles), 1 force LBVH walk in shared memory, 3 force LBVH walk in global memory
     int tile_w = 32, tile_h = 32, rank = 0, world = 1;
     float bg_spectrum[SRT_NS];
     int bg_is_zero = 1;
@@ -150,6 +152,8 @@ float* device_renderer_film(DeviceRenderer*);
 void device_renderer_stats(const DeviceRenderer*, srt_stats* s);
 
 uint64_t kernel_launches();
+double measure_fp32_tflops();
+double measure_copy_gbs(uint32_t mbytes);
 bool cuda_select_device(int dev);
 int cuda_device_count();
 

@@ -39,10 +39,12 @@ class MaterialDesc(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("wavefront_iterations", C.c_uint64), ("render_ms", C.c_double), ("lbvh_ms", C.c_double)]
+                ("wavefront_iterations", C.c_uint64), ("render_ms", C.c_double), ("lbvh_ms", C.c_double),
+                ("generate_ms", C.c_double), ("shade_ms", C.c_double), ("tail_ms", C.c_double), ("other_ms", C.c_double),
+                ("generate_launches", C.c_uint64), ("shade_launches", C.c_uint64), ("tail_launches", C.c_uint64)]
 
 
-OPT_FP_MODE, OPT_PIPELINE, OPT_TILE_W, OPT_TILE_H, OPT_RANK, OPT_WORLD, OPT_REGEN_LOOP = 1, 2, 3, 4, 5, 6, 7
+OPT_FP_MODE, OPT_PIPELINE, OPT_TILE_W, OPT_TILE_H, OPT_RANK, OPT_WORLD, OPT_REGEN_LOOP, OPT_KERNEL_TIMING, OPT_TAIL_THRESHOLD, OPT_TRAVERSAL, OPT_BLOCK_SLOTS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
 MAT_LAMBERTIAN, MAT_METALLIC, MAT_DIELECTRIC, MAT_EMISSIVE = 0, 1, 2, 4
 
 # every symbol include/srt.h declares: (name, restype, argtypes)
@@ -97,6 +99,8 @@ _SIGS = [
     ("srt_rm_device_film", _P, [_P]),
     ("srt_rm_resolve_film", C.c_int, [_P]),
     ("srt_rm_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
+    ("srt_measure_fp32_tflops", C.c_double, []),
+    ("srt_measure_copy_gbs", C.c_double, [C.c_uint32]),
     ("srt_write_ppm", C.c_int, [C.c_char_p, _P, _P, _P, C.c_uint32, C.c_uint32]),
     ("srt_write_bmp", C.c_int, [C.c_char_p, _P, _P, _P, C.c_uint32, C.c_uint32]),
 ]
@@ -322,7 +326,8 @@ class RenderManager:
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
 
-def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=False, pipeline=0, scene=None, tiles=None, regen_loop=None):
+def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=False, pipeline=0, scene=None, tiles=None, regen_loop=None,
+           kernel_timing=False, tail_threshold=None, traversal=None, block_slots=None):
     """One-call helper: returns (rgb[3,h,w] float32 0..255, xyz[3,h,w] float32, stats dict)."""
     sc = scene if scene is not None else Scene(scene_id)
     cam = sc.camera(w, h)
@@ -333,6 +338,14 @@ def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=Fals
     rm.set_option(OPT_PIPELINE, pipeline)
     if regen_loop is not None:
         rm.set_option(OPT_REGEN_LOOP, regen_loop)
+    if kernel_timing:
+        rm.set_option(OPT_KERNEL_TIMING, 1)
+    if tail_threshold is not None:
+        rm.set_option(OPT_TAIL_THRESHOLD, tail_threshold)
+    if traversal is not None:
+        rm.set_option(OPT_TRAVERSAL, traversal)
+    if block_slots is not None:
+        rm.set_option(OPT_BLOCK_SLOTS, block_slots)
     if tiles is not None:
         tw, th, rank, world = tiles
         rm.set_option(OPT_TILE_W, tw); rm.set_option(OPT_TILE_H, th); rm.set_option(OPT_RANK, rank); rm.set_option(OPT_WORLD, world)

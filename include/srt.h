@@ -172,7 +172,12 @@ int srt_rm_render_all(srt_render_manager*);
 #define SRT_OPT_TILE_H 4
 #define SRT_OPT_RANK 5         /* ... this process renders tiles with (tile_id % world) == rank */
 #define SRT_OPT_WORLD 6
-#define SRT_OPT_REGEN_LOOP 7   /* camera-ray regenerations fused per wavefront pass (tuning) */
+#define SRT_OPT_REGEN_LOOP 7   /* camera-ray regenerations a slot may do inside one wavefront pass (tuning) */
+#define SRT_OPT_KERNEL_TIMING 8 /* 1 = bracket every kernel launch with CUDA events (per-kernel totals in srt_stats) */
+#define SRT_OPT_TAIL_THRESHOLD 9 /* (unused since the persistent-block wavefront; kept for ABI stability) */
+#define SRT_OPT_BLOCK_SLOTS 11   /* pixel slots owned by one persistent wavefront block (default 1024) */
+#define SRT_OPT_TRAVERSAL 10     /* 0 auto (wide-leaf closest hit when the scene has <= 64 triangles), 1 force the LBVH walk
+                                    (scene in shared memory), 3 force the LBVH walk with the scene in global memory */
 int srt_rm_set_option(srt_render_manager*, int option, int value);
 /* pre-tonemap film of the whole image: 3 raster planes of XYZ (mean over spp) */
 int srt_rm_get_xyz(srt_render_manager*, float* xyz);
@@ -185,8 +190,17 @@ typedef struct {
     uint64_t samples, rays, kernel_launches, wavefront_iterations;
     double render_ms;   /* CUDA-event time of all step() kernels */
     double lbvh_ms;     /* last LBVH build of the scene */
+    /* filled when SRT_OPT_KERNEL_TIMING is on: summed CUDA-event durations and launch counts */
+    double generate_ms, shade_ms, tail_ms, other_ms;
+    uint64_t generate_launches, shade_launches, tail_launches;
 } srt_stats;
 int srt_rm_get_stats(const srt_render_manager*, srt_stats* out);
+
+/* measured FP32 FMA issue peak of the current device in TFLOP/s (dependent-free FFMA chains on every
+ * SM, CUDA-event timed): the roofline denominator for the instruction-bound render kernels */
+double srt_measure_fp32_tflops(void);
+/* measured device-to-device copy bandwidth in GB/s (read + write bytes) over `mbytes` MiB */
+double srt_measure_copy_gbs(uint32_t mbytes);
 
 /* ------------------------------------------------------------------ output (io/save_image.cpp:8-13, io/io.cuh:10-23) */
 int srt_write_ppm(const char* path, const float* r, const float* g, const float* b, uint32_t w, uint32_t h);

@@ -107,6 +107,17 @@ def test_pipelines_bit_identical(srt, strict):
     assert np.array_equal(a[0], b[0])
 
 
+@pytest.mark.parametrize("scene", [0, 1, 2])
+def test_wide_leaf_equals_lbvh_walk(srt, scene):
+    """the <=64-triangle wide-leaf closest hit (conservative pre-test + exact re-test) must give the
+    same film, bit for bit, as walking the LBVH (shared or global memory) with exact tests only"""
+    a = srt.render(scene_id=scene, w=320, h=180, spp=8, bounce=10, strict=True, traversal=0)[1]
+    b = srt.render(scene_id=scene, w=320, h=180, spp=8, bounce=10, strict=True, traversal=1)[1]
+    c = srt.render(scene_id=scene, w=320, h=180, spp=8, bounce=10, strict=True, traversal=3)[1]
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.array_equal(b.view(np.uint32), c.view(np.uint32))
+
+
 @pytest.mark.parametrize("scene", [0, 1])
 def test_chunked_render(srt, scene, golden):
     """-xc 48 -yc 27 on 96x54: RNG state carried per thread slot across chunks (reference Q12/Q15)."""
