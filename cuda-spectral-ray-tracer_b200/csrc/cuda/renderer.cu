@@ -32,6 +32,21 @@ int sm_count() {
 constexpr size_t kSmemSceneLimit = 96 * 1024;  // scenes whose nodes+tris+materials fit are staged in shared memory
 }  // namespace
 
+// One grow-only pinned staging buffer per process: page-locking tens of MB costs milliseconds, far
+// more than the copy it serves, so renderers share it (resolve calls are serialised by the caller).
+static float* pinned_staging(size_t bytes) {
+    static float* buf = nullptr;
+    static size_t cap = 0;
+    if (bytes > cap) {
+        if (buf) cudaFreeHost(buf);
+        buf = nullptr;
+        cap = 0;
+        if (!cuda_ok(cudaMallocHost((void**)&buf, bytes), "cudaMallocHost(staging)", __FILE__, __LINE__)) return nullptr;
+        cap = bytes;
+    }
+    return buf;
+}
+
 struct DeviceRenderer {
     const DeviceScene* scene = nullptr;
     RenderConfig cfg;
@@ -91,7 +106,6 @@ void device_renderer_destroy(DeviceRenderer* r) {
     if (!r) return;
     cudaFree(r->d_cie); cudaFree(r->d_bg); cudaFree(r->d_rays); cudaFree(r->d_rgb); cudaFree(r->d_xyz);
     cudaFree(r->P.R0); cudaFree(r->P.R1); cudaFree(r->P.P0); cudaFree(r->P.P1); cudaFree(r->P.G0); cudaFree(r->P.G1); cudaFree(r->P.sidx); cudaFree(r->P.acc);
-    if (r->h_stage) cudaFreeHost(r->h_stage);
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
@@ -141,7 +155,8 @@ static bool renderer_setup(DeviceRenderer* r) {
     SRT_CUDA(cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), r->stream));
     SRT_CUDA(cudaMalloc((void**)&r->d_rgb, 3 * ns * sizeof(float)));
     SRT_CUDA(cudaMalloc((void**)&r->d_xyz, 3 * ns * sizeof(float)));
-    SRT_CUDA(cudaMallocHost((void**)&r->h_stage, 6 * ns * sizeof(float)));
+    r->h_stage = pinned_staging(6 * ns * sizeof(float));
+    if (!r->h_stage) return false;
     std::vector<float> cie(3 * SRT_NS);
     for (int k = 0; k < 3; k++) memcpy(cie.data() + k * SRT_NS, cie_table(k), SRT_NS * sizeof(float));
     SRT_CUDA(cudaMalloc((void**)&r->d_cie, cie.size() * sizeof(float)));
@@ -250,6 +265,17 @@ bool device_renderer_resolve(DeviceRenderer* r, unsigned off_x, unsigned off_y, 
 }
 
 float* device_renderer_film(DeviceRenderer* r) { return r->P.acc; }
+
+bool device_renderer_reset(DeviceRenderer* r) {  // back to the state right after creation: empty film, unseeded RNG slots
+    SRT_CUDA(cudaMemsetAsync(r->P.acc, 0, 3 * r->P.plane * sizeof(float), r->stream));
+    SRT_CUDA(cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), r->stream));
+    SRT_CUDA(cudaStreamSynchronize(r->stream));
+    r->slots_inited = false;
+    r->samples = r->rays = 0;
+    r->render_ms = 0;
+    for (int k = 0; k < 4; k++) { r->cat_ms[k] = 0; r->cat_launches[k] = 0; }
+    return true;
+}
 
 void device_renderer_stats(const DeviceRenderer* r, srt_stats* s) {
     s->samples = r->samples;

@@ -190,6 +190,7 @@ int srt_rm_set_option(srt_render_manager* h, int opt, int v) { return h->rm->set
 int srt_rm_get_xyz(srt_render_manager* h, float* xyz) { return xyz ? h->rm->get_xyz(xyz) : SRT_ERR_ARG; }
 float* srt_rm_device_film(srt_render_manager* h) { return h->rm->device_film(); }
 int srt_rm_resolve_film(srt_render_manager* h) { return h->rm->resolve_film(); }
+int srt_rm_restart(srt_render_manager* h) { return h->rm->restart(); }
 int srt_rm_get_stats(const srt_render_manager* h, srt_stats* out) { return out ? h->rm->stats(out) : SRT_ERR_ARG; }
 
 double srt_measure_fp32_tflops(void) { return measure_fp32_tflops(); }

@@ -175,6 +175,18 @@ int RenderManager::resolve_film() {
     if (!dev_) { set_error("render manager: not initialised"); return SRT_ERR_STATE; }
     return device_renderer_resolve(dev_, 0, 0, cam_.width, cam_.height, fb_r_, fb_g_, fb_b_, xyz_.data(), cam_.width, cam_.height) ? SRT_OK : SRT_ERR_CUDA;
 }
+int RenderManager::restart() {  // make the manager renderable again from its first chunk (same seeds, empty film)
+    end_render();
+    if (!device_inited_ || !dev_) { set_error("render manager: not initialised"); return SRT_ERR_STATE; }
+    if (!device_renderer_reset(dev_)) return SRT_ERR_CUDA;
+    i_ = 0;
+    off_x_ = off_y_ = 0;
+    next_write_ = next_read_ = 0;
+    slots_[0] = Slot();
+    slots_[1] = Slot();
+    done_ = true;
+    return SRT_OK;
+}
 int RenderManager::stats(srt_stats* s) const {
     if (!dev_) { set_error("render manager: not initialised"); return SRT_ERR_STATE; }
     device_renderer_stats(dev_, s);

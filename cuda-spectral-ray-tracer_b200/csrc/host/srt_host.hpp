@@ -149,6 +149,7 @@ bool device_renderer_render_chunk(DeviceRenderer*, unsigned off_x, unsigned off_
 bool device_renderer_resolve(DeviceRenderer*, unsigned off_x, unsigned off_y, unsigned w, unsigned h, float* r, float* g,
                              float* b, float* xyz, unsigned img_w, unsigned img_h);
 float* device_renderer_film(DeviceRenderer*);
+bool device_renderer_reset(DeviceRenderer*);
 void device_renderer_stats(const DeviceRenderer*, srt_stats* s);
 
 uint64_t kernel_launches();
@@ -182,6 +183,7 @@ public:
     int get_xyz(float* xyz);
     float* device_film();
     int resolve_film();
+    int restart();
     int stats(srt_stats* s) const;
     unsigned width() const { return cam_.width; }
     unsigned height() const { return cam_.height; }

@@ -98,6 +98,7 @@ _SIGS = [
     ("srt_rm_get_xyz", C.c_int, [_P, _P]),
     ("srt_rm_device_film", _P, [_P]),
     ("srt_rm_resolve_film", C.c_int, [_P]),
+    ("srt_rm_restart", C.c_int, [_P]),
     ("srt_rm_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("srt_measure_fp32_tflops", C.c_double, []),
     ("srt_measure_copy_gbs", C.c_double, [C.c_uint32]),
@@ -314,6 +315,7 @@ class RenderManager:
     def render_all(self): _check(lib().srt_rm_render_all(self.h))
     def device_film(self): return lib().srt_rm_device_film(self.h)
     def resolve_film(self): _check(lib().srt_rm_resolve_film(self.h))
+    def restart(self): _check(lib().srt_rm_restart(self.h))
 
     def xyz(self):
         out = np.zeros(3 * self.cam.width * self.cam.height, np.float32)

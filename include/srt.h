@@ -186,6 +186,9 @@ int srt_rm_get_xyz(srt_render_manager*, float* xyz);
 float* srt_rm_device_film(srt_render_manager*);
 /* tonemaps the (possibly reduced) device film into the caller's frame buffer and XYZ planes */
 int srt_rm_resolve_film(srt_render_manager*);
+/* rewinds the manager to its first chunk with an empty film and freshly seeded RNG slots, so the
+ * same image can be rendered again (the reference's render_manager is one-shot) */
+int srt_rm_restart(srt_render_manager*);
 typedef struct {
     uint64_t samples, rays, kernel_launches, wavefront_iterations;
     double render_ms;   /* CUDA-event time of all step() kernels */
