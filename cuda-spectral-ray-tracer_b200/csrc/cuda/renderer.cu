@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstring>
 #include <vector>
+#include <mutex>
 
 namespace srt {
 
@@ -31,6 +32,41 @@ int sm_count() {
 }
 constexpr size_t kSmemSceneLimit = 96 * 1024;  // scenes whose nodes+tris+materials fit are staged in shared memory
 }  // namespace
+
+// Process-wide cache of large device buffers.  cudaMalloc/cudaFree of the ~250 MB of per-pixel state
+// cost tens of milliseconds per render manager (more than the render itself at 1080p); a caller that
+// renders frame after frame gets the previous frame's buffers back instead.
+namespace {
+struct PoolBlock { void* ptr; size_t bytes; bool used; };
+std::mutex g_pool_mu;
+std::vector<PoolBlock> g_pool;
+}  // namespace
+static bool pool_alloc(void** out, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    PoolBlock* best = nullptr;
+    for (PoolBlock& b : g_pool)
+        if (!b.used && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 && (!best || b.bytes < best->bytes)) best = &b;
+    if (best) { best->used = true; *out = best->ptr; return true; }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {  // out of memory: drop the cache and retry once
+        cudaGetLastError();
+        for (size_t i = 0; i < g_pool.size();) {
+            if (!g_pool[i].used) { cudaFree(g_pool[i].ptr); g_pool.erase(g_pool.begin() + i); } else i++;
+        }
+        if (!cuda_ok(cudaMalloc(&p, bytes), "cudaMalloc(pool)", __FILE__, __LINE__)) return false;
+    }
+    g_pool.push_back({p, bytes, true});
+    *out = p;
+    return true;
+}
+static void pool_free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (PoolBlock& b : g_pool)
+        if (b.ptr == p) { b.used = false; return; }
+    cudaFree(p);
+}
 
 // One grow-only pinned staging buffer per process: page-locking tens of MB costs milliseconds, far
 // more than the copy it serves, so renderers share it (resolve calls are serialised by the caller).
@@ -104,8 +140,8 @@ void collect_kernel_times(DeviceRenderer* r) {
 
 void device_renderer_destroy(DeviceRenderer* r) {
     if (!r) return;
-    cudaFree(r->d_cie); cudaFree(r->d_bg); cudaFree(r->d_rays); cudaFree(r->d_rgb); cudaFree(r->d_xyz);
-    cudaFree(r->P.R0); cudaFree(r->P.R1); cudaFree(r->P.P0); cudaFree(r->P.P1); cudaFree(r->P.G0); cudaFree(r->P.G1); cudaFree(r->P.sidx); cudaFree(r->P.acc);
+    cudaFree(r->d_cie); cudaFree(r->d_bg); cudaFree(r->d_rays); pool_free(r->d_rgb); pool_free(r->d_xyz);
+    pool_free(r->P.R0); pool_free(r->P.R1); pool_free(r->P.P0); pool_free(r->P.P1); pool_free(r->P.G0); pool_free(r->P.G1); pool_free(r->P.sidx); pool_free(r->P.acc);
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
@@ -142,19 +178,19 @@ static bool renderer_setup(DeviceRenderer* r) {
     SRT_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     SRT_CUDA(cudaEventCreate(&r->ev0));
     SRT_CUDA(cudaEventCreate(&r->ev1));
-    SRT_CUDA(cudaMalloc((void**)&P.R0, ns * sizeof(float4)));
-    SRT_CUDA(cudaMalloc((void**)&P.R1, ns * sizeof(float4)));
-    SRT_CUDA(cudaMalloc((void**)&P.P0, ns * sizeof(float4)));
-    SRT_CUDA(cudaMalloc((void**)&P.P1, ns * sizeof(float4)));
-    SRT_CUDA(cudaMalloc((void**)&P.G0, ns * sizeof(uint4)));
-    SRT_CUDA(cudaMalloc((void**)&P.G1, ns * sizeof(uint2)));
-    SRT_CUDA(cudaMalloc((void**)&P.sidx, ns * sizeof(uint32_t)));
-    SRT_CUDA(cudaMalloc((void**)&P.acc, 3 * P.plane * sizeof(float)));
+    if (!pool_alloc((void**)&P.R0, ns * sizeof(float4))) return false;
+    if (!pool_alloc((void**)&P.R1, ns * sizeof(float4))) return false;
+    if (!pool_alloc((void**)&P.P0, ns * sizeof(float4))) return false;
+    if (!pool_alloc((void**)&P.P1, ns * sizeof(float4))) return false;
+    if (!pool_alloc((void**)&P.G0, ns * sizeof(uint4))) return false;
+    if (!pool_alloc((void**)&P.G1, ns * sizeof(uint2))) return false;
+    if (!pool_alloc((void**)&P.sidx, ns * sizeof(uint32_t))) return false;
+    if (!pool_alloc((void**)&P.acc, 3 * P.plane * sizeof(float))) return false;
     SRT_CUDA(cudaMemsetAsync(P.acc, 0, 3 * P.plane * sizeof(float), r->stream));
     SRT_CUDA(cudaMalloc((void**)&r->d_rays, sizeof(unsigned long long)));
     SRT_CUDA(cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), r->stream));
-    SRT_CUDA(cudaMalloc((void**)&r->d_rgb, 3 * ns * sizeof(float)));
-    SRT_CUDA(cudaMalloc((void**)&r->d_xyz, 3 * ns * sizeof(float)));
+    if (!pool_alloc((void**)&r->d_rgb, 3 * ns * sizeof(float))) return false;
+    if (!pool_alloc((void**)&r->d_xyz, 3 * ns * sizeof(float))) return false;
     r->h_stage = pinned_staging(6 * ns * sizeof(float));
     if (!r->h_stage) return false;
     std::vector<float> cie(3 * SRT_NS);
