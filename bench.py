@@ -177,7 +177,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-spp", type=int, default=4, help="spp of the bounded CPU sample")
     ap.add_argument("--strict", action="store_true", help="strict FP mode (-fmad=false kernels)")
-    ap.add_argument("--block-slots", type=int, default=0)
+    ap.add_argument("--tile-w", type=int, default=32)
+    ap.add_argument("--tile-h", type=int, default=32)
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -213,10 +214,9 @@ def main():
     rm.init_renderer(depth, spp)
     rm.set_option(S.OPT_FP_MODE, 1 if a.strict else 0)
     rm.set_option(S.OPT_KERNEL_TIMING, 1)
-    if a.block_slots:
-        rm.set_option(S.OPT_BLOCK_SLOTS, a.block_slots)
+    rm.set_option(S.OPT_TILE_W, a.tile_w); rm.set_option(S.OPT_TILE_H, a.tile_h)
     if world > 1:
-        rm.set_option(S.OPT_TILE_W, 32); rm.set_option(S.OPT_TILE_H, 32); rm.set_option(S.OPT_RANK, rank); rm.set_option(S.OPT_WORLD, world)
+        rm.set_option(S.OPT_RANK, rank); rm.set_option(S.OPT_WORLD, world)
     rm.init_device_params(0, 0)
     film = None
     if world > 1:
@@ -279,10 +279,9 @@ def main():
         rm2 = S.RenderManager(sc2, sc2.camera(w, h), fb2)
         rm2.init_renderer(depth, spp)
         rm2.set_option(S.OPT_FP_MODE, 1 if a.strict else 0)
-        if a.block_slots:
-            rm2.set_option(S.OPT_BLOCK_SLOTS, a.block_slots)
+        rm2.set_option(S.OPT_TILE_W, a.tile_w); rm2.set_option(S.OPT_TILE_H, a.tile_h)
         if world > 1:
-            rm2.set_option(S.OPT_TILE_W, 32); rm2.set_option(S.OPT_TILE_H, 32); rm2.set_option(S.OPT_RANK, rank); rm2.set_option(S.OPT_WORLD, world)
+            rm2.set_option(S.OPT_RANK, rank); rm2.set_option(S.OPT_WORLD, world)
         rm2.init_device_params(0, 0)
         if world > 1:
             while rm2.step():
@@ -366,7 +365,7 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl_name, "scene": scene_id, "width": w, "height": h, "spp": spp, "depth": depth,
                    "fp_mode": "strict(-fmad=false)" if a.strict else "fast(fma, as the reference's nvcc build)",
-                   "parallelism": "tiles32x32-interleaved x%d + nccl film reduce" % world if world > 1 else "single gpu",
+                   "parallelism": "tiles%dx%d-interleaved x%d + nccl film reduce" % (a.tile_w, a.tile_h, world) if world > 1 else "single gpu",
                    "l2": "working set (per-pixel state 216 MB + film) exceeds the 126 MB L2 and is re-initialised every step"},
         "clocks": clocks,
         "e2e": {"value": total_samples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},

@@ -16,14 +16,14 @@
 // ---- device triangle, 48 B = 3 x 16-B vectors ------------------------------------------
 // q0 = plane (nx, ny, nz, D)
 // q1 = (w0, h0, w1, h1)   projected vertices on the triangle's 2-D test plane
-// q2 = (w2, h2, bits, 0)  bits: [15:0] material index, [16] clockwise, [18:17] w axis,
+// q2 = (w2, h2, bits, prio)  prio = rank in the reference's test order (equal-t tie-break); bits: [15:0] material index, [16] clockwise, [18:17] w axis,
 //                         [20:19] h axis, [23:21] material type
 struct alignas(16) SrtTri {
     float nx, ny, nz, D;
     float w0, h0, w1, h1;
     float w2, h2;
     uint32_t bits;
-    uint32_t pad;
+    uint32_t prio;
 };
 #define SRT_TRI_MAT(bits) ((bits) & 0xFFFFu)
 #define SRT_TRI_CW(bits) (((bits) >> 16) & 1u)
@@ -31,16 +31,18 @@ struct alignas(16) SrtTri {
 #define SRT_TRI_HAX(bits) (((bits) >> 19) & 3u)
 #define SRT_TRI_MTYPE(bits) (((bits) >> 21) & 7u)
 
-// ---- conservative pre-test record, 64 B = 4 x 16-B vectors (leaf order, same index as SrtTri) ----
-// q0 = plane (nx, ny, nz, D); q1 = (A.xyz, a_w), q2 = (B.xyz, b_w): barycentrics u = A.p + a_w, v = B.p + b_w
-// q3 = (eps0, eps1, tol0, tol1): slack on u,v = eps0 + eps1*|o|_1, slack on the plane distance = tol0 + tol1*|o|_1
-struct alignas(16) SrtTriFast {
+#define SRT_FLAT_MAX_TRIS 64  // scenes up to this size are one wide leaf: no tree walk at all
+
+// ---- wide-leaf pre-test unit, 64 B: one triangle or one parallelogram pair (host/flat_leaf.cpp) ----
+// q0 = plane; q1 = (A.xyz, a_w + eps); q2 = (B.xyz, b_w + eps); q3 = (c1, c2, c3, tol)
+// unit u covers flat triangle positions 2u (first half) and 2u+1 (second half, if c2 >= 0)
+struct alignas(16) SrtFlatUnit {
     float nx, ny, nz, D;
     float ax, ay, az, aw;
     float bx, by, bz, bw;
-    float eps0, eps1, tol0, tol1;
+    float c1, c2, c3, tol;
 };
-#define SRT_FLAT_MAX_TRIS 64  // scenes up to this size are one wide leaf: no tree walk at all
+#define SRT_FLAT_MAX_UNITS 32
 
 // ---- device BVH node, 64 B = 4 x 16-B vectors (both child boxes in the parent) -----------
 // q0 = (c0.xmin, c0.xmax, c0.ymin, c0.ymax)   q1 = (c1.xmin, c1.xmax, c1.ymin, c1.ymax)

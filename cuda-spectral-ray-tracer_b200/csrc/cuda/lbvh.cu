@@ -66,7 +66,11 @@ struct DeviceScene {
     uint32_t* visit = nullptr;    // n-1 refit arrival flags
     SrtNode* nodes = nullptr;     // n-1 traversal nodes
     SrtTri* tris = nullptr;       // n, LEAF order
-    SrtTriFast* fast = nullptr;   // n, LEAF order: conservative pre-test records
+    // wide leaf (scenes of <= 32 pre-test units): flat-order triangles + units, built on the host
+    SrtFlatUnit* flat_units = nullptr;
+    SrtTri* flat_tris = nullptr;
+    uint32_t n_units = 0;
+    double origin_l1_bound = 0;
     uint32_t tiles = 0;
     cudaEvent_t ev[6];
     double last_build_ms = 0;
@@ -377,47 +381,11 @@ __global__ void __launch_bounds__(256) k_refit(int n, const uint32_t* __restrict
 // ---- emit traversal layout -------------------------------------------------------------------
 __device__ __forceinline__ float widen_lo(float v) { return v - fabsf(v) * 2.4e-7f; }
 __device__ __forceinline__ float widen_hi(float v) { return v + fabsf(v) * 2.4e-7f; }
-// Conservative pre-test record of one triangle: plane + affine maps to barycentric coordinates
-// (computed in double) + error budgets.  A ray/triangle pair the pre-test rejects is guaranteed to
-// be rejected by the exact reference arithmetic too (tri_test in trace_impl.cuh); everything else
-// is re-tested exactly.  Error model: |p_approx - p| <= 2e-6 (R_scene + 2|o|_1) for true hits.
-__device__ void make_fast_record(const float* __restrict__ v, const SrtTri& T, float scene_radius, SrtTriFast& F) {
-    const double e1[3] = {(double)v[3] - v[0], (double)v[4] - v[1], (double)v[5] - v[2]};
-    const double e2[3] = {(double)v[6] - v[0], (double)v[7] - v[1], (double)v[8] - v[2]};
-    const double N[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-    const double nn = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
-    double A[3] = {0, 0, 0}, B[3] = {0, 0, 0};
-    if (nn > 0) {
-        A[0] = (e2[1] * N[2] - e2[2] * N[1]) / nn; A[1] = (e2[2] * N[0] - e2[0] * N[2]) / nn; A[2] = (e2[0] * N[1] - e2[1] * N[0]) / nn;
-        B[0] = (N[1] * e1[2] - N[2] * e1[1]) / nn; B[1] = (N[2] * e1[0] - N[0] * e1[2]) / nn; B[2] = (N[0] * e1[1] - N[1] * e1[0]) / nn;
-    }
-    F.nx = T.nx; F.ny = T.ny; F.nz = T.nz; F.D = T.D;
-    F.ax = (float)A[0]; F.ay = (float)A[1]; F.az = (float)A[2]; F.aw = (float)-(A[0] * v[0] + A[1] * v[1] + A[2] * v[2]);
-    F.bx = (float)B[0]; F.by = (float)B[1]; F.bz = (float)B[2]; F.bw = (float)-(B[0] * v[0] + B[1] * v[1] + B[2] * v[2]);
-    const float l1 = (float)(fabs(A[0]) + fabs(A[1]) + fabs(A[2]) + fabs(B[0]) + fabs(B[1]) + fabs(B[2]));
-    const float n1 = fabsf(T.nx) + fabsf(T.ny) + fabsf(T.nz);
-    F.eps1 = 16.f * 2e-6f * 2.0f * l1;                         // per unit of |o|_1
-    F.eps0 = 1e-4f + 16.f * 2e-6f * scene_radius * l1 + 4e-6f * (fabsf(F.aw) + fabsf(F.bw));
-    F.tol1 = 8e-6f * n1;
-    F.tol0 = 8e-6f * (fabsf(T.D) + 1e-3f);
-}
-
 __global__ void __launch_bounds__(256) k_emit(int n, const uint32_t* __restrict__ sorted_idx, const int32_t* __restrict__ left,
                                               const int32_t* __restrict__ right, const float* __restrict__ node_boxes,
-                                              const SrtTri* __restrict__ tris_in, const float* __restrict__ verts, const float* __restrict__ scene_box,
-                                              SrtNode* __restrict__ nodes, SrtTri* __restrict__ tris, SrtTriFast* __restrict__ fast) {
+                                              const SrtTri* __restrict__ tris_in, SrtNode* __restrict__ nodes, SrtTri* __restrict__ tris) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const uint32_t src = sorted_idx[i];
-        const SrtTri T = tris_in[src];
-        tris[i] = T;
-        float radius = 0.f;
-#pragma unroll
-        for (int c = 0; c < 6; c++) radius = fmaxf(radius, fabsf(scene_box[c]));
-        SrtTriFast F;
-        make_fast_record(verts + 9ull * src, T, 3.0f * radius, F);
-        fast[i] = F;
-    }
+    if (i < n) tris[i] = tris_in[sorted_idx[i]];
     if (i >= n - 1) return;
     const int L = left[i], R = right[i];
     const float* a = node_boxes + 6ull * L;
@@ -438,7 +406,7 @@ template <class T> static bool dalloc(T*& p, size_t count) {
     return true;
 }
 
-DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::vector<HostMaterial>& mats) {
+DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::vector<HostMaterial>& mats, double origin_l1_bound) {
     if (cuda_device_count() == 0) { set_error("libsrt: no CUDA device available (the product has no CPU fallback)"); return nullptr; }
     auto* s = new DeviceScene();
     s->n = (uint32_t)tris.size();
@@ -453,10 +421,11 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
         for (int k = 0; k < 3; k++) { dm[m].sellB[k] = mats[m].B[k]; dm[m].sellC[k] = mats[m].C[k]; }
         dm[m].type = mats[m].type;
     }
+    const std::vector<uint32_t> prio = reference_test_order(tris);
     for (uint32_t i = 0; i < n; i++) {
         for (int k = 0; k < 3; k++) { verts[9ull * i + 3 * k] = tris[i].v[k].x; verts[9ull * i + 3 * k + 1] = tris[i].v[k].y; verts[9ull * i + 3 * k + 2] = tris[i].v[k].z; }
         const uint32_t mt = tris[i].mat < mats.size() ? mats[tris[i].mat].type : SRT_LAMBERTIAN;
-        packed[i] = tris[i].pack(mt);
+        packed[i] = tris[i].pack(mt, prio[i]);
     }
     s->tiles = (n + SORT_TILE - 1) / SORT_TILE;
     bool ok = dalloc(s->verts, 9ull * n) && dalloc(s->tris_in, n) && dalloc(s->mats, mats.size()) && dalloc(s->leaf_boxes, 6ull * n) &&
@@ -464,7 +433,7 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
               dalloc(s->vals[0], n) && dalloc(s->vals[1], n) && dalloc(s->hist, SORT_PASSES * RADIX) &&
               dalloc(s->lookback, (size_t)SORT_PASSES * (s->tiles ? s->tiles : 1) * RADIX) && dalloc(s->tile_counter, SORT_PASSES) &&
               dalloc(s->left, n) && dalloc(s->right, n) && dalloc(s->parent, 2ull * n) && dalloc(s->node_boxes, 12ull * n) && dalloc(s->visit, n) &&
-              dalloc(s->nodes, n) && dalloc(s->tris, n) && dalloc(s->fast, n);
+              dalloc(s->nodes, n) && dalloc(s->tris, n);
     for (auto& e : s->ev) ok = ok && cuda_ok(cudaEventCreate(&e), "cudaEventCreate", __FILE__, __LINE__);
     if (ok && n) {
         ok = cuda_ok(cudaMemcpy(s->verts, verts.data(), verts.size() * sizeof(float), cudaMemcpyHostToDevice), "upload verts", __FILE__, __LINE__) &&
@@ -472,6 +441,14 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
     }
     if (ok && !mats.empty())
         ok = cuda_ok(cudaMemcpy(s->mats, dm.data(), dm.size() * sizeof(SrtMaterial), cudaMemcpyHostToDevice), "upload mats", __FILE__, __LINE__);
+    FlatLeaf flat;
+    s->origin_l1_bound = origin_l1_bound;
+    if (ok && build_flat_leaf(tris, mats, prio, origin_l1_bound, flat)) {
+        s->n_units = (uint32_t)flat.units.size();
+        ok = dalloc(s->flat_units, flat.units.size()) && dalloc(s->flat_tris, flat.tris.size()) &&
+             cuda_ok(cudaMemcpy(s->flat_units, flat.units.data(), flat.units.size() * sizeof(SrtFlatUnit), cudaMemcpyHostToDevice), "upload units", __FILE__, __LINE__) &&
+             cuda_ok(cudaMemcpy(s->flat_tris, flat.tris.data(), flat.tris.size() * sizeof(SrtTri), cudaMemcpyHostToDevice), "upload flat tris", __FILE__, __LINE__);
+    }
     float ms[5];
     if (ok) ok = device_scene_build_lbvh(s, 1, ms);
     if (!ok) { device_scene_destroy(s); return nullptr; }
@@ -483,7 +460,7 @@ void device_scene_destroy(DeviceScene* s) {
     cudaFree(s->verts); cudaFree(s->tris_in); cudaFree(s->mats); cudaFree(s->leaf_boxes); cudaFree(s->centroids); cudaFree(s->scene_box);
     cudaFree(s->codes); cudaFree(s->keys[0]); cudaFree(s->keys[1]); cudaFree(s->vals[0]); cudaFree(s->vals[1]); cudaFree(s->hist);
     cudaFree(s->lookback); cudaFree(s->tile_counter); cudaFree(s->left); cudaFree(s->right); cudaFree(s->parent); cudaFree(s->node_boxes);
-    cudaFree(s->visit); cudaFree(s->nodes); cudaFree(s->tris); cudaFree(s->fast);
+    cudaFree(s->visit); cudaFree(s->nodes); cudaFree(s->tris); cudaFree(s->flat_units); cudaFree(s->flat_tris);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     delete s;
 }
@@ -528,7 +505,7 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
         else SRT_CUDA(cudaMemsetAsync(s->parent, 0xFF, sizeof(int32_t), st));
         SRT_CUDA(cudaEventRecord(s->ev[3], st));
         k_refit<<<grid_n, 256, 0, st>>>((int)n, s->vals[0], s->leaf_boxes, s->left, s->right, s->parent, s->node_boxes, s->visit);
-        k_emit<<<grid_n, 256, 0, st>>>((int)n, s->vals[0], s->left, s->right, s->node_boxes, s->tris_in, s->verts, s->scene_box, s->nodes, s->tris, s->fast);
+        k_emit<<<grid_n, 256, 0, st>>>((int)n, s->vals[0], s->left, s->right, s->node_boxes, s->tris_in, s->nodes, s->tris);
         SRT_CUDA(cudaEventRecord(s->ev[4], st));
         count_launch(6 + SORT_PASSES + (n > 1 ? 1 : 0) + 1);
         SRT_CUDA_LAST();
@@ -565,7 +542,10 @@ bool device_scene_download_lbvh(const DeviceScene* s, LbvhDump& o) {
 // accessors for the renderer translation units
 const SrtNode* device_scene_nodes(const DeviceScene* s) { return s->nodes; }
 const SrtTri* device_scene_tris(const DeviceScene* s) { return s->tris; }
-const SrtTriFast* device_scene_fast(const DeviceScene* s) { return s->fast; }
+const SrtFlatUnit* device_scene_flat_units(const DeviceScene* s) { return s->flat_units; }
+const SrtTri* device_scene_flat_tris(const DeviceScene* s) { return s->flat_tris; }
+uint32_t device_scene_n_units(const DeviceScene* s) { return s->n_units; }
+double device_scene_origin_bound(const DeviceScene* s) { return s->origin_l1_bound; }
 const SrtMaterial* device_scene_mats(const DeviceScene* s) { return s->mats; }
 uint32_t device_scene_ntris(const DeviceScene* s) { return s->n; }
 uint32_t device_scene_nmats(const DeviceScene* s) { return s->n_mats; }

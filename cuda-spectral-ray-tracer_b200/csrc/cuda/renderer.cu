@@ -5,6 +5,7 @@
 #include "trace_params.h"
 #include <algorithm>
 #include <cstring>
+#include <cmath>
 #include <vector>
 #include <mutex>
 
@@ -12,7 +13,10 @@ namespace srt {
 
 const SrtNode* device_scene_nodes(const DeviceScene* s);
 const SrtTri* device_scene_tris(const DeviceScene* s);
-const SrtTriFast* device_scene_fast(const DeviceScene* s);
+const SrtFlatUnit* device_scene_flat_units(const DeviceScene* s);
+const SrtTri* device_scene_flat_tris(const DeviceScene* s);
+uint32_t device_scene_n_units(const DeviceScene* s);
+double device_scene_origin_bound(const DeviceScene* s);
 const SrtMaterial* device_scene_mats(const DeviceScene* s);
 uint32_t device_scene_ntris(const DeviceScene* s);
 uint32_t device_scene_nmats(const DeviceScene* s);
@@ -92,6 +96,8 @@ struct DeviceRenderer {
     // owned device memory
     float* d_cie = nullptr;
     float* d_bg = nullptr;
+    uint32_t* d_tiles = nullptr;
+    std::vector<uint32_t> h_tiles;  // chunk-local tiles this rank owns
     unsigned long long* d_rays = nullptr;
     float* d_rgb = nullptr;         // resolve staging (device), 3 planes of max chunk
     float* d_xyz = nullptr;
@@ -102,6 +108,7 @@ struct DeviceRenderer {
     uint64_t launches = 0, iterations = 0, samples = 0, rays = 0;
     double render_ms = 0;
     bool slots_inited = false;
+    size_t chunk_px = 0;
     // optional per-kernel timing: event pairs tagged with a category (0 generate, 1 shade, 2 tail, 3 other)
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_tag;
@@ -140,7 +147,7 @@ void collect_kernel_times(DeviceRenderer* r) {
 
 void device_renderer_destroy(DeviceRenderer* r) {
     if (!r) return;
-    cudaFree(r->d_cie); cudaFree(r->d_bg); cudaFree(r->d_rays); pool_free(r->d_rgb); pool_free(r->d_xyz);
+    cudaFree(r->d_cie); cudaFree(r->d_bg); cudaFree(r->d_tiles); cudaFree(r->d_rays); pool_free(r->d_rgb); pool_free(r->d_xyz);
     pool_free(r->P.R0); pool_free(r->P.R1); pool_free(r->P.P0); pool_free(r->P.P1); pool_free(r->P.G0); pool_free(r->P.G1); pool_free(r->P.sidx); pool_free(r->P.acc);
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->ev0) cudaEventDestroy(r->ev0);
@@ -154,7 +161,9 @@ static bool renderer_setup(DeviceRenderer* r) {
     WaveParams& P = r->P;
     P.nodes = device_scene_nodes(r->scene);
     P.tris = device_scene_tris(r->scene);
-    P.fast = device_scene_fast(r->scene);
+    P.flat_units = device_scene_flat_units(r->scene);
+    P.flat_tris = device_scene_flat_tris(r->scene);
+    P.n_units = (int)device_scene_n_units(r->scene);
     P.mats = device_scene_mats(r->scene);
     P.n_tris = (int)device_scene_ntris(r->scene);
     P.n_mats = (int)device_scene_nmats(r->scene);
@@ -164,17 +173,25 @@ static bool renderer_setup(DeviceRenderer* r) {
     P.cam.defocus_angle = c.cam.defocus_angle;
     memcpy(P.cam.center, &c.cam.camera_center, 12); memcpy(P.cam.disk_u, &c.cam.defocus_disk_u, 12); memcpy(P.cam.disk_v, &c.cam.defocus_disk_v, 12);
     P.img_w = c.cam.width; P.img_h = c.cam.height;
-    P.slot_w = c.chunk_w;
-    P.nslots = c.chunk_w * c.chunk_h;
+    P.tile_w = (uint32_t)std::max(1, c.tile_w); P.tile_h = (uint32_t)std::max(1, c.tile_h);
+    P.block_slots = P.tile_w * P.tile_h;  // one wavefront block renders one tile
+    if (P.block_slots > 65536 || P.block_slots < 32) { set_error("tile area must be in [32, 65536]"); return false; }
+    P.tiles_x = (c.chunk_w + P.tile_w - 1) / P.tile_w;
+    const uint32_t tiles_y = (c.chunk_h + P.tile_h - 1) / P.tile_h;
+    P.rank = (uint32_t)c.rank; P.world = (uint32_t)std::max(1, c.world);
+    for (uint32_t t = 0; t < P.tiles_x * tiles_y; t++)
+        if (t % P.world == P.rank) r->h_tiles.push_back(t);
+    P.n_tiles = (uint32_t)r->h_tiles.size();
+    P.nslots = P.n_tiles * P.block_slots;
     P.ref_grid_x = c.chunk_w / 28u + 1u;  // render_manager.cu:93-96
     P.spp = c.spp & 0xFFFFu;              // short_uint kernel parameters (rendering.cu:154, Q14)
     P.bounce_limit = c.bounce_limit & 0xFFFFu;
     P.regen_loop = c.regen_loop < 1 ? 1 : c.regen_loop;
-    P.tile_w = (uint32_t)std::max(1, c.tile_w); P.tile_h = (uint32_t)std::max(1, c.tile_h);
-    P.tiles_x = (P.img_w + P.tile_w - 1) / P.tile_w;
-    P.rank = (uint32_t)c.rank; P.world = (uint32_t)std::max(1, c.world);
     P.plane = (size_t)P.img_w * P.img_h;
-    const size_t ns = P.nslots;
+    const size_t ns = std::max<size_t>(P.nslots, 1);
+    SRT_CUDA(cudaMalloc((void**)&r->d_tiles, std::max<size_t>(1, r->h_tiles.size()) * sizeof(uint32_t)));
+    if (!r->h_tiles.empty()) SRT_CUDA(cudaMemcpy(r->d_tiles, r->h_tiles.data(), r->h_tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    P.tiles = r->d_tiles;
     SRT_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     SRT_CUDA(cudaEventCreate(&r->ev0));
     SRT_CUDA(cudaEventCreate(&r->ev1));
@@ -189,9 +206,11 @@ static bool renderer_setup(DeviceRenderer* r) {
     SRT_CUDA(cudaMemsetAsync(P.acc, 0, 3 * P.plane * sizeof(float), r->stream));
     SRT_CUDA(cudaMalloc((void**)&r->d_rays, sizeof(unsigned long long)));
     SRT_CUDA(cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), r->stream));
-    if (!pool_alloc((void**)&r->d_rgb, 3 * ns * sizeof(float))) return false;
-    if (!pool_alloc((void**)&r->d_xyz, 3 * ns * sizeof(float))) return false;
-    r->h_stage = pinned_staging(6 * ns * sizeof(float));
+    const size_t chunk_px = (size_t)c.chunk_w * c.chunk_h;
+    if (!pool_alloc((void**)&r->d_rgb, 3 * chunk_px * sizeof(float))) return false;
+    if (!pool_alloc((void**)&r->d_xyz, 3 * chunk_px * sizeof(float))) return false;
+    r->h_stage = pinned_staging(6 * chunk_px * sizeof(float));
+    r->chunk_px = chunk_px;
     if (!r->h_stage) return false;
     std::vector<float> cie(3 * SRT_NS);
     for (int k = 0; k < 3; k++) memcpy(cie.data() + k * SRT_NS, cie_table(k), SRT_NS * sizeof(float));
@@ -203,12 +222,16 @@ static bool renderer_setup(DeviceRenderer* r) {
     P.bg = r->d_bg;
     P.ray_counter = r->d_rays;
     const LaunchTable& T = table(c.fp_strict);
-    r->mode = P.n_tris <= SRT_FLAT_MAX_TRIS && c.traversal != 1 ? 2 : 1;
-    if (c.traversal == 0 && P.n_tris > SRT_FLAT_MAX_TRIS) r->mode = 1;
+    // wide leaf only when the scene collapsed into <= 32 units AND this camera's origins respect the
+    // origin bound the units' error budgets were computed for
+    const double cam_l1 = std::fabs(c.cam.camera_center.x) + std::fabs(c.cam.camera_center.y) + std::fabs(c.cam.camera_center.z) +
+                          std::fabs(c.cam.defocus_disk_u.x) + std::fabs(c.cam.defocus_disk_u.y) + std::fabs(c.cam.defocus_disk_u.z) +
+                          std::fabs(c.cam.defocus_disk_v.x) + std::fabs(c.cam.defocus_disk_v.y) + std::fabs(c.cam.defocus_disk_v.z);
+    const bool flat_ok = P.n_units > 0 && cam_l1 <= device_scene_origin_bound(r->scene);
+    r->mode = flat_ok && c.traversal == 0 ? 2 : 1;
     size_t need = T.smem_bytes(P, r->mode);
     if (need > kSmemSceneLimit || c.traversal == 3) { r->mode = 0; need = 0; }
     r->smem = need;
-    P.block_slots = (uint32_t)std::min(65536, std::max(32, c.block_slots));
     P.queue_bytes = (2u * 4u * P.block_slots * (uint32_t)sizeof(uint16_t) + 15u) & ~15u;
     SRT_CUDA(T.configure(r->smem + P.queue_bytes));
     // persistent grid: a multiple of the SM count, enough blocks to fill every SM's thread slots
@@ -233,18 +256,20 @@ bool device_renderer_render_chunk(DeviceRenderer* r, unsigned off_x, unsigned of
     cudaStream_t st = r->stream;
     P.off_x = off_x; P.off_y = off_y; P.cw = w; P.ch = h;
     SRT_CUDA(cudaEventRecord(r->ev0, st));
-    if (!r->slots_inited) {  // RNG states are seeded once and carried across chunks (rendering.cu:209,232)
+    if (!r->slots_inited && P.n_tiles) {  // RNG states are seeded once and carried across chunks (rendering.cu:209,232)
         KernelTimer kt(r, 3);
         T.init_slots(P, st);
         r->launches++; count_launch();
         r->slots_inited = true;
     }
-    if (r->cfg.pipeline == 1) {
+    if (P.n_tiles == 0) {
+        // this rank owns no tile of the image: nothing to launch
+    } else if (r->cfg.pipeline == 1) {
         KernelTimer kt(r, 2);
         T.megakernel(P, r->mode, r->grid, r->smem, st);
     } else {  // one persistent-block launch renders the whole chunk
         KernelTimer kt(r, 1);
-        const int blocks = (int)((P.nslots + P.block_slots - 1) / P.block_slots);
+        const int blocks = (int)P.n_tiles;
         T.wavefront(P, r->mode, blocks, r->smem + P.queue_bytes, st);
         r->iterations++;
     }
@@ -256,15 +281,13 @@ bool device_renderer_render_chunk(DeviceRenderer* r, unsigned off_x, unsigned of
     SRT_CUDA(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
     r->render_ms += ms;
     collect_kernel_times(r);
-    // owned pixels of this chunk (tile ownership) for the sample count
+    // owned pixels of this chunk for the sample count: the owned tiles clipped to the chunk
     uint64_t owned = 0;
-    for (unsigned y = off_y; y < off_y + h; y += 1) {
-        const unsigned ty = y / P.tile_h;
-        for (unsigned tx = off_x / P.tile_w; tx <= (off_x + w - 1) / P.tile_w; tx++) {
-            if ((tx + ty * P.tiles_x) % P.world != P.rank) continue;
-            const unsigned x0 = std::max(off_x, tx * P.tile_w), x1 = std::min(off_x + w, (tx + 1) * P.tile_w);
-            owned += x1 - x0;
-        }
+    for (uint32_t tile : r->h_tiles) {
+        const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+        const uint32_t x0 = tx * P.tile_w, y0 = ty * P.tile_h;
+        if (x0 >= w || y0 >= h) continue;
+        owned += (uint64_t)(std::min(w, x0 + P.tile_w) - x0) * (std::min(h, y0 + P.tile_h) - y0);
     }
     r->samples += owned * P.spp;
     unsigned long long rays = 0;
@@ -277,8 +300,8 @@ bool device_renderer_resolve(DeviceRenderer* r, unsigned off_x, unsigned off_y, 
                              unsigned img_w, unsigned img_h) {
     const LaunchTable& T = table(r->cfg.fp_strict);
     const size_t n = (size_t)w * h;
-    if (n > (size_t)r->P.nslots) {  // whole-image resolve after a chunked / reduced render: go band by band
-        const unsigned rows = std::max(1u, (unsigned)(r->P.nslots / w));
+    if (n > r->chunk_px) {  // whole-image resolve after a chunked / reduced render: go band by band
+        const unsigned rows = std::max(1u, (unsigned)(r->chunk_px / w));
         for (unsigned y = 0; y < h; y += rows)
             if (!device_renderer_resolve(r, off_x, off_y + y, w, std::min(rows, h - y), fr, fg, fb, xyz, img_w, img_h)) return false;
         return true;
@@ -326,7 +349,7 @@ void device_renderer_stats(const DeviceRenderer* r, srt_stats* s) {
 
 bool device_scene_trace(const DeviceScene* s, uint32_t n, const float* o, const float* d, float* t, int32_t* tri, float* ms) {
     WaveParams P{};
-    P.nodes = device_scene_nodes(s); P.tris = device_scene_tris(s); P.fast = device_scene_fast(s); P.mats = device_scene_mats(s); P.n_tris = (int)device_scene_ntris(s);
+    P.nodes = device_scene_nodes(s); P.tris = device_scene_tris(s); P.mats = device_scene_mats(s); P.n_tris = (int)device_scene_ntris(s);
     float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
     int32_t* d_tri = nullptr;
     cudaEvent_t e0, e1;

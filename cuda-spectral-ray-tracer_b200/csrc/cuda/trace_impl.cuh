@@ -69,7 +69,8 @@ __device__ __forceinline__ float rng_range(Rng& s, float lo, float hi) {  // uti
 struct SceneRef {
     const SrtNode* nodes;
     const SrtTri* tris;
-    const SrtTriFast* fast;
+    const SrtFlatUnit* units;  // wide leaf only
+    int n_units;
     const SrtMaterial* mats;
     const float* cie;  // x[95] y[95] z[95]
     const float* bg;   // [95]
@@ -125,43 +126,61 @@ __device__ __forceinline__ bool tri_test(const SrtTri* __restrict__ tp, V3 o, V3
     return true;
 }
 
-// Wide-leaf closest hit for scenes of <= 64 triangles (all three reference scenes): the whole
-// LBVH collapses into ONE leaf, so there is no tree walk, no stack and no divergent descent.
-//   phase 1: every lane runs the same branch-free loop over all triangles (triangle data is a
-//            warp-uniform shared-memory broadcast) evaluating a CONSERVATIVE pre-test in explicit
-//            FMAs (plane distance with an approximate reciprocal + barycentrics with error slack)
-//            and records survivors in a 64-bit mask;
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// equal-t ties go to the triangle the reference would have tested last (SrtTri::prio, host/ref_order.cpp)
+__device__ __forceinline__ void consider_hit(const SrtTri* __restrict__ tris, int i, V3 o, V3 d, float& closest, int& best, uint32_t& best_prio) {
+    float t;
+    if (!tri_test(tris + i, o, d, closest, t)) return;
+    const uint32_t prio = tris[i].prio;
+    if (t < closest || best < 0 || prio > best_prio) { closest = t; best = i; best_prio = prio; }
+}
+
+// Wide-leaf closest hit for scenes that collapse into <= 32 pre-test units (all three reference
+// scenes): the whole LBVH is ONE leaf, so there is no tree walk, no stack and no divergent descent.
+//   phase 1: every lane runs the same branch-free loop over the units (unit data is a warp-uniform
+//            shared-memory broadcast).  A unit is a triangle or a parallelogram pair (two coplanar
+//            triangles sharing a diagonal, i.e. every quad the reference builds): plane distance with
+//            an approximate reciprocal, the point in the unit's affine frame, then "certainly outside"
+//            tests with the error budget folded into the constants; survivors set bits 2u / 2u+1;
 //   phase 2: the few survivors (the triangles the ray really pierces, ~1-4) get the exact
-//            reference arithmetic (tri_test), nearest wins.
-// The pre-test only ever rejects pairs the exact test rejects too, so results are identical to
-// testing every triangle exactly -- which is what "closest hit" means in the reference (bvh.cu:98-166).
+//            reference arithmetic (tri_test), nearest wins, ties by reference test order.
+// Phase 1 only ever rejects pairs the exact test rejects too, so the result equals testing every
+// triangle exactly -- which is what "closest hit" means in the reference (bvh.cu:98-166).
+__device__ __forceinline__ uint32_t flat_unit_bits(const float4* __restrict__ up, int u, V3 o, V3 d) {
+    const float4 pl = up[4 * u], A = up[4 * u + 1], B = up[4 * u + 2], C = up[4 * u + 3];
+    const float denom = __fmaf_rn(pl.z, d.z, __fmaf_rn(pl.y, d.y, pl.x * d.x));
+    const float num = pl.w - __fmaf_rn(pl.z, o.z, __fmaf_rn(pl.y, o.y, pl.x * o.x));
+    const float t = num * rcp_approx(denom);
+    const float px = __fmaf_rn(t, d.x, o.x), py = __fmaf_rn(t, d.y, o.y), pz = __fmaf_rn(t, d.z, o.z);
+    const float al = __fmaf_rn(A.z, pz, __fmaf_rn(A.y, py, __fmaf_rn(A.x, px, A.w)));
+    const float be = __fmaf_rn(B.z, pz, __fmaf_rn(B.y, py, __fmaf_rn(B.x, px, B.w)));
+    const float s = al + be;
+    // every comparison is phrased as "certainly outside" so NaN / inf fall through to the exact test
+    const bool behind = (t < 0.0f) & (fabsf(num) > C.w);
+    const bool out_i = behind | (fminf(al, be) < 0.0f) | (s > C.x);
+    const bool out_j = behind | (fmaxf(al, be) > C.y) | (s < C.z);
+    return (out_i ? 0u : 1u) | (out_j ? 0u : 2u);
+}
 __device__ __forceinline__ int closest_hit_flat(const SceneRef& sc, V3 o, V3 d, float& t_hit) {
-    const float o1 = fabsf(o.x) + fabsf(o.y) + fabsf(o.z);
+    const float4* __restrict__ up = reinterpret_cast<const float4*>(sc.units);
     uint32_t m0 = 0, m1 = 0;
-    const float4* __restrict__ fp = reinterpret_cast<const float4*>(sc.fast);
-    for (int i = 0; i < sc.n_tris; i++) {
-        const float4 pl = fp[4 * i], A = fp[4 * i + 1], B = fp[4 * i + 2], T = fp[4 * i + 3];
-        const float denom = __fmaf_rn(pl.z, d.z, __fmaf_rn(pl.y, d.y, pl.x * d.x));
-        const float num = pl.w - __fmaf_rn(pl.z, o.z, __fmaf_rn(pl.y, o.y, pl.x * o.x));
-        const float t = __fdividef(num, denom);
-        const float px = __fmaf_rn(t, d.x, o.x), py = __fmaf_rn(t, d.y, o.y), pz = __fmaf_rn(t, d.z, o.z);
-        const float u = __fmaf_rn(A.z, pz, __fmaf_rn(A.y, py, __fmaf_rn(A.x, px, A.w)));
-        const float v = __fmaf_rn(B.z, pz, __fmaf_rn(B.y, py, __fmaf_rn(B.x, px, B.w)));
-        const float eps = __fmaf_rn(T.y, o1, T.x), tol = __fmaf_rn(T.w, o1, T.z);
-        // written as "certainly outside" so that NaN/inf fall through to the exact test
-        const bool reject = (u < -eps) | (v < -eps) | (u + v > 1.0f + eps) | ((t < 0.0f) & (fabsf(num) > tol));
-        const uint32_t bit = reject ? 0u : 1u;
-        if (i < 32) m0 |= bit << i;
-        else m1 |= bit << (i - 32);
-    }
+    const int n = sc.n_units, n0 = n < 16 ? n : 16;
+#pragma unroll 4
+    for (int u = 0; u < n0; u++) m0 |= flat_unit_bits(up, u, o, d) << (2 * u);
+#pragma unroll 4
+    for (int u = 16; u < n; u++) m1 |= flat_unit_bits(up, u, o, d) << (2 * (u - 16));
     float closest = FLT_MAX;
     int best = -1;
+    uint32_t best_prio = 0;
     while (m0 | m1) {
         int i;
         if (m0) { i = __ffs(m0) - 1; m0 &= m0 - 1; }
         else { i = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
-        float t;
-        if (tri_test(sc.tris + i, o, d, closest, t)) { closest = t; best = i; }
+        consider_hit(sc.tris, i, o, d, closest, best, best_prio);
     }
     t_hit = closest;
     return best;
@@ -173,6 +192,7 @@ template <bool FLAT>
 __device__ __forceinline__ int closest_hit(const SceneRef& sc, V3 o, V3 d, float& t_hit) {
     float closest = FLT_MAX;
     int best = -1;
+    uint32_t best_prio = 0;
     if (sc.n_tris <= 0) return -1;
     // A NaN ray (buggy-Sellmeier refraction, Q1) can never hit: every tri::hit computes a NaN t.
     // Answer "miss" up front instead of walking the whole tree.
@@ -215,16 +235,12 @@ __device__ __forceinline__ int closest_hit(const SceneRef& sc, V3 o, V3 d, float
         // c0 = first child to process (if h0), c1 = second (if h1)
         int next = -1;
         if (h0) {
-            if (c0 < 0) {
-                float t;
-                if (tri_test(sc.tris + (~c0), o, d, closest, t)) { closest = t; best = ~c0; }
-            } else next = c0;
+            if (c0 < 0) consider_hit(sc.tris, ~c0, o, d, closest, best, best_prio);
+            else next = c0;
         }
         if (h1) {
-            if (c1 < 0) {
-                float t;
-                if (tri_test(sc.tris + (~c1), o, d, closest, t)) { closest = t; best = ~c1; }
-            } else if (next < 0) next = c1;
+            if (c1 < 0) consider_hit(sc.tris, ~c1, o, d, closest, best, best_prio);
+            else if (next < 0) next = c1;
             else stack[sp++] = c1;
         }
         if (next >= 0) { node = next; continue; }
@@ -406,24 +422,27 @@ __device__ __forceinline__ SceneRef load_scene(const WaveParams& P, unsigned cha
     SceneRef sc;
     sc.n_tris = P.n_tris;
     if (!SMEM) {
-        sc.nodes = P.nodes; sc.tris = P.tris; sc.fast = P.fast; sc.mats = P.mats; sc.cie = P.cie; sc.bg = P.bg;
+        sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.mats = P.mats; sc.cie = P.cie; sc.bg = P.bg;
         return sc;
     }
     // layout: [nodes | pre-test records (flat scenes)] | tris | mats | cie | bg
     const int n_nodes = P.n_tris > 1 ? P.n_tris - 1 : 0;
     float4* dst = reinterpret_cast<float4*>(smem);
-    const int v_head = FLAT ? P.n_tris * (int)(sizeof(SrtTriFast) / 16) : n_nodes * (int)(sizeof(SrtNode) / 16);
-    const float4* head = FLAT ? reinterpret_cast<const float4*>(P.fast) : reinterpret_cast<const float4*>(P.nodes);
-    const int v_tris = P.n_tris * (int)(sizeof(SrtTri) / 16), v_mats = P.n_mats * (int)(sizeof(SrtMaterial) / 16);
+    const int v_head = FLAT ? P.n_units * (int)(sizeof(SrtFlatUnit) / 16) : n_nodes * (int)(sizeof(SrtNode) / 16);
+    const float4* head = FLAT ? reinterpret_cast<const float4*>(P.flat_units) : reinterpret_cast<const float4*>(P.nodes);
+    const int n_stage_tris = FLAT ? 2 * P.n_units : P.n_tris;  // flat order: two triangle slots per unit
+    const float4* tri_src = FLAT ? reinterpret_cast<const float4*>(P.flat_tris) : reinterpret_cast<const float4*>(P.tris);
+    const int v_tris = n_stage_tris * (int)(sizeof(SrtTri) / 16), v_mats = P.n_mats * (int)(sizeof(SrtMaterial) / 16);
     for (int i = threadIdx.x; i < v_head; i += blockDim.x) dst[i] = head[i];
-    for (int i = threadIdx.x; i < v_tris; i += blockDim.x) dst[v_head + i] = reinterpret_cast<const float4*>(P.tris)[i];
+    for (int i = threadIdx.x; i < v_tris; i += blockDim.x) dst[v_head + i] = tri_src[i];
     for (int i = threadIdx.x; i < v_mats; i += blockDim.x) dst[v_head + v_tris + i] = reinterpret_cast<const float4*>(P.mats)[i];
     float* f = reinterpret_cast<float*>(dst + v_head + v_tris + v_mats);
     for (int i = threadIdx.x; i < 3 * SRT_NS; i += blockDim.x) f[i] = P.cie[i];
     for (int i = threadIdx.x; i < SRT_NS; i += blockDim.x) f[3 * SRT_NS + i] = P.bg[i];
     __syncthreads();
     sc.nodes = FLAT ? nullptr : reinterpret_cast<const SrtNode*>(dst);
-    sc.fast = FLAT ? reinterpret_cast<const SrtTriFast*>(dst) : nullptr;
+    sc.units = FLAT ? reinterpret_cast<const SrtFlatUnit*>(dst) : nullptr;
+    sc.n_units = FLAT ? P.n_units : 0;
     sc.tris = reinterpret_cast<const SrtTri*>(dst + v_head);
     sc.mats = reinterpret_cast<const SrtMaterial*>(dst + v_head + v_tris);
     sc.cie = f;
@@ -432,9 +451,16 @@ __device__ __forceinline__ SceneRef load_scene(const WaveParams& P, unsigned cha
 }
 
 // ------------------------------------------------------------------------------ slot <-> pixel
+// Slots are grouped by image tile: slot = k * (tile_w*tile_h) + pixel-in-tile, where k indexes the
+// list of chunk-local tiles THIS rank owns (tile_id % world == rank).  A wavefront block therefore
+// renders one 2-D tile, and a rank only allocates state for its own pixels.
 __device__ __forceinline__ void slot_pixel(const WaveParams& P, uint32_t slot, uint32_t& ci, uint32_t& cj) {
-    cj = slot / P.slot_w;
-    ci = slot - cj * P.slot_w;
+    const uint32_t k = slot / P.block_slots, l = slot - k * P.block_slots;
+    const uint32_t tile = P.tiles[k];
+    const uint32_t ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
+    const uint32_t ly = l / P.tile_w, lx = l - ly * P.tile_w;
+    ci = tx * P.tile_w + lx;
+    cj = ty * P.tile_h + ly;
 }
 // the reference's per-thread seed index (rendering.cu:125-137, 28x16 blocks, grid from the nominal chunk size)
 __device__ __forceinline__ uint32_t ref_thread_index(const WaveParams& P, uint32_t ci, uint32_t cj) {
@@ -485,9 +511,7 @@ __device__ __forceinline__ Rng load_rng(const WaveParams& P, uint32_t slot) {
 __device__ __forceinline__ bool slot_owned(const WaveParams& P, uint32_t slot, uint32_t& ci, uint32_t& cj) {
     if (slot >= P.nslots) return false;
     slot_pixel(P, slot, ci, cj);
-    if (ci >= P.cw || cj >= P.ch) return false;
-    const uint32_t x = P.off_x + ci, y = P.off_y + cj;
-    return ((x / P.tile_w) + (y / P.tile_h) * P.tiles_x) % P.world == P.rank;
+    return ci < P.cw && cj < P.ch;  // edge tiles stick out of the (clipped) chunk
 }
 
 // ------------------------------------------------------------------------------ kernels
@@ -663,7 +687,7 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_trace_rays(WaveParams P, uint32_t
                                                           const uint32_t* __restrict__ sorted_idx, float* __restrict__ t_out,
                                                           int32_t* __restrict__ tri_out) {
     SceneRef sc;
-    sc.nodes = P.nodes; sc.tris = P.tris; sc.fast = P.fast; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
+    sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float t = 0.f;
         const int tri = closest_hit<false>(sc, mk(o[3ull * i], o[3ull * i + 1], o[3ull * i + 2]), mk(d[3ull * i], d[3ull * i + 1], d[3ull * i + 2]), t);
@@ -677,8 +701,8 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_trace_rays(WaveParams P, uint32_t
 // 2: scene staged in shared memory, <= 64 triangles, wide-leaf closest hit (no tree walk)
 static size_t scene_smem_bytes(const WaveParams& P, int mode) {
     const size_t n_nodes = P.n_tris > 1 ? P.n_tris - 1 : 0;
-    const size_t head = mode == 2 ? (size_t)P.n_tris * sizeof(SrtTriFast) : n_nodes * sizeof(SrtNode);
-    return head + (size_t)P.n_tris * sizeof(SrtTri) + (size_t)P.n_mats * sizeof(SrtMaterial) + 4 * SRT_NS * sizeof(float);
+    const size_t head = mode == 2 ? (size_t)P.n_units * sizeof(SrtFlatUnit) : n_nodes * sizeof(SrtNode);
+    return head + (size_t)(mode == 2 ? 2 * P.n_units : P.n_tris) * sizeof(SrtTri) + (size_t)P.n_mats * sizeof(SrtMaterial) + 4 * SRT_NS * sizeof(float);
 }
 #define SRT_DISPATCH(KERNEL, MODE, GRID, SMEMB, ST, ...)                                  \
     do {                                                                                  \

@@ -13,7 +13,9 @@ struct WaveParams {
     // scene (global memory; small scenes are staged into shared memory by every block)
     const SrtNode* nodes;
     const SrtTri* tris;  // leaf order
-    const SrtTriFast* fast;  // leaf order, conservative pre-test records
+    const SrtFlatUnit* flat_units;  // wide-leaf pre-test units (mode 2), triangles in flat order follow
+    const SrtTri* flat_tris;
+    int n_units;
     const SrtMaterial* mats;
     const float* cie;    // x[95] y[95] z[95]
     const float* bg;     // background spectrum [95]
@@ -22,11 +24,13 @@ struct WaveParams {
     SrtCamera cam;
     uint32_t off_x, off_y, cw, ch;   // current chunk (pixels)
     uint32_t img_w, img_h;
-    uint32_t slot_w, nslots;         // slot = cj * slot_w + ci over the NOMINAL chunk size
+    uint32_t nslots;                 // n_tiles * block_slots
+    const uint32_t* tiles;           // chunk-local tile ids owned by this rank (tile_id % world == rank)
+    uint32_t n_tiles;
     uint32_t ref_grid_x;             // nominal_chunk_w / 28 + 1 (reference launch geometry -> seeds)
     uint32_t spp, bounce_limit;
     int regen_loop;
-    uint32_t tile_w, tile_h, tiles_x, rank, world;
+    uint32_t tile_w, tile_h, tiles_x, rank, world;  // tiles_x: tiles per row of the nominal chunk
     // per-slot path state, 16-byte vectors
     float4* R0;    // hit point xyz | triangle (leaf order)
     float4* R1;    // incoming direction xyz | valid[2:0] + bounce

@@ -1,6 +1,8 @@
 // extern "C" surface of libsrt.so (include/srt.h).  Thin: argument checks + forwarding.
 #include "srt_host.hpp"
 #include <cstring>
+#include <cmath>
+#include <algorithm>
 
 using namespace srt;
 
@@ -61,7 +63,13 @@ void srt_set_ref_compat(int on) { g_ref_compat = on != 0; }
 
 static srt_scene* finish_scene(srt_scene* h) {
     Scene& s = h->s;
-    s.dev = device_scene_create(s.desc.tris, s.desc.mats);
+    // ray origins are the camera (lens) or points inside the scene box: bound |o|_1 for the wide-leaf error budgets
+    double radius = 0;
+    for (const HostTri& t : s.desc.tris)
+        for (float b : t.bbox) radius = std::max(radius, (double)std::fabs(b));
+    const vec3f c = s.desc.camera.lookfrom;
+    const double bound = std::max(3.0 * radius, 1.25 * (std::fabs(c.x) + std::fabs(c.y) + std::fabs(c.z)) + 16.0);
+    s.dev = device_scene_create(s.desc.tris, s.desc.mats, bound);
     s.ok = s.dev != nullptr;
     s.msg = s.ok ? "World created" : last_error();  // scene.cu:427 / the result{false,...} returns of init_world
     return h;

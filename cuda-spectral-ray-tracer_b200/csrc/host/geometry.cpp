@@ -54,7 +54,7 @@ void HostTri::derive() {  // tri::init, tri.cu:47-84
     }
 }
 
-SrtTri HostTri::pack(uint32_t mat_type) const {
+SrtTri HostTri::pack(uint32_t mat_type, uint32_t prio) const {
     int w, h;
     projection_axes(aa_plane, w, h);
     SrtTri t{};
@@ -64,6 +64,7 @@ SrtTri HostTri::pack(uint32_t mat_type) const {
     t.w2 = v[2][w]; t.h2 = v[2][h];
     t.bits = (mat & 0xFFFFu) | ((uint32_t)(clockwise ? 1 : 0) << 16) | ((uint32_t)w << 17) | ((uint32_t)h << 19) |
              ((mat_type & 7u) << 21);
+    t.prio = prio;
     return t;
 }
 

@@ -64,7 +64,7 @@ struct HostTri {
     uint32_t mat = 0;
     float bbox[6] = {0, 0, 0, 0, 0, 0};
     void derive();  // normal, plane constant, winding, projection plane, padded box
-    SrtTri pack(uint32_t mat_type) const;
+    SrtTri pack(uint32_t mat_type, uint32_t prio) const;
 };
 struct HostMaterial {
     uint32_t type = SRT_LAMBERTIAN;
@@ -112,6 +112,15 @@ const float* cie_table(int which);  // 0 x, 1 y, 2 z, 3 normalised D65 (95 float
 float spectrum_interp_host(const float* table95, float lambda);
 void background_spectrum(vec3f rgb, float out95[SRT_NS]);
 
+std::vector<uint32_t> reference_test_order(const std::vector<HostTri>& tris);
+struct FlatLeaf {
+    std::vector<SrtFlatUnit> units;   // <= 32
+    std::vector<SrtTri> tris;         // 2 per unit
+    std::vector<uint32_t> to_orig;    // flat position -> original triangle index
+};
+bool build_flat_leaf(const std::vector<HostTri>& tris, const std::vector<HostMaterial>& mats, const std::vector<uint32_t>& prio,
+                     double origin_l1_bound, FlatLeaf& out);
+
 // ---------------------------------------------------------------- device objects (defined in cuda/*.cu)
 struct DeviceScene;     // triangles, materials, LBVH
 struct DeviceRenderer;  // per-pixel state, queues, film
@@ -123,7 +132,7 @@ struct LbvhDump {
     float scene_box[6];
 };
 
-DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::vector<HostMaterial>& mats);
+DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::vector<HostMaterial>& mats, double origin_l1_bound);
 void device_scene_destroy(DeviceScene*);
 bool device_scene_build_lbvh(DeviceScene*, int repeats, float ms_out[5]);
 bool device_scene_download_lbvh(const DeviceScene*, LbvhDump& out);

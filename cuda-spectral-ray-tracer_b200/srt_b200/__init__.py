@@ -346,11 +346,11 @@ def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=Fals
         rm.set_option(OPT_TAIL_THRESHOLD, tail_threshold)
     if traversal is not None:
         rm.set_option(OPT_TRAVERSAL, traversal)
-    if block_slots is not None:
-        rm.set_option(OPT_BLOCK_SLOTS, block_slots)
     if tiles is not None:
         tw, th, rank, world = tiles
         rm.set_option(OPT_TILE_W, tw); rm.set_option(OPT_TILE_H, th); rm.set_option(OPT_RANK, rank); rm.set_option(OPT_WORLD, world)
+    if block_slots is not None:  # legacy spelling: a tile of 32 x (block_slots/32) pixels per wavefront block
+        rm.set_option(OPT_TILE_W, 32); rm.set_option(OPT_TILE_H, max(1, block_slots // 32))
     rm.init_device_params(*chunk)
     rm.render_all()
     return fb.rgb().copy(), rm.xyz(), rm.stats()

@@ -168,14 +168,14 @@ int srt_rm_render_all(srt_render_manager*);
 /* additions needed for grading / multi-GPU (no reference counterpart) */
 #define SRT_OPT_FP_MODE 1      /* 0 = fast (FMA contraction, like the reference's nvcc build), 1 = strict (-fmad=false, matches the host oracle) */
 #define SRT_OPT_PIPELINE 2     /* 0 = wavefront (default), 1 = per-pixel persistent megakernel */
-#define SRT_OPT_TILE_W 3       /* multi-GPU tile ownership: tile size ... */
+#define SRT_OPT_TILE_W 3       /* image tile rendered by one wavefront block and unit of multi-GPU ownership (default 32x32) */
 #define SRT_OPT_TILE_H 4
 #define SRT_OPT_RANK 5         /* ... this process renders tiles with (tile_id % world) == rank */
 #define SRT_OPT_WORLD 6
 #define SRT_OPT_REGEN_LOOP 7   /* camera-ray regenerations a slot may do inside one wavefront pass (tuning) */
 #define SRT_OPT_KERNEL_TIMING 8 /* 1 = bracket every kernel launch with CUDA events (per-kernel totals in srt_stats) */
 #define SRT_OPT_TAIL_THRESHOLD 9 /* (unused since the persistent-block wavefront; kept for ABI stability) */
-#define SRT_OPT_BLOCK_SLOTS 11   /* pixel slots owned by one persistent wavefront block (default 1024) */
+#define SRT_OPT_BLOCK_SLOTS 11   /* (unused: a wavefront block renders one tile, see SRT_OPT_TILE_W/H) */
 #define SRT_OPT_TRAVERSAL 10     /* 0 auto (wide-leaf closest hit when the scene has <= 64 triangles), 1 force the LBVH walk
                                     (scene in shared memory), 3 force the LBVH walk with the scene in global memory */
 int srt_rm_set_option(srt_render_manager*, int option, int value);
