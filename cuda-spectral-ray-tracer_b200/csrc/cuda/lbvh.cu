@@ -62,7 +62,7 @@ struct DeviceScene {
     uint32_t* lookback = nullptr; // SORT_PASSES x tiles x RADIX status words
     uint32_t* tile_counter = nullptr;  // SORT_PASSES dynamic tile ids
     int32_t *left = nullptr, *right = nullptr, *parent = nullptr;
-    float* node_boxes = nullptr;  // (2n-1) x 6
+    float4 *node_box_lo = nullptr, *node_box_hi = nullptr;  // (2n-1) each: (xmin,ymin,zmin,-), (xmax,ymax,zmax,-)
     uint32_t* visit = nullptr;    // n-1 refit arrival flags
     SrtNode* nodes = nullptr;     // n-1 traversal nodes
     SrtTri* tris = nullptr;       // n, LEAF order
@@ -346,58 +346,51 @@ __global__ void __launch_bounds__(256) k_hierarchy(const uint32_t* __restrict__ 
     parent[R] = i;
 }
 
-// ---- refit ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_refit(int n, const uint32_t* __restrict__ sorted_idx, const float* __restrict__ leaf_boxes,
-                                               const int32_t* __restrict__ left, const int32_t* __restrict__ right,
-                                               const int32_t* __restrict__ parent, float* node_boxes, uint32_t* visit) {
+// ---- refit + emit (one kernel) ------------------------------------------------------------------
+// One thread per leaf: writes its leaf-order triangle, then climbs.  The first thread to reach an
+// internal node leaves (its subtree's box is already published); the second one owns both child
+// boxes -- its own running box and the sibling's published one -- so it unions them (fmin/fmax:
+// order independent, hence deterministic), publishes the node's box for the level above AND writes
+// the 64-byte traversal node right there.  Boxes travel as two 16-byte vectors (lo.xyz, hi.xyz).
+__device__ __forceinline__ float widen_lo(float v) { return v - fabsf(v) * 2.4e-7f; }
+__device__ __forceinline__ float widen_hi(float v) { return v + fabsf(v) * 2.4e-7f; }
+__global__ void __launch_bounds__(256) k_refit_emit(int n, const uint32_t* __restrict__ sorted_idx, const float* __restrict__ leaf_boxes,
+                                                    const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                                    const int32_t* __restrict__ parent, float4* node_box_lo, float4* node_box_hi, uint32_t* visit,
+                                                    const SrtTri* __restrict__ tris_in, SrtNode* __restrict__ nodes, SrtTri* __restrict__ tris) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    float b[6];
     const uint32_t src = sorted_idx[k];
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-        b[c] = leaf_boxes[6ull * src + c];
-        node_boxes[6ull * (n - 1 + k) + c] = b[c];
-    }
-    int node = parent[n - 1 + k];
+    tris[k] = tris_in[src];
+    float4 lo = make_float4(leaf_boxes[6ull * src], leaf_boxes[6ull * src + 2], leaf_boxes[6ull * src + 4], 0.f);
+    float4 hi = make_float4(leaf_boxes[6ull * src + 1], leaf_boxes[6ull * src + 3], leaf_boxes[6ull * src + 5], 0.f);
     int from = n - 1 + k;
+    node_box_lo[from] = lo;
+    node_box_hi[from] = hi;
+    int node = parent[from];
     while (node >= 0) {
         __threadfence();
         if (atomicAdd(&visit[node], 1u) == 0) return;  // the sibling subtree finishes this node
-        const int other = left[node] == from ? right[node] : left[node];
-        const volatile float* ob = node_boxes + 6ull * other;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            b[2 * c] = fminf(b[2 * c], ob[2 * c]);
-            b[2 * c + 1] = fmaxf(b[2 * c + 1], ob[2 * c + 1]);
-        }
-#pragma unroll
-        for (int c = 0; c < 6; c++) node_boxes[6ull * node + c] = b[c];
+        const int L = left[node], R = right[node];
+        const int other = L == from ? R : L;
+        const float4 olo = __ldcg(node_box_lo + other), ohi = __ldcg(node_box_hi + other);
+        const float4 llo = L == from ? lo : olo, lhi = L == from ? hi : ohi;  // left child's box
+        const float4 rlo = L == from ? olo : lo, rhi = L == from ? ohi : hi;  // right child's box
+        SrtNode nd;
+        nd.c0xmin = widen_lo(llo.x); nd.c0xmax = widen_hi(lhi.x); nd.c0ymin = widen_lo(llo.y); nd.c0ymax = widen_hi(lhi.y);
+        nd.c1xmin = widen_lo(rlo.x); nd.c1xmax = widen_hi(rhi.x); nd.c1ymin = widen_lo(rlo.y); nd.c1ymax = widen_hi(rhi.y);
+        nd.c0zmin = widen_lo(llo.z); nd.c0zmax = widen_hi(lhi.z); nd.c1zmin = widen_lo(rlo.z); nd.c1zmax = widen_hi(rhi.z);
+        nd.child0 = L >= n - 1 ? ~(L - (n - 1)) : L;
+        nd.child1 = R >= n - 1 ? ~(R - (n - 1)) : R;
+        nd.pad0 = nd.pad1 = 0;
+        nodes[node] = nd;
+        lo = make_float4(fminf(lo.x, olo.x), fminf(lo.y, olo.y), fminf(lo.z, olo.z), 0.f);
+        hi = make_float4(fmaxf(hi.x, ohi.x), fmaxf(hi.y, ohi.y), fmaxf(hi.z, ohi.z), 0.f);
+        node_box_lo[node] = lo;
+        node_box_hi[node] = hi;
         from = node;
         node = parent[node];
     }
-}
-
-// ---- emit traversal layout -------------------------------------------------------------------
-__device__ __forceinline__ float widen_lo(float v) { return v - fabsf(v) * 2.4e-7f; }
-__device__ __forceinline__ float widen_hi(float v) { return v + fabsf(v) * 2.4e-7f; }
-__global__ void __launch_bounds__(256) k_emit(int n, const uint32_t* __restrict__ sorted_idx, const int32_t* __restrict__ left,
-                                              const int32_t* __restrict__ right, const float* __restrict__ node_boxes,
-                                              const SrtTri* __restrict__ tris_in, SrtNode* __restrict__ nodes, SrtTri* __restrict__ tris) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) tris[i] = tris_in[sorted_idx[i]];
-    if (i >= n - 1) return;
-    const int L = left[i], R = right[i];
-    const float* a = node_boxes + 6ull * L;
-    const float* b = node_boxes + 6ull * R;
-    SrtNode nd;
-    nd.c0xmin = widen_lo(a[0]); nd.c0xmax = widen_hi(a[1]); nd.c0ymin = widen_lo(a[2]); nd.c0ymax = widen_hi(a[3]);
-    nd.c1xmin = widen_lo(b[0]); nd.c1xmax = widen_hi(b[1]); nd.c1ymin = widen_lo(b[2]); nd.c1ymax = widen_hi(b[3]);
-    nd.c0zmin = widen_lo(a[4]); nd.c0zmax = widen_hi(a[5]); nd.c1zmin = widen_lo(b[4]); nd.c1zmax = widen_hi(b[5]);
-    nd.child0 = L >= n - 1 ? ~(L - (n - 1)) : L;
-    nd.child1 = R >= n - 1 ? ~(R - (n - 1)) : R;
-    nd.pad0 = nd.pad1 = 0;
-    nodes[i] = nd;
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -432,7 +425,7 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
               dalloc(s->centroids, 3ull * n) && dalloc(s->scene_box, 6) && dalloc(s->codes, n) && dalloc(s->keys[0], n) && dalloc(s->keys[1], n) &&
               dalloc(s->vals[0], n) && dalloc(s->vals[1], n) && dalloc(s->hist, SORT_PASSES * RADIX) &&
               dalloc(s->lookback, (size_t)SORT_PASSES * (s->tiles ? s->tiles : 1) * RADIX) && dalloc(s->tile_counter, SORT_PASSES) &&
-              dalloc(s->left, n) && dalloc(s->right, n) && dalloc(s->parent, 2ull * n) && dalloc(s->node_boxes, 12ull * n) && dalloc(s->visit, n) &&
+              dalloc(s->left, n) && dalloc(s->right, n) && dalloc(s->parent, 2ull * n) && dalloc(s->node_box_lo, 2ull * n) && dalloc(s->node_box_hi, 2ull * n) && dalloc(s->visit, n) &&
               dalloc(s->nodes, n) && dalloc(s->tris, n);
     for (auto& e : s->ev) ok = ok && cuda_ok(cudaEventCreate(&e), "cudaEventCreate", __FILE__, __LINE__);
     if (ok && n) {
@@ -459,7 +452,7 @@ void device_scene_destroy(DeviceScene* s) {
     if (!s) return;
     cudaFree(s->verts); cudaFree(s->tris_in); cudaFree(s->mats); cudaFree(s->leaf_boxes); cudaFree(s->centroids); cudaFree(s->scene_box);
     cudaFree(s->codes); cudaFree(s->keys[0]); cudaFree(s->keys[1]); cudaFree(s->vals[0]); cudaFree(s->vals[1]); cudaFree(s->hist);
-    cudaFree(s->lookback); cudaFree(s->tile_counter); cudaFree(s->left); cudaFree(s->right); cudaFree(s->parent); cudaFree(s->node_boxes);
+    cudaFree(s->lookback); cudaFree(s->tile_counter); cudaFree(s->left); cudaFree(s->right); cudaFree(s->parent); cudaFree(s->node_box_lo); cudaFree(s->node_box_hi);
     cudaFree(s->visit); cudaFree(s->nodes); cudaFree(s->tris); cudaFree(s->flat_units); cudaFree(s->flat_tris);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     delete s;
@@ -504,10 +497,10 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
         if (n > 1) k_hierarchy<<<grid_n, 256, 0, st>>>(s->keys[0], (int)n, s->left, s->right, s->parent);
         else SRT_CUDA(cudaMemsetAsync(s->parent, 0xFF, sizeof(int32_t), st));
         SRT_CUDA(cudaEventRecord(s->ev[3], st));
-        k_refit<<<grid_n, 256, 0, st>>>((int)n, s->vals[0], s->leaf_boxes, s->left, s->right, s->parent, s->node_boxes, s->visit);
-        k_emit<<<grid_n, 256, 0, st>>>((int)n, s->vals[0], s->left, s->right, s->node_boxes, s->tris_in, s->nodes, s->tris);
+        k_refit_emit<<<grid_n, 256, 0, st>>>((int)n, s->vals[0], s->leaf_boxes, s->left, s->right, s->parent, s->node_box_lo, s->node_box_hi, s->visit,
+                                             s->tris_in, s->nodes, s->tris);
         SRT_CUDA(cudaEventRecord(s->ev[4], st));
-        count_launch(6 + SORT_PASSES + (n > 1 ? 1 : 0) + 1);
+        count_launch(6 + SORT_PASSES + (n > 1 ? 1 : 0));
         SRT_CUDA_LAST();
     }
     SRT_CUDA(cudaEventSynchronize(s->ev[4]));
@@ -534,7 +527,15 @@ bool device_scene_download_lbvh(const DeviceScene* s, LbvhDump& o) {
         SRT_CUDA(cudaMemcpy(o.right.data(), s->right, (n - 1) * 4, cudaMemcpyDeviceToHost));
     }
     SRT_CUDA(cudaMemcpy(o.parent.data(), s->parent, (2 * n - 1) * 4, cudaMemcpyDeviceToHost));
-    SRT_CUDA(cudaMemcpy(o.node_boxes.data(), s->node_boxes, 6ull * (2 * n - 1) * 4, cudaMemcpyDeviceToHost));
+    {
+        std::vector<float4> lo(2 * n - 1), hi(2 * n - 1);
+        SRT_CUDA(cudaMemcpy(lo.data(), s->node_box_lo, lo.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+        SRT_CUDA(cudaMemcpy(hi.data(), s->node_box_hi, hi.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < lo.size(); i++) {
+            float* b = o.node_boxes.data() + 6 * i;
+            b[0] = lo[i].x; b[1] = hi[i].x; b[2] = lo[i].y; b[3] = hi[i].y; b[4] = lo[i].z; b[5] = hi[i].z;
+        }
+    }
     SRT_CUDA(cudaMemcpy(o.scene_box, s->scene_box, 24, cudaMemcpyDeviceToHost));
     return true;
 }

@@ -150,7 +150,7 @@ __device__ __forceinline__ void consider_hit(const SrtTri* __restrict__ tris, in
 //            reference arithmetic (tri_test), nearest wins, ties by reference test order.
 // Phase 1 only ever rejects pairs the exact test rejects too, so the result equals testing every
 // triangle exactly -- which is what "closest hit" means in the reference (bvh.cu:98-166).
-__device__ __forceinline__ uint32_t flat_unit_bits(const float4* __restrict__ up, int u, V3 o, V3 d) {
+__device__ __forceinline__ void flat_unit_test(const float4* __restrict__ up, int u, V3 o, V3 d, uint32_t bit_i, uint32_t& mask) {
     const float4 pl = up[4 * u], A = up[4 * u + 1], B = up[4 * u + 2], C = up[4 * u + 3];
     const float denom = __fmaf_rn(pl.z, d.z, __fmaf_rn(pl.y, d.y, pl.x * d.x));
     const float num = pl.w - __fmaf_rn(pl.z, o.z, __fmaf_rn(pl.y, o.y, pl.x * o.x));
@@ -163,16 +163,17 @@ __device__ __forceinline__ uint32_t flat_unit_bits(const float4* __restrict__ up
     const bool behind = (t < 0.0f) & (fabsf(num) > C.w);
     const bool out_i = behind | (fminf(al, be) < 0.0f) | (s > C.x);
     const bool out_j = behind | (fmaxf(al, be) > C.y) | (s < C.z);
-    return (out_i ? 0u : 1u) | (out_j ? 0u : 2u);
+    if (!out_i) mask |= bit_i;       // bit_i is warp-uniform (uniform datapath): one predicated LOP3 each
+    if (!out_j) mask |= bit_i << 1;
 }
 __device__ __forceinline__ int closest_hit_flat(const SceneRef& sc, V3 o, V3 d, float& t_hit) {
     const float4* __restrict__ up = reinterpret_cast<const float4*>(sc.units);
     uint32_t m0 = 0, m1 = 0;
     const int n = sc.n_units, n0 = n < 16 ? n : 16;
 #pragma unroll 4
-    for (int u = 0; u < n0; u++) m0 |= flat_unit_bits(up, u, o, d) << (2 * u);
+    for (int u = 0; u < n0; u++) flat_unit_test(up, u, o, d, 1u << (2 * u), m0);
 #pragma unroll 4
-    for (int u = 16; u < n; u++) m1 |= flat_unit_bits(up, u, o, d) << (2 * (u - 16));
+    for (int u = 16; u < n; u++) flat_unit_test(up, u, o, d, 1u << (2 * (u - 16)), m1);
     float closest = FLT_MAX;
     int best = -1;
     uint32_t best_prio = 0;
@@ -533,7 +534,7 @@ __global__ void k_init_slots(WaveParams P) {  // init_random_states (rendering.c
 // balances the uneven pixel costs over the SMs.  The ray trace (extend) has ONE call site so the
 // hot loop stays inside the instruction cache.
 template <bool SMEM, bool FLAT>
-__global__ void __launch_bounds__(SRT_BLOCK, 4) k_wavefront(WaveParams P) {
+__global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefront(WaveParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t S = P.block_slots;
     uint16_t* qbuf = reinterpret_cast<uint16_t*>(smem);  // [2][4][S]
@@ -730,9 +731,9 @@ LaunchTable make_launch_table() {
     t.init_slots = [](const WaveParams& P, cudaStream_t st) { k_init_slots<<<(P.nslots + 255) / 256, 256, 0, st>>>(P); };
     t.wavefront = [](const WaveParams& P, int mode, int grid, size_t smem, cudaStream_t st) {
         // the queues always live in shared memory, also when the scene does not
-        if (mode == 2) k_wavefront<true, true><<<grid, SRT_BLOCK, smem, st>>>(P);
-        else if (mode == 1) k_wavefront<true, false><<<grid, SRT_BLOCK, smem, st>>>(P);
-        else k_wavefront<false, false><<<grid, SRT_BLOCK, smem, st>>>(P);
+        if (mode == 2) k_wavefront<true, true><<<grid, SRT_WAVE_BLOCK, smem, st>>>(P);
+        else if (mode == 1) k_wavefront<true, false><<<grid, SRT_WAVE_BLOCK, smem, st>>>(P);
+        else k_wavefront<false, false><<<grid, SRT_WAVE_BLOCK, smem, st>>>(P);
     };
     t.megakernel = [](const WaveParams& P, int mode, int grid, size_t smem, cudaStream_t st) { SRT_DISPATCH(k_megakernel, mode, grid, smem, st, P); };
     t.resolve = [](const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, float* rgb,

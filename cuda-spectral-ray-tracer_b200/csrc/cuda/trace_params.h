@@ -6,6 +6,10 @@
 #include "../common/srt_types.h"
 
 #define SRT_BLOCK 256
+#ifndef SRT_WAVE_BLOCK
+#define SRT_WAVE_BLOCK 256      // threads of a persistent wavefront block
+#define SRT_WAVE_MIN_BLOCKS 4   // resident blocks per SM the register allocation must allow
+#endif
 
 namespace srt {
 

@@ -168,6 +168,14 @@ def camera(w, h):
     return cam
 
 
+def camera_make(w, h, vfov, lookfrom, lookat, vup, defocus_angle, focus_dist, background=(0, 0, 0)):
+    cam = OCam()
+    L = lib()
+    L.srt_oracle_camera_make.argtypes = [C.c_int, C.c_int, C.c_float, OV3, OV3, OV3, C.c_float, C.c_float, OV3, C.POINTER(OCam)]
+    L.srt_oracle_camera_make(w, h, vfov, OV3(*lookfrom), OV3(*lookat), OV3(*vup), defocus_angle, focus_dist, OV3(*background), C.byref(cam))
+    return cam
+
+
 def camera_array(cam):
     v = lambda a: [a.x, a.y, a.z]
     return np.array([cam.w, cam.h] + v(cam.du) + v(cam.dv) + v(cam.p00) + [cam.defocus_angle] + v(cam.center)

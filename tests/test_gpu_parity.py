@@ -3,9 +3,10 @@ oracle (oracle/libsrt_oracle.so) on identical scenes and identical per-pixel RNG
 
 Tolerances (grounded in measurements there):
   * LBVH (Morton codes, sorted order, topology, boxes): bit-exact, zero tolerance.
-  * strict FP mode (-fmad=false) vs oracle, C1 400x225/8spp: >= 99.5 % of pixels within +-1/255 on
-    every channel (the images are speckle: one flipped decision changes a pixel by up to 255, so a
-    max-abs bound only makes sense on the matching set); residual flips come from powf().
+  * strict FP mode (-fmad=false) vs the reference, C1 400x225/8spp: >= 99.95 % of pixels within +-1/255
+    on every channel (measured: 100 %, XYZ bit-identical, all three scenes).  The images are speckle:
+    one flipped decision changes a pixel by up to 255, so a max-abs bound only makes sense on the
+    matching set; the only arithmetic that can differ from the host is powf() (Schlick, OETF).
   * fast FP mode (FMA contraction, like the reference's nvcc build): >= 99 % within +-1/255.
   * image means: within 1 % of the oracle's mean XYZ.
   * wavefront vs megakernel pipeline, same FP mode: bit-identical films.
@@ -81,7 +82,7 @@ def test_c1_image_strict(srt, scene, golden):
     rmse_match = float(np.sqrt((((xyz - g["c1_xyz"]) ** 2)[:, ok]).mean()))
     print("scene %d strict: match %.5f, XYZ rmse all %.3e matching %.3e, mean XYZ gpu %s ref %s" %
           (scene, frac, rmse_all, rmse_match, xyz.reshape(3, -1).mean(1), g["c1_xyz"].reshape(3, -1).mean(1)))
-    assert frac >= 0.995
+    assert frac >= 0.9995  # measured 1.00000: every pixel of all three scenes is bit-identical in strict mode
     assert rmse_match < 1e-3
     assert np.allclose(xyz.reshape(3, -1).mean(1), g["c1_xyz"].reshape(3, -1).mean(1), rtol=0.01)
     assert st["samples"] == 400 * 225 * 8
@@ -141,6 +142,42 @@ def test_edge_cases(srt):
     rgb, xyz, _ = srt.render(scene_id=1, w=57, h=33, spp=3, bounce=10, strict=True)
     orgb, oxyz = oracle.render(oracle.Scene(1), oracle.camera(57, 33), 3, 10)
     assert match_fraction(rgb, orgb) >= 0.99
+
+
+def render_with_camera(srt, scene, cam, spp, bounce, strict=True):
+    fb = srt.FrameBuffer(cam.width, cam.height)
+    rm = srt.RenderManager(scene, cam, fb)
+    rm.init_renderer(bounce, spp)
+    rm.set_option(srt.OPT_FP_MODE, 1 if strict else 0)
+    rm.init_device_params(0, 0)
+    rm.render_all()
+    return fb.rgb().copy(), rm.xyz()
+
+
+def test_defocus_camera_and_background(srt):
+    """dormant reference features: thin-lens defocus disk (rendering.cu:42-47) and a non-black
+    background (the miss branch multiplies by the background spectrum, rendering.cu:24-27)"""
+    args = dict(vfov=40.0, lookfrom=(278, 278, -800), lookat=(278, 278, 0), vup=(0, 1, 0), defocus_angle=1.5, focus_dist=900.0)
+    b = srt.CameraBuilder().setVfov(40).setLookfrom(278, 278, -800).setLookat(278, 278, 0).setVup(0, 1, 0).setDefocusAngle(1.5).setFocusDist(900).setBackground(0.7, 0.8, 1.0)
+    cam = b.getCamera(160, 90)
+    ocam = oracle.camera_make(160, 90, background=(0.7, 0.8, 1.0), **args)
+    assert np.array_equal(cam.as_array().view(np.uint32), oracle.camera_array(ocam).view(np.uint32))
+    rgb, xyz = render_with_camera(srt, srt.Scene(0), cam, 4, 10)
+    orgb, oxyz = oracle.render(oracle.Scene(0), ocam, 4, 10)
+    assert match_fraction(rgb, orgb) >= 0.995
+    assert rgb.mean() > 50  # the sky is visible around the box
+
+
+def test_soup_render_through_lbvh_walk(srt):
+    """a scene too big for the wide leaf (2000 triangles): the wavefront walks the LBVH in global or
+    shared memory; compared with the oracle, whose closest hit comes from the reference's own BVH"""
+    n = 2000
+    sg = srt.Scene(soup=n, seed=11)
+    rgb, xyz, st = srt.render(scene=sg, w=128, h=72, spp=4, bounce=6, strict=True)
+    orgb, oxyz = oracle.render(oracle.Scene(soup=n, seed=11), oracle.camera(128, 72), 4, 6)
+    assert match_fraction(rgb, orgb) >= 0.99
+    rgb2 = srt.render(scene=sg, w=128, h=72, spp=4, bounce=6, strict=True, traversal=3)[0]
+    assert np.array_equal(rgb, rgb2)  # shared-memory and global-memory walks agree bit for bit
 
 
 def test_tile_ownership_partition(srt):
