@@ -177,8 +177,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-spp", type=int, default=4, help="spp of the bounded CPU sample")
     ap.add_argument("--strict", action="store_true", help="strict FP mode (-fmad=false kernels)")
-    ap.add_argument("--tile-w", type=int, default=32)
-    ap.add_argument("--tile-h", type=int, default=32)
+    ap.add_argument("--tile-w", type=int, default=0, help="0 = library picks by pixels per rank")
+    ap.add_argument("--tile-h", type=int, default=0)
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -365,7 +365,7 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl_name, "scene": scene_id, "width": w, "height": h, "spp": spp, "depth": depth,
                    "fp_mode": "strict(-fmad=false)" if a.strict else "fast(fma, as the reference's nvcc build)",
-                   "parallelism": "tiles%dx%d-interleaved x%d + nccl film reduce" % (a.tile_w, a.tile_h, world) if world > 1 else "single gpu",
+                   "parallelism": "image tiles (auto size) interleaved over %d ranks + nccl film reduce" % world if world > 1 else "single gpu",
                    "l2": "working set (per-pixel state 216 MB + film) exceeds the 126 MB L2 and is re-initialised every step"},
         "clocks": clocks,
         "e2e": {"value": total_samples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},

@@ -179,8 +179,10 @@ static bool renderer_setup(DeviceRenderer* r) {
     P.tiles_x = (c.chunk_w + P.tile_w - 1) / P.tile_w;
     const uint32_t tiles_y = (c.chunk_h + P.tile_h - 1) / P.tile_h;
     P.rank = (uint32_t)c.rank; P.world = (uint32_t)std::max(1, c.world);
+    // owner(tile) = (tx + 5 ty) mod world: diagonal interleave, so every rank samples every image
+    // column and row (vertical stripes would hand one rank the glass pyramid and another the margin)
     for (uint32_t t = 0; t < P.tiles_x * tiles_y; t++)
-        if (t % P.world == P.rank) r->h_tiles.push_back(t);
+        if (((t % P.tiles_x) + 5u * (t / P.tiles_x)) % P.world == P.rank) r->h_tiles.push_back(t);
     P.n_tiles = (uint32_t)r->h_tiles.size();
     P.nslots = P.n_tiles * P.block_slots;
     P.ref_grid_x = c.chunk_w / 28u + 1u;  // render_manager.cu:93-96

@@ -159,12 +159,13 @@ __device__ __forceinline__ void flat_unit_test(const float4* __restrict__ up, in
     const float al = __fmaf_rn(A.z, pz, __fmaf_rn(A.y, py, __fmaf_rn(A.x, px, A.w)));
     const float be = __fmaf_rn(B.z, pz, __fmaf_rn(B.y, py, __fmaf_rn(B.x, px, B.w)));
     const float s = al + be;
-    // every comparison is phrased as "certainly outside" so NaN / inf fall through to the exact test
+    // One "violation" value per half: positive means certainly outside.  fminf/fmaxf drop NaN operands
+    // and NaN > 0 is false, so NaN / inf can only ever keep a candidate (the exact test decides).
+    const float vi = fmaxf(-fminf(al, be), s - C.x);          // first half:  alpha',beta' >= 0, alpha'+beta' <= c1
+    const float vj = fmaxf(fmaxf(al, be) - C.y, C.z - s);     // second half: alpha',beta' <= c2, alpha'+beta' >= c3
     const bool behind = (t < 0.0f) & (fabsf(num) > C.w);
-    const bool out_i = behind | (fminf(al, be) < 0.0f) | (s > C.x);
-    const bool out_j = behind | (fmaxf(al, be) > C.y) | (s < C.z);
-    if (!out_i) mask |= bit_i;       // bit_i is warp-uniform (uniform datapath): one predicated LOP3 each
-    if (!out_j) mask |= bit_i << 1;
+    if (!(behind | (vi > 0.0f))) mask |= bit_i;
+    if (!(behind | (vj > 0.0f))) mask |= bit_i << 1;
 }
 __device__ __forceinline__ int closest_hit_flat(const SceneRef& sc, V3 o, V3 d, float& t_hit) {
     const float4* __restrict__ up = reinterpret_cast<const float4*>(sc.units);
@@ -287,7 +288,7 @@ __device__ __forceinline__ void camera_ray(const SrtCamera& c, uint32_t i, uint3
     p.bounce = 0;
 }
 
-__device__ __noinline__ void mul_spectrum(Path& p, const float* __restrict__ spec) {  // ray/ray.cuh:60-69
+__device__ __forceinline__ void mul_spectrum(Path& p, const float* __restrict__ spec) {  // ray/ray.cuh:60-69
     float wl[SRT_N_WL];
     hero_rotations(p.hero, wl);
 #pragma unroll
@@ -295,23 +296,30 @@ __device__ __noinline__ void mul_spectrum(Path& p, const float* __restrict__ spe
         if ((uint32_t)k < p.valid) p.pw[k] *= interp95(spec, wl[k]);
 }
 
-// dev_spectrum_to_XYZ (color/color.cu:88-104) added into the film accumulator of one pixel
-__device__ __noinline__ void film_add(const SceneRef& sc, const Path& p, float* __restrict__ acc, size_t plane, size_t pix) {
-    if (p.valid == 0) return;  // contributes (0,0,0): x + 0 leaves the sum unchanged
+// dev_spectrum_to_XYZ (color/color.cu:88-104) added into the film accumulator of one pixel.
+// Rare (about 1 % of the rays reach an emitter), so it is an out-of-line call; all arguments are
+// scalars so that the caller's path state stays in registers.
+__device__ __noinline__ void film_add_scalars(const float* __restrict__ cie, float* __restrict__ acc, size_t plane, size_t pix, float hero,
+                                              uint32_t valid, float w0, float w1, float w2, float w3, float w4, float w5, float w6) {
     float wl[SRT_N_WL];
-    hero_rotations(p.hero, wl);
+    hero_rotations(hero, wl);
+    const float pw[SRT_N_WL] = {w0, w1, w2, w3, w4, w5, w6};
     const float delta = (830.0f - 360.0f) / 7.0f;
     float x = 0.0f, y = 0.0f, z = 0.0f;
 #pragma unroll
     for (int k = 0; k < SRT_N_WL; k++)
-        if ((uint32_t)k < p.valid) {
-            x += interp95(sc.cie, wl[k]) * p.pw[k] * delta;
-            y += interp95(sc.cie + SRT_NS, wl[k]) * p.pw[k] * delta;
-            z += interp95(sc.cie + 2 * SRT_NS, wl[k]) * p.pw[k] * delta;
+        if ((uint32_t)k < valid) {
+            x += interp95(cie, wl[k]) * pw[k] * delta;
+            y += interp95(cie + SRT_NS, wl[k]) * pw[k] * delta;
+            z += interp95(cie + 2 * SRT_NS, wl[k]) * pw[k] * delta;
         }
     acc[pix] += x;
     acc[plane + pix] += y;
     acc[2 * plane + pix] += z;
+}
+__device__ __forceinline__ void film_add(const SceneRef& sc, const Path& p, float* __restrict__ acc, size_t plane, size_t pix) {
+    if (p.valid == 0) return;  // contributes (0,0,0): x + 0 leaves the sum unchanged
+    film_add_scalars(sc.cie, acc, plane, pix, p.hero, p.valid, p.pw[0], p.pw[1], p.pw[2], p.pw[3], p.pw[4], p.pw[5], p.pw[6]);
 }
 
 __device__ __forceinline__ V3 random_unit_vector(Rng& rng) {  // vec3.cuh:209-227; draws x, y, z in that order (Q13)
@@ -397,18 +405,18 @@ template <bool FLAT>
 __device__ __forceinline__ int extend(const SceneRef& sc, const WaveParams& P, Path& p, int& tri_out, float* acc, size_t pix) {
     float t = 0.f;
     const int tri = closest_hit<FLAT>(sc, p.o, p.d, t);
-    if (tri < 0) {  // miss: ray_bounce, rendering.cu:24-27
-        if (!P.bg_is_zero) {
-            mul_spectrum(p, sc.bg);
+    uint32_t bits = 0, mtype = SRT_LAMBERTIAN;
+    if (tri >= 0) {
+        bits = __float_as_uint((reinterpret_cast<const float4*>(sc.tris + tri) + 2)->z);
+        mtype = SRT_TRI_MTYPE(bits);
+    }
+    if (tri < 0 || mtype == SRT_EMISSIVE) {
+        // the sample ends here: a miss multiplies by the background spectrum (ray_bounce, rendering.cu:24-27),
+        // an emitter by its emission spectrum (scatter() returns false, material.cu:83-86,95)
+        if (tri >= 0 || !P.bg_is_zero) {
+            mul_spectrum(p, tri < 0 ? sc.bg : sc.mats[SRT_TRI_MAT(bits)].spec);
             film_add(sc, p, acc, P.plane, pix);
         }
-        return EV_DONE;
-    }
-    const uint32_t bits = __float_as_uint((reinterpret_cast<const float4*>(sc.tris + tri) + 2)->z);
-    const uint32_t mtype = SRT_TRI_MTYPE(bits);
-    if (mtype == SRT_EMISSIVE) {  // scatter() returns false after multiplying by the emission spectrum
-        mul_spectrum(p, sc.mats[SRT_TRI_MAT(bits)].spec);
-        film_add(sc, p, acc, P.plane, pix);
         return EV_DONE;
     }
     p.o = mk(p.o.x + t * p.d.x, p.o.y + t * p.d.y, p.o.z + t * p.d.z);  // ray::at, ray/ray.cuh:44-47

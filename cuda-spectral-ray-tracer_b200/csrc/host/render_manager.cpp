@@ -66,7 +66,17 @@ int RenderManager::init_device_params(unsigned cw, unsigned ch) {  // render_man
     if (cw == 0 && ch == 0) { cw = cam_.width; ch = cam_.height; }  // init_device_params() overload
     if (cw == 0) cw = ch;  // io/params.h:53-63 defaults
     if (ch == 0) ch = cw;
-    if (cfg_.rank < 0 || cfg_.rank >= cfg_.world || cfg_.tile_w < 1 || cfg_.tile_h < 1) { set_error("bad tile ownership options"); return SRT_ERR_ARG; }
+    if (cfg_.tile_w <= 0 || cfg_.tile_h <= 0) {
+        // auto tile size: a wavefront block walks its tile's bounce chain serially, so a rank wants at
+        // least ~3 waves of tiles over its block slots (148 SMs x 4); fewer pixels per rank => smaller tiles.
+        // Deterministic in (chunk size, world), so every rank picks the same partition.
+        const double per_rank = double(cw) * ch / std::max(1, cfg_.world);
+        const double target = per_rank / (148.0 * 4.0 * 3.0);
+        if (target >= 2048) { cfg_.tile_w = 32; cfg_.tile_h = 32; }
+        else if (target >= 512) { cfg_.tile_w = 32; cfg_.tile_h = 16; }
+        else { cfg_.tile_w = 16; cfg_.tile_h = 16; }
+    }
+    if (cfg_.rank < 0 || cfg_.rank >= cfg_.world) { set_error("bad tile ownership options"); return SRT_ERR_ARG; }
     chunk_w_ = cw;
     chunk_h_ = ch;
     x_chunks_ = (unsigned)std::ceil(float(cam_.width) / float(cw));

@@ -146,7 +146,7 @@ struct RenderConfig {
     int fp_strict = 0, pipeline = 0, regen_loop = 4, kernel_timing = 0, tail_threshold = 0;
     int block_slots = 1024;  // pixel slots owned by one persistent wavefront block
     int traversal = 0;  // 0 auto (wide leaf when <= 64 triangles), 1 force LBVH walk in shared memory, 3 force LBVH walk in global memory
-    int tile_w = 32, tile_h = 32, rank = 0, world = 1;
+    int tile_w = 0, tile_h = 0, rank = 0, world = 1;  // tile 0x0 = pick automatically
     float bg_spectrum[SRT_NS];
     int bg_is_zero = 1;
 };

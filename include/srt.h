@@ -168,9 +168,9 @@ int srt_rm_render_all(srt_render_manager*);
 /* additions needed for grading / multi-GPU (no reference counterpart) */
 #define SRT_OPT_FP_MODE 1      /* 0 = fast (FMA contraction, like the reference's nvcc build), 1 = strict (-fmad=false, matches the host oracle) */
 #define SRT_OPT_PIPELINE 2     /* 0 = wavefront (default), 1 = per-pixel persistent megakernel */
-#define SRT_OPT_TILE_W 3       /* image tile rendered by one wavefront block and unit of multi-GPU ownership (default 32x32) */
+#define SRT_OPT_TILE_W 3       /* image tile rendered by one wavefront block and unit of multi-GPU ownership (default 0 = automatic: 32x32, 32x16 or 16x16 by pixels per rank) */
 #define SRT_OPT_TILE_H 4
-#define SRT_OPT_RANK 5         /* ... this process renders tiles with (tile_id % world) == rank */
+#define SRT_OPT_RANK 5         /* ... this process renders the tiles with (tile_x + 5 tile_y) % world == rank */
 #define SRT_OPT_WORLD 6
 #define SRT_OPT_REGEN_LOOP 7   /* camera-ray regenerations a slot may do inside one wavefront pass (tuning) */
 #define SRT_OPT_KERNEL_TIMING 8 /* 1 = bracket every kernel launch with CUDA events (per-kernel totals in srt_stats) */

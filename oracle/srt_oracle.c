@@ -959,8 +959,8 @@ int srt_oracle_render_tiles(const oscene* sc, const ocam* cam, int spp, int boun
 #pragma omp parallel for schedule(dynamic, 4)
     for (int j = 0; j < H; j++) {
         for (int i = 0; i < W; i++) {
-            const int tile = (i / tile_w) + (j / tile_h) * tiles_x;
-            if (tile % world != rank) continue;
+            (void)tiles_x;
+            if (((i / tile_w) + 5 * (j / tile_h)) % world != rank) continue; /* diagonal tile interleave */
             const uint32_t idx = ((uint32_t)j % ty) * tx + ((uint32_t)i % tx) + tx * ty * (((uint32_t)j / ty) * gx + (uint32_t)i / tx);
             rngc s;
             srt_oracle_rng_init(1984u + idx, &s.r);

@@ -100,7 +100,7 @@ void srt_oracle_color_spectrum(float r, float g, float b, int emissive, float po
 int srt_oracle_render(const oscene*, const ocam*, int spp, int bounce_limit, int chunk_w, int chunk_h,
                       float* rgb, float* xyz, ocounters* counters, int nthreads);
 
-/* render only the pixels whose (x/tile_w + (y/tile_h)*tiles_x) % world == rank (multi-GPU
+/* render only the pixels whose (x/tile_w + 5*(y/tile_h)) % world == rank (multi-GPU
  * tile ownership test); other pixels are left zero.  Single full-image chunk. */
 int srt_oracle_render_tiles(const oscene*, const ocam*, int spp, int bounce_limit, int tile_w, int tile_h,
                             int rank, int world, float* xyz_sum);
