@@ -351,6 +351,19 @@ def main():
         ach = 256.0 * (1 << 20) / (t * 1e-3) / 1e9
         lb = {"n_tris": 1 << 20, "build_ms": t, "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                                                               "peak_source": hbm_src, "algorithmic_bytes_per_tri": 256}}
+        # BASELINE.json configs[3]: closest-hit rays/s through the device LBVH of the same soup
+        # (primary = the reference camera at 1920x1080, secondary = one random bounce off the primary hits)
+        cam_a = soup.camera(1920, 1080).as_array()
+        ys, xs = np.mgrid[0:1080, 0:1920]
+        d = (cam_a[8:11][None, :] + xs.reshape(-1, 1) * cam_a[2:5][None, :] + ys.reshape(-1, 1) * cam_a[5:8][None, :] - cam_a[12:15][None, :]).astype(np.float32)
+        o = np.tile(cam_a[12:15], (d.shape[0], 1)).astype(np.float32)
+        tt, tri, ms1 = soup.trace_rays(o, d)
+        hit = tri >= 0
+        rs = np.random.RandomState(1)
+        d2 = rs.randn(int(hit.sum()), 3).astype(np.float32)
+        o2 = (o[hit] + tt[hit, None] * d[hit] + 1e-3 * d2).astype(np.float32)
+        _, _, ms2 = soup.trace_rays(o2, d2)
+        lb["trace"] = {"primary_rays_per_s": d.shape[0] / (ms1 * 1e-3), "secondary_rays_per_s": d2.shape[0] / (ms2 * 1e-3), "primary_hit_fraction": float(hit.mean())}
         del soup
 
     cpu_base = None

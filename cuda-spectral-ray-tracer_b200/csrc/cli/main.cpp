@@ -39,6 +39,24 @@ int main(int argc, char** argv) {
     std::fprintf(stderr, "done, took %g seconds.\n", sec);
     std::printf("total rendering time (seconds): %g\nkernel time (ms): %g\nsamples/s: %g\nrays: %llu\n", sec, st.render_ms,
                 st.samples / (st.render_ms * 1e-3), (unsigned long long)st.rays);
+    if (srt_params_log_active(pm)) {  // same "key: value" lines as the reference's log_context (_log_/log_context.cpp:5-65)
+        mkdir("logs", 0755);
+        std::string dir = "logs";
+        if (srt_params_log_subdir(pm)[0]) { dir += std::string("/") + srt_params_log_subdir(pm); mkdir(dir.c_str(), 0755); }
+        std::string title = srt_params_img_title(pm);
+        for (char& c : title) c = c == ' ' ? '_' : (char)std::tolower((unsigned char)c);
+        const long long ts = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
+        const std::string path = dir + "/" + std::to_string(ts) + "_" + title + "_log.txt";
+        if (FILE* f = std::fopen(path.c_str(), "w")) {
+            std::fprintf(f, "image width: %u\nimage height: %u\nscene type: %s\n# primitives: %u\n# materials: %u\nsamples per pixel: %u\nbounce limit: %u\n",
+                         cam.width, cam.height, srt_params_scene_id(pm) == 1 ? "Prism World" : (srt_params_scene_id(pm) == 2 ? "Different Materials" : "Cornell Box"),
+                         srt_scene_num_tris(scene), srt_scene_num_materials(scene), srt_params_nsamples(pm), srt_params_bounce_limit(pm));
+            std::fprintf(f, "chunk width: %u\nchunk height: %u\ntotal rendering time (seconds): %g\nkernel time (ms): %g\nsamples per second: %g\nrays: %llu\nlbvh build (ms): %g\n",
+                         srt_params_xcsize(pm), srt_params_ycsize(pm), sec, st.render_ms, st.samples / (st.render_ms * 1e-3), (unsigned long long)st.rays, st.lbvh_ms);
+            std::fclose(f);
+            std::printf("log written to %s\n", path.c_str());
+        }
+    }
     if (srt_params_do_save(pm)) {
         std::string name = srt_params_img_title(pm);
         for (char& c : name) c = c == ' ' ? '_' : (char)std::tolower((unsigned char)c);  // utils/utility.h:30-39
