@@ -99,9 +99,8 @@ struct DeviceRenderer {
     uint32_t* d_tiles = nullptr;
     std::vector<uint32_t> h_tiles;  // chunk-local tiles this rank owns
     unsigned long long* d_rays = nullptr;
-    float* d_rgb = nullptr;         // resolve staging (device), 3 planes of max chunk
-    float* d_xyz = nullptr;
-    float* h_stage = nullptr;       // pinned, 6 planes of max chunk
+    unsigned char* d_rgb = nullptr; // resolve staging (device), 3 byte planes of one chunk
+    unsigned char* h_stage = nullptr;  // pinned: 3 byte planes of one chunk, or 3 float planes of the whole film (get_xyz)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // stats
@@ -147,7 +146,7 @@ void collect_kernel_times(DeviceRenderer* r) {
 
 void device_renderer_destroy(DeviceRenderer* r) {
     if (!r) return;
-    cudaFree(r->d_cie); cudaFree(r->d_bg); cudaFree(r->d_tiles); cudaFree(r->d_rays); pool_free(r->d_rgb); pool_free(r->d_xyz);
+    cudaFree(r->d_cie); cudaFree(r->d_bg); cudaFree(r->d_tiles); cudaFree(r->d_rays); pool_free(r->d_rgb);
     pool_free(r->P.R0); pool_free(r->P.R1); pool_free(r->P.P0); pool_free(r->P.P1); pool_free(r->P.G0); pool_free(r->P.G1); pool_free(r->P.sidx); pool_free(r->P.acc);
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->ev0) cudaEventDestroy(r->ev0);
@@ -209,9 +208,8 @@ static bool renderer_setup(DeviceRenderer* r) {
     SRT_CUDA(cudaMalloc((void**)&r->d_rays, sizeof(unsigned long long)));
     SRT_CUDA(cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), r->stream));
     const size_t chunk_px = (size_t)c.chunk_w * c.chunk_h;
-    if (!pool_alloc((void**)&r->d_rgb, 3 * chunk_px * sizeof(float))) return false;
-    if (!pool_alloc((void**)&r->d_xyz, 3 * chunk_px * sizeof(float))) return false;
-    r->h_stage = pinned_staging(6 * chunk_px * sizeof(float));
+    if (!pool_alloc((void**)&r->d_rgb, 3 * chunk_px)) return false;
+    r->h_stage = (unsigned char*)pinned_staging(3 * chunk_px);
     r->chunk_px = chunk_px;
     if (!r->h_stage) return false;
     std::vector<float> cie(3 * SRT_NS);
@@ -298,30 +296,45 @@ bool device_renderer_render_chunk(DeviceRenderer* r, unsigned off_x, unsigned of
     return true;
 }
 
-bool device_renderer_resolve(DeviceRenderer* r, unsigned off_x, unsigned off_y, unsigned w, unsigned h, float* fr, float* fg, float* fb, float* xyz,
+bool device_renderer_resolve(DeviceRenderer* r, unsigned off_x, unsigned off_y, unsigned w, unsigned h, float* fr, float* fg, float* fb,
                              unsigned img_w, unsigned img_h) {
     const LaunchTable& T = table(r->cfg.fp_strict);
     const size_t n = (size_t)w * h;
     if (n > r->chunk_px) {  // whole-image resolve after a chunked / reduced render: go band by band
         const unsigned rows = std::max(1u, (unsigned)(r->chunk_px / w));
         for (unsigned y = 0; y < h; y += rows)
-            if (!device_renderer_resolve(r, off_x, off_y + y, w, std::min(rows, h - y), fr, fg, fb, xyz, img_w, img_h)) return false;
+            if (!device_renderer_resolve(r, off_x, off_y + y, w, std::min(rows, h - y), fr, fg, fb, img_w, img_h)) return false;
         return true;
     }
-    T.resolve(r->P.acc, r->P.plane, r->P.img_w, off_x, off_y, w, h, r->P.spp, r->d_rgb, r->d_xyz, r->stream);
+    T.resolve(r->P.acc, r->P.plane, r->P.img_w, off_x, off_y, w, h, r->P.spp, r->d_rgb, r->stream);
     r->launches++; count_launch();
     r->cat_launches[3]++;
     SRT_CUDA_LAST();
-    SRT_CUDA(cudaMemcpyAsync(r->h_stage, r->d_rgb, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
-    SRT_CUDA(cudaMemcpyAsync(r->h_stage + 3 * n, r->d_xyz, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    r->h_stage = (unsigned char*)pinned_staging(3 * n);
+    if (!r->h_stage) return false;
+    SRT_CUDA(cudaMemcpyAsync(r->h_stage, r->d_rgb, 3 * n, cudaMemcpyDeviceToHost, r->stream));
     SRT_CUDA(cudaStreamSynchronize(r->stream));
     float* dst[3] = {fr, fg, fb};
-    const size_t img_plane = (size_t)img_w * img_h;
-    for (int c = 0; c < 3; c++)
+    for (int c = 0; c < 3; c++) {
+        if (!dst[c]) continue;
         for (unsigned y = 0; y < h; y++) {
-            if (dst[c]) memcpy(dst[c] + (size_t)(off_y + y) * img_w + off_x, r->h_stage + c * n + (size_t)y * w, w * sizeof(float));
-            if (xyz) memcpy(xyz + c * img_plane + (size_t)(off_y + y) * img_w + off_x, r->h_stage + 3 * n + c * n + (size_t)y * w, w * sizeof(float));
+            const unsigned char* src = r->h_stage + c * n + (size_t)y * w;
+            float* o = dst[c] + (size_t)(off_y + y) * img_w + off_x;
+            for (unsigned x = 0; x < w; x++) o[x] = (float)src[x];  // frame_buffer holds 0..255 as float (frame_buffer.cuh:6-44)
         }
+    }
+    return true;
+}
+
+// pre-tonemap film: XYZ sums -> mean, with the same float operation as the kernels ((1/spp) * v)
+bool device_renderer_download_xyz(DeviceRenderer* r, float* xyz) {
+    const size_t n = 3 * r->P.plane;
+    float* stage = pinned_staging(n * sizeof(float));
+    if (!stage) return false;
+    SRT_CUDA(cudaMemcpyAsync(stage, r->P.acc, n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    SRT_CUDA(cudaStreamSynchronize(r->stream));
+    const float inv = 1 / (float)r->P.spp;
+    for (size_t i = 0; i < n; i++) xyz[i] = inv * stage[i];
     return true;
 }
 

@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_megakernel(WaveParams P) {
 
 // film: XYZ sum / spp -> sRGB 0..255 (save_to_fb rendering.cu:140-149, color.cu:15-49), raster order
 __global__ void k_resolve(const float* __restrict__ acc, size_t plane, uint32_t img_w, uint32_t off_x, uint32_t off_y, uint32_t w, uint32_t h,
-                          uint32_t spp, float* __restrict__ out_rgb, float* __restrict__ out_xyz) {
+                          uint32_t spp, unsigned char* __restrict__ out_rgb) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w * h) return;
     const uint32_t cy = i / w, cx = i - cy * w;
@@ -684,11 +684,8 @@ __global__ void k_resolve(const float* __restrict__ acc, size_t plane, uint32_t 
     for (int c = 0; c < 3; c++) {
         const float v = lin[c];
         const float g = v < 0.0f ? 0.0f : (v < 0.0031308f ? 12.92f * v : (v < 1.0f ? ((1.055f * powf(v, 0.416666f)) - 0.055f) : 1.0f));
-        out_rgb[c * n + i] = (float)(int)(g * 255.99f);
+        out_rgb[c * n + i] = (unsigned char)(int)(g * 255.99f);  // 0..255: one byte per channel crosses PCIe, the host widens it
     }
-    out_xyz[i] = X;
-    out_xyz[n + i] = Y;
-    out_xyz[2 * n + i] = Z;
 }
 
 // standalone closest-hit queries (BASELINE.json configs[3]); always global-memory scene
@@ -744,10 +741,8 @@ LaunchTable make_launch_table() {
         else k_wavefront<false, false><<<grid, SRT_WAVE_BLOCK, smem, st>>>(P);
     };
     t.megakernel = [](const WaveParams& P, int mode, int grid, size_t smem, cudaStream_t st) { SRT_DISPATCH(k_megakernel, mode, grid, smem, st, P); };
-    t.resolve = [](const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, float* rgb,
-                   float* xyz, cudaStream_t st) {
-        k_resolve<<<(w * h + 255) / 256, 256, 0, st>>>(acc, plane, img_w, ox, oy, w, h, spp, rgb, xyz);
-    };
+    t.resolve = [](const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,
+                   cudaStream_t st) { k_resolve<<<(w * h + 255) / 256, 256, 0, st>>>(acc, plane, img_w, ox, oy, w, h, spp, rgb); };
     t.trace_rays = [](const WaveParams& P, uint32_t n, const float* o, const float* d, const uint32_t* sorted_idx, float* t_out, int32_t* tri_out,
                       int grid, cudaStream_t st) { k_trace_rays<<<grid, SRT_BLOCK, 0, st>>>(P, n, o, d, sorted_idx, t_out, tri_out); };
     return t;

@@ -56,8 +56,8 @@ struct LaunchTable {
     void (*init_slots)(const WaveParams&, cudaStream_t);
     void (*wavefront)(const WaveParams&, int mode, int grid, size_t smem, cudaStream_t);
     void (*megakernel)(const WaveParams&, int mode, int grid, size_t smem, cudaStream_t);
-    void (*resolve)(const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, float* rgb,
-                    float* xyz, cudaStream_t);
+    void (*resolve)(const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,
+                    cudaStream_t);
     void (*trace_rays)(const WaveParams&, uint32_t n, const float* o, const float* d, const uint32_t* sorted_idx, float* t_out, int32_t* tri_out,
                        int grid, cudaStream_t);
 };

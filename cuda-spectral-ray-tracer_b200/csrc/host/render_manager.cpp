@@ -87,7 +87,6 @@ int RenderManager::init_device_params(unsigned cw, unsigned ch) {  // render_man
     device_renderer_destroy(dev_);
     dev_ = device_renderer_create(scene_->dev, cfg_);
     if (!dev_) return SRT_ERR_CUDA;
-    xyz_.assign(3ull * cam_.width * cam_.height, 0.f);
     i_ = 0;
     off_x_ = off_y_ = 0;
     next_write_ = next_read_ = 0;
@@ -139,7 +138,7 @@ int RenderManager::update_fb() {  // render_manager.cuh:68-142
         if (!slot->full) return worker_rc_;
     }
     // the film already is in raster order: the reference's block-linear un-swizzle (:88-133) has no counterpart
-    const bool ok = device_renderer_resolve(dev_, slot->off_x, slot->off_y, slot->w, slot->h, fb_r_, fb_g_, fb_b_, xyz_.data(), cam_.width, cam_.height);
+    const bool ok = device_renderer_resolve(dev_, slot->off_x, slot->off_y, slot->w, slot->h, fb_r_, fb_g_, fb_b_, cam_.width, cam_.height);
     const bool last = slot->is_last;
     {
         std::lock_guard<std::mutex> lock(mu_);
@@ -177,13 +176,12 @@ int RenderManager::end_render() {  // render_manager.cuh:169-174
 
 int RenderManager::get_xyz(float* xyz) {
     if (!device_inited_) { set_error("render manager: not initialised"); return SRT_ERR_STATE; }
-    std::copy(xyz_.begin(), xyz_.end(), xyz);
-    return SRT_OK;
+    return device_renderer_download_xyz(dev_, xyz) ? SRT_OK : SRT_ERR_CUDA;
 }
 float* RenderManager::device_film() { return dev_ ? device_renderer_film(dev_) : nullptr; }
 int RenderManager::resolve_film() {
     if (!dev_) { set_error("render manager: not initialised"); return SRT_ERR_STATE; }
-    return device_renderer_resolve(dev_, 0, 0, cam_.width, cam_.height, fb_r_, fb_g_, fb_b_, xyz_.data(), cam_.width, cam_.height) ? SRT_OK : SRT_ERR_CUDA;
+    return device_renderer_resolve(dev_, 0, 0, cam_.width, cam_.height, fb_r_, fb_g_, fb_b_, cam_.width, cam_.height) ? SRT_OK : SRT_ERR_CUDA;
 }
 int RenderManager::restart() {  // make the manager renderable again from its first chunk (same seeds, empty film)
     end_render();

@@ -156,7 +156,8 @@ void device_renderer_destroy(DeviceRenderer*);
 bool device_renderer_render_chunk(DeviceRenderer*, unsigned off_x, unsigned off_y, unsigned w, unsigned h);
 // tonemaps film region -> host planes (pinned staging inside); any pointer may be null
 bool device_renderer_resolve(DeviceRenderer*, unsigned off_x, unsigned off_y, unsigned w, unsigned h, float* r, float* g,
-                             float* b, float* xyz, unsigned img_w, unsigned img_h);
+                             float* b, unsigned img_w, unsigned img_h);
+bool device_renderer_download_xyz(DeviceRenderer*, float* xyz);
 float* device_renderer_film(DeviceRenderer*);
 bool device_renderer_reset(DeviceRenderer*);
 void device_renderer_stats(const DeviceRenderer*, srt_stats* s);
@@ -206,7 +207,6 @@ private:
     Scene* scene_;
     srt_camera cam_;
     float *fb_r_, *fb_g_, *fb_b_;
-    std::vector<float> xyz_;
     bool scene_inited_ = false, renderer_inited_ = false, device_inited_ = false, done_ = true;
     RenderConfig cfg_;
     DeviceRenderer* dev_ = nullptr;

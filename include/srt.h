@@ -179,7 +179,7 @@ int srt_rm_render_all(srt_render_manager*);
 #define SRT_OPT_TRAVERSAL 10     /* 0 auto (wide-leaf closest hit when the scene has <= 64 triangles), 1 force the LBVH walk
                                     (scene in shared memory), 3 force the LBVH walk with the scene in global memory */
 int srt_rm_set_option(srt_render_manager*, int option, int value);
-/* pre-tonemap film of the whole image: 3 raster planes of XYZ (mean over spp) */
+/* pre-tonemap film of the whole image: 3 raster planes of XYZ (mean over spp); downloaded on demand */
 int srt_rm_get_xyz(srt_render_manager*, float* xyz);
 /* device pointer to the XYZ SUM film (3 planes, W*H floats each, zeros outside owned tiles);
  * a caller that owns an NCCL communicator reduces it in place and then calls srt_rm_tonemap_device */
