@@ -220,3 +220,54 @@ def test_full_size_properties(srt):
     assert 3.0 < rays_per_sample < 3.6  # 3.28
     g1 = oracle.render(oracle.Scene(0), oracle.camera(400, 225), 8, 10)[1]
     assert np.allclose(xyz.reshape(3, -1).mean(1), g1.reshape(3, -1).mean(1), rtol=0.15)
+
+
+def test_api_guards_and_degenerate_inputs(srt):
+    """call-order guards (render_manager.cu:87-88,100-101,131), empty scenes, zero samples"""
+    L = srt.lib()
+    sc = srt.Scene(1)
+    cam = sc.camera(32, 18)
+    fb = srt.FrameBuffer(32, 18)
+    rm = srt.RenderManager(sc, cam, fb)
+    assert L.srt_rm_init_device_params(rm.h, 0, 0) == 3  # SRT_ERR_STATE: init_renderer must come first
+    assert not rm.isReadyToRender()
+    assert L.srt_rm_step(rm.h) < 0
+    rm.init_renderer(10, 2)
+    rm.init_device_params(0, 0)
+    assert rm.isReadyToRender()
+    assert L.srt_rm_set_option(rm.h, srt.OPT_FP_MODE, 1) == 3  # options are frozen after init_device_params
+    assert rm.step() is False  # single chunk: no more chunks after this one
+    assert rm.update_fb() is False
+    assert rm.isDone() and not rm.isReadyToRender()
+    assert L.srt_rm_step(rm.h) == 0  # nothing left
+    first = fb.rgb().copy()
+    rm.restart()
+    rm.render_all()
+    assert np.array_equal(first, fb.rgb())  # same seeds -> same image
+    # a scene without triangles renders black and does not crash
+    m = srt.MaterialDesc(type=srt.MAT_LAMBERTIAN, color=(0.5, 0.5, 0.5), fuzz=1.0)
+    empty = srt.Scene(mesh=(np.zeros((0, 9), np.float32), np.zeros(0, np.uint32), [m]))
+    rgb, xyz, st = srt.render(scene=empty, w=40, h=20, spp=2, bounce=4)
+    assert rgb.max() == 0 and st["rays"] == 40 * 20 * 2
+    # single triangle (LBVH with no internal node) in front of the camera, emissive: some pixels light up
+    tri = np.array([[100, 100, 100, 450, 100, 100, 278, 450, 100]], np.float32)
+    e = srt.MaterialDesc(type=srt.MAT_EMISSIVE, color=(1, 1, 1), fuzz=1.0, emission_power=2.0)
+    one = srt.Scene(mesh=(tri, np.zeros(1, np.uint32), [e]))
+    for trav in (0, 1, 3):
+        rgb, xyz, st = srt.render(scene=one, w=64, h=36, spp=1, bounce=3, traversal=trav)
+        assert 50 < (rgb.sum(0) > 0).sum() < 64 * 36
+    # a triangle that references a missing material is rejected
+    with pytest.raises(srt.SrtError):
+        srt.Scene(mesh=(tri, np.array([3], np.uint32), [e]))
+    # spp = 0: film / 0 = NaN -> OETF falls through to 1.0 -> 255, exactly what the reference's arithmetic does
+    rgb, xyz, st = srt.render(scene_id=1, w=16, h=9, spp=0, bounce=3)
+    assert rgb.min() == 255
+
+
+def test_obj_scene_renders(srt, tmp_path):
+    obj = tmp_path / "floor_and_light.obj"
+    obj.write_text("v 0 0 0\nv 555 0 0\nv 555 0 555\nv 0 0 555\nf 1 2 3 4\n")
+    m = srt.MaterialDesc(type=srt.MAT_EMISSIVE, color=(1, 1, 1), fuzz=1.0, emission_power=1.0)
+    sc = srt.Scene(obj=(obj, [m]))
+    rgb, xyz, st = srt.render(scene=sc, w=64, h=36, spp=1, bounce=2)
+    assert (rgb[:, 30:, :].sum(0) > 0).any() and rgb[:, :10, :].max() == 0  # the glowing floor fills the lower half only
