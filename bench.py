@@ -272,6 +272,27 @@ def main():
     total_samples = w * h * spp
     value = total_samples / (step_ms * 1e-3)
 
+    # ---- the same resident-state measurement in strict FP mode (-fmad=false kernels: the mode whose film is
+    # bit-identical to the reference's host-compiled image); reported next to the headline, single GPU only
+    strict_info = None
+    if world == 1 and not a.strict:
+        fb_s = S.FrameBuffer(w, h)
+        rm_s = S.RenderManager(sc, cam, fb_s)
+        rm_s.init_renderer(depth, spp)
+        rm_s.set_option(S.OPT_FP_MODE, 1)
+        rm_s.set_option(S.OPT_TILE_W, a.tile_w); rm_s.set_option(S.OPT_TILE_H, a.tile_h)
+        rm_s.init_device_params(0, 0)
+        ms_s = []
+        for i in range(2 + min(a.steps, 3)):
+            rm_s.restart()
+            while rm_s.step():
+                pass
+            if i >= 2:
+                ms_s.append(rm_s.stats()["render_ms"])
+        strict_info = {"value": total_samples / (float(np.mean(ms_s)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ms_s)),
+                       "what": "same workload, kernels built with -fmad=false: film bit-identical to the reference's host build (tests/test_gpu_parity.py)"}
+        del rm_s
+
     # ---- end-to-end arm: host buffers in, host film out, every step
     def e2e_step():
         sc2 = S.Scene(scene_id)  # host triangle/material build + H2D + device LBVH
@@ -357,13 +378,19 @@ def main():
         ys, xs = np.mgrid[0:1080, 0:1920]
         d = (cam_a[8:11][None, :] + xs.reshape(-1, 1) * cam_a[2:5][None, :] + ys.reshape(-1, 1) * cam_a[5:8][None, :] - cam_a[12:15][None, :]).astype(np.float32)
         o = np.tile(cam_a[12:15], (d.shape[0], 1)).astype(np.float32)
-        tt, tri, ms1 = soup.trace_rays(o, d)
+        tt, tri, ms1, v1 = soup.trace_rays(o, d, counted=True)
         hit = tri >= 0
         rs = np.random.RandomState(1)
         d2 = rs.randn(int(hit.sum()), 3).astype(np.float32)
         o2 = (o[hit] + tt[hit, None] * d[hit] + 1e-3 * d2).astype(np.float32)
-        _, _, ms2 = soup.trace_rays(o2, d2)
-        lb["trace"] = {"primary_rays_per_s": d.shape[0] / (ms1 * 1e-3), "secondary_rays_per_s": d2.shape[0] / (ms2 * 1e-3), "primary_hit_fraction": float(hit.mean())}
+        _, _, ms2, v2 = soup.trace_rays(o2, d2, counted=True)
+        def walk_roofline(visits, ms):  # 32 B per node visit + 48 B per triangle test
+            ach = (32.0 * visits[0] + 48.0 * visits[1]) / (ms * 1e-3) / 1e9
+            return {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": hbm_src}
+        lb["trace"] = {"primary_rays_per_s": d.shape[0] / (ms1 * 1e-3), "secondary_rays_per_s": d2.shape[0] / (ms2 * 1e-3), "primary_hit_fraction": float(hit.mean()),
+                       "primary_nodes_per_ray": v1[0] / d.shape[0], "primary_tris_per_ray": v1[1] / d.shape[0],
+                       "secondary_nodes_per_ray": v2[0] / max(1, d2.shape[0]), "secondary_tris_per_ray": v2[1] / max(1, d2.shape[0]),
+                       "primary_roofline": walk_roofline(v1, ms1), "secondary_roofline": walk_roofline(v2, ms2)}
         del soup
 
     cpu_base = None
@@ -386,6 +413,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_base,
         "reference_cuda": ref_cuda,
+        "strict_fp": strict_info,
         "lbvh": lb,
     }
     print(json.dumps(line))

@@ -362,7 +362,7 @@ void device_renderer_stats(const DeviceRenderer* r, srt_stats* s) {
     s->generate_launches = r->cat_launches[0]; s->shade_launches = r->cat_launches[1]; s->tail_launches = r->cat_launches[2];
 }
 
-bool device_scene_trace(const DeviceScene* s, uint32_t n, const float* o, const float* d, float* t, int32_t* tri, float* ms) {
+bool device_scene_trace(const DeviceScene* s, uint32_t n, const float* o, const float* d, float* t, int32_t* tri, float* ms, uint64_t* visits) {
     WaveParams P{};
     P.nodes = device_scene_nodes(s); P.tris = device_scene_tris(s); P.mats = device_scene_mats(s); P.n_tris = (int)device_scene_ntris(s);
     float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
@@ -378,11 +378,22 @@ bool device_scene_trace(const DeviceScene* s, uint32_t n, const float* o, const 
     SRT_CUDA(cudaMemcpy(d_d, d, 3ull * n * sizeof(float), cudaMemcpyHostToDevice));
     const int grid = (int)std::min<uint64_t>((n + SRT_BLOCK - 1) / SRT_BLOCK, (uint64_t)sm_count() * 8);
     const LaunchTable& T = table(1);
-    T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, grid, nullptr);  // warm-up
+    T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, nullptr, grid, nullptr);  // warm-up
     SRT_CUDA(cudaEventRecord(e0));
-    T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, grid, nullptr);
+    T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, nullptr, grid, nullptr);
     SRT_CUDA(cudaEventRecord(e1));
     count_launch(2);
+    if (visits) {  // untimed third pass that counts node visits and leaf tests (algorithmic bytes of the walk)
+        unsigned long long* d_cnt = nullptr;
+        SRT_CUDA(cudaMalloc((void**)&d_cnt, 2 * sizeof(unsigned long long)));
+        SRT_CUDA(cudaMemset(d_cnt, 0, 2 * sizeof(unsigned long long)));
+        T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, d_cnt, grid, nullptr);
+        count_launch();
+        unsigned long long h[2] = {0, 0};
+        SRT_CUDA(cudaMemcpy(h, d_cnt, sizeof h, cudaMemcpyDeviceToHost));
+        visits[0] = h[0]; visits[1] = h[1];
+        cudaFree(d_cnt);
+    }
     SRT_CUDA(cudaEventSynchronize(e1));
     SRT_CUDA_LAST();
     float el = 0;

@@ -132,6 +132,26 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 // equal-t ties go to the triangle the reference would have tested last (SrtTri::prio, host/ref_order.cpp)
+// leaf test of the LBVH walk: most leaves whose box the ray enters are still missed, so look at the
+// plane distance with an approximate reciprocal first and only run the exact arithmetic (IEEE
+// division, 2-D edge functions) when the hit could matter.  The skip is conservative: it needs the
+// approximate t to be outside [0, closest] by far more than its error (relative 1e-5 + the
+// cancellation bound of D - n.o), NaN falls through to the exact test.
+__device__ __forceinline__ void consider_leaf(const SrtTri* __restrict__ tris, int i, V3 o, V3 d, float& closest, int& best, uint32_t& best_prio) {
+    const float4 q0 = *reinterpret_cast<const float4*>(tris + i);
+    const float denom = __fmaf_rn(q0.z, d.z, __fmaf_rn(q0.y, d.y, q0.x * d.x));
+    const float no = __fmaf_rn(q0.z, o.z, __fmaf_rn(q0.y, o.y, q0.x * o.x));
+    const float num = q0.w - no;
+    const float slack = 8e-6f * (fabsf(q0.w) + fabsf(q0.x * o.x) + fabsf(q0.y * o.y) + fabsf(q0.z * o.z));
+    const float ta = num * rcp_approx(denom);
+    const bool far_behind = (ta < 0.0f) & (fabsf(num) > slack);
+    const bool far_beyond = ta > closest * 1.00002f + 1e-30f;
+    if (far_behind | (far_beyond & (fabsf(num) > slack))) return;
+    float t;
+    if (!tri_test(tris + i, o, d, closest, t)) return;
+    const uint32_t prio = tris[i].prio;
+    if (t < closest || best < 0 || prio > best_prio) { closest = t; best = i; best_prio = prio; }
+}
 __device__ __forceinline__ void consider_hit(const SrtTri* __restrict__ tris, int i, V3 o, V3 d, float& closest, int& best, uint32_t& best_prio) {
     float t;
     if (!tri_test(tris + i, o, d, closest, t)) return;
@@ -191,7 +211,7 @@ __device__ __forceinline__ int closest_hit_flat(const SceneRef& sc, V3 o, V3 d, 
 // closest hit over the LBVH: both child boxes live in the parent node (4 x 16-B loads),
 // near child first, far child pushed.  Returns leaf-order triangle index or -1.
 template <bool FLAT>
-__device__ __forceinline__ int closest_hit(const SceneRef& sc, V3 o, V3 d, float& t_hit) {
+__device__ __forceinline__ int closest_hit(const SceneRef& sc, V3 o, V3 d, float& t_hit, uint32_t* visits = nullptr) {
     float closest = FLT_MAX;
     int best = -1;
     uint32_t best_prio = 0;
@@ -211,6 +231,7 @@ __device__ __forceinline__ int closest_hit(const SceneRef& sc, V3 o, V3 d, float
     int node = 0;
     while (true) {
         const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
+        if (visits) visits[0]++;
         const float4 b0 = np[0], b1 = np[1], b2 = np[2];
         const int4 ch = *reinterpret_cast<const int4*>(np + 3);
         // slabs; a NaN direction makes every comparison below false -> both children are visited,
@@ -237,11 +258,11 @@ __device__ __forceinline__ int closest_hit(const SceneRef& sc, V3 o, V3 d, float
         // c0 = first child to process (if h0), c1 = second (if h1)
         int next = -1;
         if (h0) {
-            if (c0 < 0) consider_hit(sc.tris, ~c0, o, d, closest, best, best_prio);
+            if (c0 < 0) { if (visits) visits[1]++; consider_leaf(sc.tris, ~c0, o, d, closest, best, best_prio); }
             else next = c0;
         }
         if (h1) {
-            if (c1 < 0) consider_hit(sc.tris, ~c1, o, d, closest, best, best_prio);
+            if (c1 < 0) { if (visits) visits[1]++; consider_leaf(sc.tris, ~c1, o, d, closest, best, best_prio); }
             else if (next < 0) next = c1;
             else stack[sp++] = c1;
         }
@@ -689,16 +710,20 @@ __global__ void k_resolve(const float* __restrict__ acc, size_t plane, uint32_t 
 }
 
 // standalone closest-hit queries (BASELINE.json configs[3]); always global-memory scene
+template <bool COUNT>
 __global__ void __launch_bounds__(SRT_BLOCK) k_trace_rays(WaveParams P, uint32_t n, const float* __restrict__ o, const float* __restrict__ d,
                                                           const uint32_t* __restrict__ sorted_idx, float* __restrict__ t_out,
-                                                          int32_t* __restrict__ tri_out) {
+                                                          int32_t* __restrict__ tri_out, unsigned long long* counters) {
     SceneRef sc;
     sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float t = 0.f;
-        const int tri = closest_hit<false>(sc, mk(o[3ull * i], o[3ull * i + 1], o[3ull * i + 2]), mk(d[3ull * i], d[3ull * i + 1], d[3ull * i + 2]), t);
+        uint32_t visits[2] = {0, 0};
+        const int tri = closest_hit<false>(sc, mk(o[3ull * i], o[3ull * i + 1], o[3ull * i + 2]), mk(d[3ull * i], d[3ull * i + 1], d[3ull * i + 2]), t,
+                                           COUNT ? visits : nullptr);
         t_out[i] = tri >= 0 ? t : -1.0f;
         tri_out[i] = tri >= 0 ? (int32_t)sorted_idx[tri] : -1;
+        if (COUNT) { atomicAdd(counters, (unsigned long long)visits[0]); atomicAdd(counters + 1, (unsigned long long)visits[1]); }
     }
 }
 
@@ -744,7 +769,10 @@ LaunchTable make_launch_table() {
     t.resolve = [](const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,
                    cudaStream_t st) { k_resolve<<<(w * h + 255) / 256, 256, 0, st>>>(acc, plane, img_w, ox, oy, w, h, spp, rgb); };
     t.trace_rays = [](const WaveParams& P, uint32_t n, const float* o, const float* d, const uint32_t* sorted_idx, float* t_out, int32_t* tri_out,
-                      int grid, cudaStream_t st) { k_trace_rays<<<grid, SRT_BLOCK, 0, st>>>(P, n, o, d, sorted_idx, t_out, tri_out); };
+                      unsigned long long* counters, int grid, cudaStream_t st) {
+        if (counters) k_trace_rays<true><<<grid, SRT_BLOCK, 0, st>>>(P, n, o, d, sorted_idx, t_out, tri_out, counters);
+        else k_trace_rays<false><<<grid, SRT_BLOCK, 0, st>>>(P, n, o, d, sorted_idx, t_out, tri_out, nullptr);
+    };
     return t;
 }
 

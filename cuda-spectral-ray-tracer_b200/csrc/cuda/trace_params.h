@@ -59,7 +59,7 @@ struct LaunchTable {
     void (*resolve)(const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,
                     cudaStream_t);
     void (*trace_rays)(const WaveParams&, uint32_t n, const float* o, const float* d, const uint32_t* sorted_idx, float* t_out, int32_t* tri_out,
-                       int grid, cudaStream_t);
+                       unsigned long long* counters, int grid, cudaStream_t);
 };
 
 namespace fastfp { LaunchTable make_launch_table(); }

@@ -166,7 +166,14 @@ int srt_scene_rebuild_lbvh(srt_scene* s, int repeats, float ms_out[5]) {
 int srt_scene_trace_rays(const srt_scene* s, uint32_t n, const float* o, const float* d, float* t_out, int32_t* tri_out, float* ms_out) {
     if (!s || !s->s.dev || !o || !d || !t_out || !tri_out) { set_error("bad argument"); return SRT_ERR_ARG; }
     if (n == 0) return SRT_OK;
-    return device_scene_trace(s->s.dev, n, o, d, t_out, tri_out, ms_out) ? SRT_OK : SRT_ERR_CUDA;
+    return device_scene_trace(s->s.dev, n, o, d, t_out, tri_out, ms_out, nullptr) ? SRT_OK : SRT_ERR_CUDA;
+}
+int srt_scene_trace_rays_counted(const srt_scene* s, uint32_t n, const float* o, const float* d, float* t_out, int32_t* tri_out, float* ms_out,
+                                 uint64_t visits_out[2]) {
+    if (!s || !s->s.dev || !o || !d || !t_out || !tri_out || !visits_out) { set_error("bad argument"); return SRT_ERR_ARG; }
+    visits_out[0] = visits_out[1] = 0;
+    if (n == 0) return SRT_OK;
+    return device_scene_trace(s->s.dev, n, o, d, t_out, tri_out, ms_out, visits_out) ? SRT_OK : SRT_ERR_CUDA;
 }
 
 srt_render_manager* srt_render_manager_create(srt_scene* s, const srt_camera* cam, float* r, float* g, float* b) {

@@ -136,7 +136,7 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
 void device_scene_destroy(DeviceScene*);
 bool device_scene_build_lbvh(DeviceScene*, int repeats, float ms_out[5]);
 bool device_scene_download_lbvh(const DeviceScene*, LbvhDump& out);
-bool device_scene_trace(const DeviceScene*, uint32_t n, const float* o, const float* d, float* t, int32_t* tri, float* ms);
+bool device_scene_trace(const DeviceScene*, uint32_t n, const float* o, const float* d, float* t, int32_t* tri, float* ms, uint64_t* visits);
 double device_scene_lbvh_ms(const DeviceScene*);
 
 struct RenderConfig {

@@ -86,6 +86,7 @@ _SIGS = [
     ("srt_scene_get_lbvh", C.c_int, [_P] * 8),
     ("srt_scene_rebuild_lbvh", C.c_int, [_P, C.c_int, _P]),
     ("srt_scene_trace_rays", C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, _P]),
+    ("srt_scene_trace_rays_counted", C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, _P, _P]),
     ("srt_render_manager_create", _P, [_P, C.POINTER(Camera), _P, _P, _P]),
     ("srt_render_manager_destroy", None, [_P]),
     ("srt_rm_init_renderer", C.c_int, [_P, C.c_uint, C.c_uint]),
@@ -257,10 +258,14 @@ class Scene:
         _check(lib().srt_scene_rebuild_lbvh(self.h, repeats, ms.ctypes.data))
         return dict(total=float(ms[0]), bounds_morton=float(ms[1]), sort=float(ms[2]), hierarchy=float(ms[3]), refit_emit=float(ms[4]))
 
-    def trace_rays(self, o, d):
+    def trace_rays(self, o, d, counted=False):
         o = np.ascontiguousarray(o, np.float32); d = np.ascontiguousarray(d, np.float32)
         n = o.shape[0]
         t = np.zeros(n, np.float32); tri = np.zeros(n, np.int32); ms = C.c_float(0)
+        if counted:
+            v = np.zeros(2, np.uint64)
+            _check(lib().srt_scene_trace_rays_counted(self.h, n, o.ctypes.data, d.ctypes.data, t.ctypes.data, tri.ctypes.data, C.byref(ms), v.ctypes.data))
+            return t, tri, ms.value, (int(v[0]), int(v[1]))
         _check(lib().srt_scene_trace_rays(self.h, n, o.ctypes.data, d.ctypes.data, t.ctypes.data, tri.ctypes.data, C.byref(ms)))
         return t, tri, ms.value
 

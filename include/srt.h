@@ -138,6 +138,11 @@ int srt_scene_rebuild_lbvh(srt_scene*, int repeats, float ms_out[5]);
 int srt_scene_trace_rays(const srt_scene*, uint32_t n, const float* o, const float* d, float* t_out,
                          int32_t* tri_out, float* ms_out);
 
+/* same, plus visits_out = {BVH nodes visited, leaf triangles tested} summed over all rays (counted in an
+ * extra untimed pass): the algorithmic traffic of the walk is 32 B per node visit + 48 B per triangle test */
+int srt_scene_trace_rays_counted(const srt_scene*, uint32_t n, const float* o, const float* d, float* t_out,
+                                 int32_t* tri_out, float* ms_out, uint64_t visits_out[2]);
+
 /* ------------------------------------------------------------------ render manager
  * replaces rendering/render_manager.cuh:37-173 + render_manager.cu:3-132 and the renderer
  * behind it (rendering/rendering.cuh:39-155, rendering.cu:151-357). */

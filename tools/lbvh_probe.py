@@ -22,4 +22,7 @@ for n in (1 << 20, 10 * (1 << 20)):
     d2 = rs_.randn(p.shape[0], 3).astype(np.float32)
     t2, tri2, ms2 = sc.trace_rays(p + 1e-3 * d2, d2)
     print("   secondary (incoherent): %.2f ms, %.2f Grays/s, hit fraction %.3f" % (ms2, p.shape[0] / ms2 / 1e6, (tri2 >= 0).mean()), flush=True)
+    if n <= (1 << 20):
+        rgb, xyz, st = S.render(scene=sc, w=1920, h=1080, spp=4, bounce=10)
+        print('   render 1080p 4spp depth 10 through the wavefront: %.1f ms, %.3f Gsamples/s, %.2f Grays/s, rays/sample %.2f' % (st['render_ms'], st['samples']/st['render_ms']/1e6, st['rays']/st['render_ms']/1e6, st['rays']/st['samples']), flush=True)
     del sc
