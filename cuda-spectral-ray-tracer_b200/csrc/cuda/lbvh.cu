@@ -17,6 +17,8 @@
 #include <cfloat>
 #include <cstdio>
 #include <vector>
+#include <algorithm>
+#include <cmath>
 
 namespace srt {
 
@@ -71,6 +73,7 @@ struct DeviceScene {
     SrtTri* flat_tris = nullptr;
     uint32_t n_units = 0;
     double origin_l1_bound = 0;
+    float host_lo[3] = {0, 0, 0}, host_hi[3] = {0, 0, 0};  // union of the triangle boxes (host)
     uint32_t tiles = 0;
     cudaEvent_t ev[6];
     double last_build_ms = 0;
@@ -415,6 +418,9 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
         dm[m].type = mats[m].type;
     }
     const std::vector<uint32_t> prio = reference_test_order(tris);
+    for (int a = 0; a < 3; a++) { s->host_lo[a] = n ? INFINITY : 0.f; s->host_hi[a] = n ? -INFINITY : 0.f; }
+    for (const HostTri& t : tris)
+        for (int a = 0; a < 3; a++) { s->host_lo[a] = std::min(s->host_lo[a], t.bbox[2 * a]); s->host_hi[a] = std::max(s->host_hi[a], t.bbox[2 * a + 1]); }
     for (uint32_t i = 0; i < n; i++) {
         for (int k = 0; k < 3; k++) { verts[9ull * i + 3 * k] = tris[i].v[k].x; verts[9ull * i + 3 * k + 1] = tris[i].v[k].y; verts[9ull * i + 3 * k + 2] = tris[i].v[k].z; }
         const uint32_t mt = tris[i].mat < mats.size() ? mats[tris[i].mat].type : SRT_LAMBERTIAN;
@@ -547,6 +553,7 @@ const SrtFlatUnit* device_scene_flat_units(const DeviceScene* s) { return s->fla
 const SrtTri* device_scene_flat_tris(const DeviceScene* s) { return s->flat_tris; }
 uint32_t device_scene_n_units(const DeviceScene* s) { return s->n_units; }
 double device_scene_origin_bound(const DeviceScene* s) { return s->origin_l1_bound; }
+void device_scene_bounds(const DeviceScene* s, float lo[3], float hi[3]) { for (int a = 0; a < 3; a++) { lo[a] = s->host_lo[a]; hi[a] = s->host_hi[a]; } }
 const SrtMaterial* device_scene_mats(const DeviceScene* s) { return s->mats; }
 uint32_t device_scene_ntris(const DeviceScene* s) { return s->n; }
 uint32_t device_scene_nmats(const DeviceScene* s) { return s->n_mats; }

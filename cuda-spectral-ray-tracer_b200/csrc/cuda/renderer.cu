@@ -17,6 +17,7 @@ const SrtFlatUnit* device_scene_flat_units(const DeviceScene* s);
 const SrtTri* device_scene_flat_tris(const DeviceScene* s);
 uint32_t device_scene_n_units(const DeviceScene* s);
 double device_scene_origin_bound(const DeviceScene* s);
+void device_scene_bounds(const DeviceScene* s, float lo[3], float hi[3]);
 const SrtMaterial* device_scene_mats(const DeviceScene* s);
 uint32_t device_scene_ntris(const DeviceScene* s);
 uint32_t device_scene_nmats(const DeviceScene* s);
@@ -174,7 +175,13 @@ static bool renderer_setup(DeviceRenderer* r) {
     P.img_w = c.cam.width; P.img_h = c.cam.height;
     P.tile_w = (uint32_t)std::max(1, c.tile_w); P.tile_h = (uint32_t)std::max(1, c.tile_h);
     P.block_slots = P.tile_w * P.tile_h;  // one wavefront block renders one tile
-    if (P.block_slots > 65536 || P.block_slots < 32) { set_error("tile area must be in [32, 65536]"); return false; }
+    if (P.block_slots > 65536 || P.block_slots < 32 || (P.tile_w & (P.tile_w - 1)) || (P.tile_h & (P.tile_h - 1))) {
+        set_error("tile width and height must be powers of two with an area in [32, 65536]");
+        return false;
+    }
+    for (P.block_slots_log2 = 0; (1u << P.block_slots_log2) < P.block_slots; P.block_slots_log2++) {}
+    for (P.tile_w_log2 = 0; (1u << P.tile_w_log2) < P.tile_w; P.tile_w_log2++) {}
+    device_scene_bounds(r->scene, P.scene_lo, P.scene_hi);
     P.tiles_x = (c.chunk_w + P.tile_w - 1) / P.tile_w;
     const uint32_t tiles_y = (c.chunk_h + P.tile_h - 1) / P.tile_h;
     P.rank = (uint32_t)c.rank; P.world = (uint32_t)std::max(1, c.world);

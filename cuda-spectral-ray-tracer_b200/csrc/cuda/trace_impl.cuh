@@ -422,10 +422,26 @@ enum : int { EV_DONE = -1 };  // sample finished; otherwise the value is the que
 
 // trace p's ray and either finish the sample or leave p at the hit (p.o = hit point).
 // Returns EV_DONE or the material queue (1 lambertian, 2 metallic, 3 dielectric); tri_out = leaf-order index.
+// ray vs the scene's bounding box, conservative (approximate reciprocals, 1e-4 relative slack)
+__device__ __forceinline__ bool misses_scene_box(const WaveParams& P, V3 o, V3 d) {
+    const float ix = rcp_approx(d.x), iy = rcp_approx(d.y), iz = rcp_approx(d.z);
+    const float ax = (P.scene_lo[0] - o.x) * ix, bx = (P.scene_hi[0] - o.x) * ix;
+    const float ay = (P.scene_lo[1] - o.y) * iy, by = (P.scene_hi[1] - o.y) * iy;
+    const float az = (P.scene_lo[2] - o.z) * iz, bz = (P.scene_hi[2] - o.z) * iz;
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    return tn > tf * 1.0002f + 1e-3f;  // NaN anywhere -> false -> not a certain miss
+}
+
 template <bool FLAT>
-__device__ __forceinline__ int extend(const SceneRef& sc, const WaveParams& P, Path& p, int& tri_out, float* acc, size_t pix) {
+__device__ __forceinline__ int extend(const SceneRef& sc, const WaveParams& P, Path& p, int& tri_out, float* acc, size_t pix, bool primary = false) {
     float t = 0.f;
-    const int tri = closest_hit<FLAT>(sc, p.o, p.d, t);
+    int tri = -1;
+    // camera rays of a whole warp often all pass beside the scene (46 % of the 16:9 frame lies outside
+    // the box): one cheap slab test spares the warp the whole wide-leaf loop.  `primary` is warp-uniform.
+    bool skip = false;
+    if (FLAT && primary) skip = __all_sync(__activemask(), misses_scene_box(P, p.o, p.d));
+    if (!skip) tri = closest_hit<FLAT>(sc, p.o, p.d, t);
     uint32_t bits = 0, mtype = SRT_LAMBERTIAN;
     if (tri >= 0) {
         bits = __float_as_uint((reinterpret_cast<const float4*>(sc.tris + tri) + 2)->z);
@@ -485,10 +501,11 @@ __device__ __forceinline__ SceneRef load_scene(const WaveParams& P, unsigned cha
 // list of chunk-local tiles THIS rank owns (tile_id % world == rank).  A wavefront block therefore
 // renders one 2-D tile, and a rank only allocates state for its own pixels.
 __device__ __forceinline__ void slot_pixel(const WaveParams& P, uint32_t slot, uint32_t& ci, uint32_t& cj) {
-    const uint32_t k = slot / P.block_slots, l = slot - k * P.block_slots;
+    // tile_w and tile_w*tile_h are powers of two (checked on the host): shifts, not divisions
+    const uint32_t k = slot >> P.block_slots_log2, l = slot & (P.block_slots - 1u);
     const uint32_t tile = P.tiles[k];
     const uint32_t ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
-    const uint32_t ly = l / P.tile_w, lx = l - ly * P.tile_w;
+    const uint32_t ly = l >> P.tile_w_log2, lx = l & (P.tile_w - 1u);
     ci = tx * P.tile_w + lx;
     cj = ty * P.tile_h + ly;
 }
@@ -637,7 +654,7 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
             }
             if (trace) {
                 rays++;
-                ev = extend<FLAT>(sc, P, p, tri, P.acc, pix);
+                ev = extend<FLAT>(sc, P, p, tri, P.acc, pix, kind == 0);
             }
             if (have) {
                 store_rng(P, slot, rng);
