@@ -778,9 +778,10 @@ LaunchTable make_launch_table() {
     t.init_slots = [](const WaveParams& P, cudaStream_t st) { k_init_slots<<<(P.nslots + 255) / 256, 256, 0, st>>>(P); };
     t.wavefront = [](const WaveParams& P, int mode, int grid, size_t smem, cudaStream_t st) {
         // the queues always live in shared memory, also when the scene does not
-        if (mode == 2) k_wavefront<true, true><<<grid, SRT_WAVE_BLOCK, smem, st>>>(P);
-        else if (mode == 1) k_wavefront<true, false><<<grid, SRT_WAVE_BLOCK, smem, st>>>(P);
-        else k_wavefront<false, false><<<grid, SRT_WAVE_BLOCK, smem, st>>>(P);
+        const int threads = (int)P.block_threads;  // <= SRT_WAVE_BLOCK, the launch bound the registers were allocated for
+        if (mode == 2) k_wavefront<true, true><<<grid, threads, smem, st>>>(P);
+        else if (mode == 1) k_wavefront<true, false><<<grid, threads, smem, st>>>(P);
+        else k_wavefront<false, false><<<grid, threads, smem, st>>>(P);
     };
     t.megakernel = [](const WaveParams& P, int mode, int grid, size_t smem, cudaStream_t st) { SRT_DISPATCH(k_megakernel, mode, grid, smem, st, P); };
     t.resolve = [](const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,

@@ -48,6 +48,7 @@ struct WaveParams {
     // persistent-block wavefront: slots per block and the shared-memory bytes its queues take
     uint32_t block_slots, queue_bytes;
     uint32_t block_slots_log2, tile_w_log2;
+    uint32_t block_threads;  // threads of a wavefront block (128 or 256)
     float scene_lo[3], scene_hi[3];  // bounding box of all triangles (host)
     unsigned long long* ray_counter;
 };

@@ -52,6 +52,7 @@ int RenderManager::set_option(int opt, int value) {
         case SRT_OPT_TAIL_THRESHOLD: cfg_.tail_threshold = value; break;
         case SRT_OPT_TRAVERSAL: cfg_.traversal = value; break;
         case SRT_OPT_BLOCK_SLOTS: cfg_.block_slots = value; break;
+        case SRT_OPT_BLOCK_THREADS: cfg_.block_threads = value; break;
         default: set_error("unknown option"); return SRT_ERR_ARG;
     }
     return SRT_OK;

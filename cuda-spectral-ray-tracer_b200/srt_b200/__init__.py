@@ -44,7 +44,7 @@ class Stats(C.Structure):
                 ("generate_launches", C.c_uint64), ("shade_launches", C.c_uint64), ("tail_launches", C.c_uint64)]
 
 
-OPT_FP_MODE, OPT_PIPELINE, OPT_TILE_W, OPT_TILE_H, OPT_RANK, OPT_WORLD, OPT_REGEN_LOOP, OPT_KERNEL_TIMING, OPT_TAIL_THRESHOLD, OPT_TRAVERSAL, OPT_BLOCK_SLOTS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
+OPT_FP_MODE, OPT_PIPELINE, OPT_TILE_W, OPT_TILE_H, OPT_RANK, OPT_WORLD, OPT_REGEN_LOOP, OPT_KERNEL_TIMING, OPT_TAIL_THRESHOLD, OPT_TRAVERSAL, OPT_BLOCK_SLOTS, OPT_BLOCK_THREADS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
 MAT_LAMBERTIAN, MAT_METALLIC, MAT_DIELECTRIC, MAT_EMISSIVE = 0, 1, 2, 4
 
 # every symbol include/srt.h declares: (name, restype, argtypes)
@@ -334,7 +334,7 @@ class RenderManager:
 
 
 def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=False, pipeline=0, scene=None, tiles=None, regen_loop=None,
-           kernel_timing=False, tail_threshold=None, traversal=None, block_slots=None):
+           kernel_timing=False, tail_threshold=None, traversal=None, block_slots=None, block_threads=None):
     """One-call helper: returns (rgb[3,h,w] float32 0..255, xyz[3,h,w] float32, stats dict)."""
     sc = scene if scene is not None else Scene(scene_id)
     cam = sc.camera(w, h)
@@ -351,6 +351,8 @@ def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=Fals
         rm.set_option(OPT_TAIL_THRESHOLD, tail_threshold)
     if traversal is not None:
         rm.set_option(OPT_TRAVERSAL, traversal)
+    if block_threads is not None:
+        rm.set_option(OPT_BLOCK_THREADS, block_threads)
     if tiles is not None:
         tw, th, rank, world = tiles
         rm.set_option(OPT_TILE_W, tw); rm.set_option(OPT_TILE_H, th); rm.set_option(OPT_RANK, rank); rm.set_option(OPT_WORLD, world)
