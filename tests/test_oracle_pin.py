@@ -150,3 +150,26 @@ def test_live_reference_matches_golden_when_present(golden):
     g = golden["ref_scene1"]
     assert np.array_equal(g["small_rgb"], rgb.astype(np.uint8))
     assert np.array_equal(bits(g["small_xyz"]), bits(xyz))
+
+
+def test_lbvh_spec_fixture():
+    """LBVH artefacts of the CPU specification (oracle/lbvh_oracle.c) for the named scenes and a
+    seeded soup, committed so that a change of the specification cannot slip through unnoticed.
+    PARITY UNPINNED against the reference (it has no LBVH); the GPU build is compared with these bit for bit."""
+    import pathlib
+
+    g = np.load(pathlib.Path(__file__).resolve().parent / "golden" / "lbvh_spec.npz")
+    for name, sc in (("scene0", oracle.Scene(0)), ("scene1", oracle.Scene(1)), ("scene2", oracle.Scene(2)), ("soup1000", oracle.Scene(soup=1000, seed=2984))):
+        f, _ = sc.tris()
+        third = np.float32(1) / np.float32(3)
+        cen = (third * ((f[:, 0:3] + f[:, 3:6]) + f[:, 6:9])).astype(np.float32)
+        r = oracle.lbvh_build(f[:, 13:19], cen)
+        for k, v in r.items():
+            assert np.array_equal(np.ascontiguousarray(v).view(np.uint32), np.ascontiguousarray(g[name + "_" + k]).view(np.uint32)), (name, k)
+        # structural invariants of a Karras tree
+        n = len(r["codes"])
+        assert sorted(r["sorted_idx"].tolist()) == list(range(n))
+        assert np.all(np.diff(r["codes"][r["sorted_idx"]].astype(np.int64)) >= 0)
+        kids = np.concatenate([r["left"], r["right"]])
+        assert sorted(kids.tolist()) == list(range(1, 2 * n - 1))  # every node but the root is a child exactly once
+        assert r["parent"][0] == -1
