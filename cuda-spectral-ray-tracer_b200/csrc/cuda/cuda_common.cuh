@@ -9,6 +9,9 @@ namespace srt {
 extern std::atomic<uint64_t> g_kernel_launches;
 inline void count_launch(uint64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 bool cuda_ok(cudaError_t e, const char* what, const char* file, int line);
+// process-wide cache of device buffers (renderer.cu): a freed block is handed to the next request of a similar size
+bool device_pool_alloc(void** out, size_t bytes);
+void device_pool_free(void* p);
 }  // namespace srt
 
 #define SRT_CUDA(call)                                                   \

@@ -397,10 +397,10 @@ __global__ void __launch_bounds__(256) k_refit_emit(int n, const uint32_t* __res
 }
 
 // ------------------------------------------------------------------------------------------ host
-template <class T> static bool dalloc(T*& p, size_t count) {
-    SRT_CUDA(cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T)));
-    return true;
+template <class T> static bool dalloc(T*& p, size_t count) {  // cached: creating a scene per frame must not pay ~25 cudaMallocs
+    return device_pool_alloc((void**)&p, (count ? count : 1) * sizeof(T));
 }
+static void dfree(void* p) { device_pool_free(p); }
 
 DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::vector<HostMaterial>& mats, double origin_l1_bound) {
     if (cuda_device_count() == 0) { set_error("libsrt: no CUDA device available (the product has no CPU fallback)"); return nullptr; }
@@ -456,10 +456,10 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
 
 void device_scene_destroy(DeviceScene* s) {
     if (!s) return;
-    cudaFree(s->verts); cudaFree(s->tris_in); cudaFree(s->mats); cudaFree(s->leaf_boxes); cudaFree(s->centroids); cudaFree(s->scene_box);
-    cudaFree(s->codes); cudaFree(s->keys[0]); cudaFree(s->keys[1]); cudaFree(s->vals[0]); cudaFree(s->vals[1]); cudaFree(s->hist);
-    cudaFree(s->lookback); cudaFree(s->tile_counter); cudaFree(s->left); cudaFree(s->right); cudaFree(s->parent); cudaFree(s->node_box_lo); cudaFree(s->node_box_hi);
-    cudaFree(s->visit); cudaFree(s->nodes); cudaFree(s->tris); cudaFree(s->flat_units); cudaFree(s->flat_tris);
+    dfree(s->verts); dfree(s->tris_in); dfree(s->mats); dfree(s->leaf_boxes); dfree(s->centroids); dfree(s->scene_box);
+    dfree(s->codes); dfree(s->keys[0]); dfree(s->keys[1]); dfree(s->vals[0]); dfree(s->vals[1]); dfree(s->hist);
+    dfree(s->lookback); dfree(s->tile_counter); dfree(s->left); dfree(s->right); dfree(s->parent); dfree(s->node_box_lo); dfree(s->node_box_hi);
+    dfree(s->visit); dfree(s->nodes); dfree(s->tris); dfree(s->flat_units); dfree(s->flat_tris);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     delete s;
 }

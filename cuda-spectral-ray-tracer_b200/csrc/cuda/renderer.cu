@@ -8,6 +8,7 @@
 #include <cmath>
 #include <vector>
 #include <mutex>
+#include <thread>
 
 namespace srt {
 
@@ -46,7 +47,7 @@ struct PoolBlock { void* ptr; size_t bytes; bool used; };
 std::mutex g_pool_mu;
 std::vector<PoolBlock> g_pool;
 }  // namespace
-static bool pool_alloc(void** out, size_t bytes) {
+bool device_pool_alloc(void** out, size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
     std::lock_guard<std::mutex> lock(g_pool_mu);
     PoolBlock* best = nullptr;
@@ -65,7 +66,7 @@ static bool pool_alloc(void** out, size_t bytes) {
     *out = p;
     return true;
 }
-static void pool_free(void* p) {
+void device_pool_free(void* p) {
     if (!p) return;
     std::lock_guard<std::mutex> lock(g_pool_mu);
     for (PoolBlock& b : g_pool)
@@ -147,8 +148,8 @@ void collect_kernel_times(DeviceRenderer* r) {
 
 void device_renderer_destroy(DeviceRenderer* r) {
     if (!r) return;
-    cudaFree(r->d_cie); cudaFree(r->d_bg); cudaFree(r->d_tiles); cudaFree(r->d_rays); pool_free(r->d_rgb);
-    pool_free(r->P.R0); pool_free(r->P.R1); pool_free(r->P.P0); pool_free(r->P.P1); pool_free(r->P.G0); pool_free(r->P.G1); pool_free(r->P.sidx); pool_free(r->P.acc);
+    device_pool_free(r->d_cie); device_pool_free(r->d_bg); device_pool_free(r->d_tiles); device_pool_free(r->d_rays); device_pool_free(r->d_rgb);
+    device_pool_free(r->P.R0); device_pool_free(r->P.R1); device_pool_free(r->P.P0); device_pool_free(r->P.P1); device_pool_free(r->P.G0); device_pool_free(r->P.G1); device_pool_free(r->P.sidx); device_pool_free(r->P.acc);
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
@@ -200,32 +201,32 @@ static bool renderer_setup(DeviceRenderer* r) {
     P.regen_loop = c.regen_loop < 1 ? 1 : c.regen_loop;
     P.plane = (size_t)P.img_w * P.img_h;
     const size_t ns = std::max<size_t>(P.nslots, 1);
-    SRT_CUDA(cudaMalloc((void**)&r->d_tiles, std::max<size_t>(1, r->h_tiles.size()) * sizeof(uint32_t)));
+    if (!device_pool_alloc((void**)&r->d_tiles, std::max<size_t>(1, r->h_tiles.size()) * sizeof(uint32_t))) return false;
     if (!r->h_tiles.empty()) SRT_CUDA(cudaMemcpy(r->d_tiles, r->h_tiles.data(), r->h_tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     P.tiles = r->d_tiles;
     SRT_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     SRT_CUDA(cudaEventCreate(&r->ev0));
     SRT_CUDA(cudaEventCreate(&r->ev1));
-    if (!pool_alloc((void**)&P.R0, ns * sizeof(float4))) return false;
-    if (!pool_alloc((void**)&P.R1, ns * sizeof(float4))) return false;
-    if (!pool_alloc((void**)&P.P0, ns * sizeof(float4))) return false;
-    if (!pool_alloc((void**)&P.P1, ns * sizeof(float4))) return false;
-    if (!pool_alloc((void**)&P.G0, ns * sizeof(uint4))) return false;
-    if (!pool_alloc((void**)&P.G1, ns * sizeof(uint2))) return false;
-    if (!pool_alloc((void**)&P.sidx, ns * sizeof(uint32_t))) return false;
-    if (!pool_alloc((void**)&P.acc, 3 * P.plane * sizeof(float))) return false;
+    if (!device_pool_alloc((void**)&P.R0, ns * sizeof(float4))) return false;
+    if (!device_pool_alloc((void**)&P.R1, ns * sizeof(float4))) return false;
+    if (!device_pool_alloc((void**)&P.P0, ns * sizeof(float4))) return false;
+    if (!device_pool_alloc((void**)&P.P1, ns * sizeof(float4))) return false;
+    if (!device_pool_alloc((void**)&P.G0, ns * sizeof(uint4))) return false;
+    if (!device_pool_alloc((void**)&P.G1, ns * sizeof(uint2))) return false;
+    if (!device_pool_alloc((void**)&P.sidx, ns * sizeof(uint32_t))) return false;
+    if (!device_pool_alloc((void**)&P.acc, 3 * P.plane * sizeof(float))) return false;
     SRT_CUDA(cudaMemsetAsync(P.acc, 0, 3 * P.plane * sizeof(float), r->stream));
-    SRT_CUDA(cudaMalloc((void**)&r->d_rays, sizeof(unsigned long long)));
+    if (!device_pool_alloc((void**)&r->d_rays, sizeof(unsigned long long))) return false;
     SRT_CUDA(cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), r->stream));
     const size_t chunk_px = (size_t)c.chunk_w * c.chunk_h;
-    if (!pool_alloc((void**)&r->d_rgb, 3 * chunk_px)) return false;
+    if (!device_pool_alloc((void**)&r->d_rgb, 3 * chunk_px)) return false;
     r->h_stage = (unsigned char*)pinned_staging(3 * chunk_px);
     r->chunk_px = chunk_px;
     if (!r->h_stage) return false;
     std::vector<float> cie(3 * SRT_NS);
     for (int k = 0; k < 3; k++) memcpy(cie.data() + k * SRT_NS, cie_table(k), SRT_NS * sizeof(float));
-    SRT_CUDA(cudaMalloc((void**)&r->d_cie, cie.size() * sizeof(float)));
-    SRT_CUDA(cudaMalloc((void**)&r->d_bg, SRT_NS * sizeof(float)));
+    if (!device_pool_alloc((void**)&r->d_cie, cie.size() * sizeof(float))) return false;
+    if (!device_pool_alloc((void**)&r->d_bg, SRT_NS * sizeof(float))) return false;
     SRT_CUDA(cudaMemcpy(r->d_cie, cie.data(), cie.size() * sizeof(float), cudaMemcpyHostToDevice));
     SRT_CUDA(cudaMemcpy(r->d_bg, c.bg_spectrum, SRT_NS * sizeof(float), cudaMemcpyHostToDevice));
     P.cie = r->d_cie;
@@ -325,13 +326,22 @@ bool device_renderer_resolve(DeviceRenderer* r, unsigned off_x, unsigned off_y, 
     SRT_CUDA(cudaMemcpyAsync(r->h_stage, r->d_rgb, 3 * n, cudaMemcpyDeviceToHost, r->stream));
     SRT_CUDA(cudaStreamSynchronize(r->stream));
     float* dst[3] = {fr, fg, fb};
-    for (int c = 0; c < 3; c++) {
-        if (!dst[c]) continue;
+    const unsigned char* stage = r->h_stage;
+    auto widen = [&](int c) {  // frame_buffer holds 0..255 as float (frame_buffer.cuh:6-44)
+        if (!dst[c]) return;
         for (unsigned y = 0; y < h; y++) {
-            const unsigned char* src = r->h_stage + c * n + (size_t)y * w;
+            const unsigned char* src = stage + c * n + (size_t)y * w;
             float* o = dst[c] + (size_t)(off_y + y) * img_w + off_x;
-            for (unsigned x = 0; x < w; x++) o[x] = (float)src[x];  // frame_buffer holds 0..255 as float (frame_buffer.cuh:6-44)
+            for (unsigned x = 0; x < w; x++) o[x] = (float)src[x];
         }
+    };
+    if (n >= (1u << 18)) {  // big chunks: one host thread per colour plane
+        std::thread tg(widen, 1), tb(widen, 2);
+        widen(0);
+        tg.join();
+        tb.join();
+    } else {
+        for (int c = 0; c < 3; c++) widen(c);
     }
     return true;
 }
