@@ -182,6 +182,9 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU reference legs must use every host core (the OpenMP
+    # runtime reads the variable when the oracle library is loaded, which happens later)
+    os.environ.pop("OMP_NUM_THREADS", None)
     wl_name = a.workload
     wl = WORKLOADS[wl_name]
     scene_id, w, h, spp, depth = wl
