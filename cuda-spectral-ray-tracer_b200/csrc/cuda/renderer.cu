@@ -396,18 +396,21 @@ bool device_scene_trace(const DeviceScene* s, uint32_t n, const float* o, const 
     SRT_CUDA(cudaMalloc((void**)&d_tri, (size_t)n * sizeof(int32_t)));
     SRT_CUDA(cudaMemcpy(d_o, o, 3ull * n * sizeof(float), cudaMemcpyHostToDevice));
     SRT_CUDA(cudaMemcpy(d_d, d, 3ull * n * sizeof(float), cudaMemcpyHostToDevice));
-    const int grid = (int)std::min<uint64_t>((n + SRT_BLOCK - 1) / SRT_BLOCK, (uint64_t)sm_count() * 8);
+    // persistent warps that refill themselves from a ray counter: one resident wave is the whole grid
+    const int grid = (int)std::min<uint64_t>((n + SRT_BLOCK - 1) / SRT_BLOCK, (uint64_t)sm_count() * 6);
+    uint32_t* d_next = nullptr;
+    SRT_CUDA(cudaMalloc((void**)&d_next, sizeof(uint32_t)));
     const LaunchTable& T = table(1);
-    T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, nullptr, grid, nullptr);  // warm-up
+    T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, nullptr, d_next, grid, nullptr);  // warm-up
     SRT_CUDA(cudaEventRecord(e0));
-    T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, nullptr, grid, nullptr);
+    T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, nullptr, d_next, grid, nullptr);
     SRT_CUDA(cudaEventRecord(e1));
     count_launch(2);
     if (visits) {  // untimed third pass that counts node visits and leaf tests (algorithmic bytes of the walk)
         unsigned long long* d_cnt = nullptr;
         SRT_CUDA(cudaMalloc((void**)&d_cnt, 2 * sizeof(unsigned long long)));
         SRT_CUDA(cudaMemset(d_cnt, 0, 2 * sizeof(unsigned long long)));
-        T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, d_cnt, grid, nullptr);
+        T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, d_cnt, d_next, grid, nullptr);
         count_launch();
         unsigned long long h[2] = {0, 0};
         SRT_CUDA(cudaMemcpy(h, d_cnt, sizeof h, cudaMemcpyDeviceToHost));
@@ -421,7 +424,7 @@ bool device_scene_trace(const DeviceScene* s, uint32_t n, const float* o, const 
     if (ms) *ms = el;
     SRT_CUDA(cudaMemcpy(t, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
     SRT_CUDA(cudaMemcpy(tri, d_tri, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_tri);
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_tri); cudaFree(d_next);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return true;
 }

@@ -208,6 +208,54 @@ __device__ __forceinline__ int closest_hit_flat(const SceneRef& sc, V3 o, V3 d, 
     return best;
 }
 
+// One step of the LBVH walk: fetch `node` (both child boxes live in the parent: 4 x 16-B loads), test the
+// two boxes, test leaf children on the spot, continue with the nearer internal child and stack the farther.
+// Returns false when the walk is over.
+__device__ __forceinline__ bool lbvh_step(const SceneRef& sc, V3 o, V3 d, V3 inv, int& node, int& sp, int* __restrict__ stack, float& closest, int& best,
+                                          uint32_t& best_prio, uint32_t* visits) {
+    const float ix = inv.x, iy = inv.y, iz = inv.z;
+    const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
+    if (visits) visits[0]++;
+    const float4 b0 = np[0], b1 = np[1], b2 = np[2];
+    const int4 ch = *reinterpret_cast<const int4*>(np + 3);
+    // slabs; a NaN direction makes every comparison below false -> both children are visited,
+    // every triangle test then fails (NaN t), i.e. the path misses exactly like the reference (Q1)
+    float t0x = (b0.x - o.x) * ix, t1x = (b0.y - o.x) * ix;
+    float t0y = (b0.z - o.y) * iy, t1y = (b0.w - o.y) * iy;
+    float t0z = (b2.x - o.z) * iz, t1z = (b2.y - o.z) * iz;
+    float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+    float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    t0x = (b1.x - o.x) * ix; t1x = (b1.y - o.x) * ix;
+    t0y = (b1.z - o.y) * iy; t1y = (b1.w - o.y) * iy;
+    t0z = (b2.z - o.z) * iz; t1z = (b2.w - o.z) * iz;
+    float n1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+    float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    // conservative: one-sided slack on both ends so rounding can only add candidates
+    bool h0 = !(n0 * 0.9999995f > fminf(f0 * 1.0000005f, closest));
+    bool h1 = !(n1 * 0.9999995f > fminf(f1 * 1.0000005f, closest));
+    int c0 = ch.x, c1 = ch.y;
+    if (h0 && h1 && n1 < n0) {  // visit the nearer child first
+        const int tc = c0; c0 = c1; c1 = tc;
+    } else if (!h0) {
+        c0 = c1; h0 = h1; h1 = false;
+    }
+    // c0 = first child to process (if h0), c1 = second (if h1)
+    int next = -1;
+    if (h0) {
+        if (c0 < 0) { if (visits) visits[1]++; consider_leaf(sc.tris, ~c0, o, d, closest, best, best_prio); }
+        else next = c0;
+    }
+    if (h1) {
+        if (c1 < 0) { if (visits) visits[1]++; consider_leaf(sc.tris, ~c1, o, d, closest, best, best_prio); }
+        else if (next < 0) next = c1;
+        else stack[sp++] = c1;
+    }
+    if (next >= 0) { node = next; return true; }
+    if (sp == 0) return false;
+    node = stack[--sp];
+    return true;
+}
+
 // closest hit over the LBVH: both child boxes live in the parent node (4 x 16-B loads),
 // near child first, far child pushed.  Returns leaf-order triangle index or -1.
 template <bool FLAT>
@@ -225,51 +273,11 @@ __device__ __forceinline__ int closest_hit(const SceneRef& sc, V3 o, V3 d, float
         if (tri_test(sc.tris, o, d, closest, t)) { t_hit = t; return 0; }
         return -1;
     }
-    const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+    const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     int stack[64];
     int sp = 0;
     int node = 0;
-    while (true) {
-        const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
-        if (visits) visits[0]++;
-        const float4 b0 = np[0], b1 = np[1], b2 = np[2];
-        const int4 ch = *reinterpret_cast<const int4*>(np + 3);
-        // slabs; a NaN direction makes every comparison below false -> both children are visited,
-        // every triangle test then fails (NaN t), i.e. the path misses exactly like the reference (Q1)
-        float t0x = (b0.x - o.x) * ix, t1x = (b0.y - o.x) * ix;
-        float t0y = (b0.z - o.y) * iy, t1y = (b0.w - o.y) * iy;
-        float t0z = (b2.x - o.z) * iz, t1z = (b2.y - o.z) * iz;
-        float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-        float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-        t0x = (b1.x - o.x) * ix; t1x = (b1.y - o.x) * ix;
-        t0y = (b1.z - o.y) * iy; t1y = (b1.w - o.y) * iy;
-        t0z = (b2.z - o.z) * iz; t1z = (b2.w - o.z) * iz;
-        float n1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-        float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-        // conservative: one-sided slack on both ends so rounding can only add candidates
-        bool h0 = !(n0 * 0.9999995f > fminf(f0 * 1.0000005f, closest));
-        bool h1 = !(n1 * 0.9999995f > fminf(f1 * 1.0000005f, closest));
-        int c0 = ch.x, c1 = ch.y;
-        if (h0 && h1 && n1 < n0) {  // visit the nearer child first
-            const int tc = c0; c0 = c1; c1 = tc;
-        } else if (!h0) {
-            c0 = c1; h0 = h1; h1 = false;
-        }
-        // c0 = first child to process (if h0), c1 = second (if h1)
-        int next = -1;
-        if (h0) {
-            if (c0 < 0) { if (visits) visits[1]++; consider_leaf(sc.tris, ~c0, o, d, closest, best, best_prio); }
-            else next = c0;
-        }
-        if (h1) {
-            if (c1 < 0) { if (visits) visits[1]++; consider_leaf(sc.tris, ~c1, o, d, closest, best, best_prio); }
-            else if (next < 0) next = c1;
-            else stack[sp++] = c1;
-        }
-        if (next >= 0) { node = next; continue; }
-        if (sp == 0) break;
-        node = stack[--sp];
-    }
+    while (lbvh_step(sc, o, d, inv, node, sp, stack, closest, best, best_prio, visits)) {}
     t_hit = closest;
     return best;
 }
@@ -726,22 +734,68 @@ __global__ void k_resolve(const float* __restrict__ acc, size_t plane, uint32_t 
     }
 }
 
-// standalone closest-hit queries (BASELINE.json configs[3]); always global-memory scene
+// Standalone closest-hit queries (BASELINE.json configs[3]); the scene stays in global memory.
+// Persistent warps with ray refill: rays of one warp end after very different numbers of node visits
+// (ncu on 1M incoherent rays: 7.8 of 32 lanes active with one ray per thread), so lanes that are done
+// fetch the next unprocessed rays from a global counter instead of idling until the warp's longest ray
+// ends.  Every active lane processes exactly one BVH node per loop iteration.
+#define SRT_NO_RAY 0xFFFFFFFFu
 template <bool COUNT>
 __global__ void __launch_bounds__(SRT_BLOCK) k_trace_rays(WaveParams P, uint32_t n, const float* __restrict__ o, const float* __restrict__ d,
                                                           const uint32_t* __restrict__ sorted_idx, float* __restrict__ t_out,
-                                                          int32_t* __restrict__ tri_out, unsigned long long* counters) {
+                                                          int32_t* __restrict__ tri_out, unsigned long long* counters, uint32_t* next_ray) {
     SceneRef sc;
     sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float t = 0.f;
-        uint32_t visits[2] = {0, 0};
-        const int tri = closest_hit<false>(sc, mk(o[3ull * i], o[3ull * i + 1], o[3ull * i + 2]), mk(d[3ull * i], d[3ull * i + 1], d[3ull * i + 2]), t,
-                                           COUNT ? visits : nullptr);
-        t_out[i] = tri >= 0 ? t : -1.0f;
-        tri_out[i] = tri >= 0 ? (int32_t)sorted_idx[tri] : -1;
-        if (COUNT) { atomicAdd(counters, (unsigned long long)visits[0]); atomicAdd(counters + 1, (unsigned long long)visits[1]); }
+    const uint32_t lane = threadIdx.x & 31;
+    int stack[64];
+    int sp = 0, node = 0, best = -1;
+    uint32_t ray = SRT_NO_RAY, best_prio = 0;
+    float closest = FLT_MAX;
+    V3 ro = mk(0, 0, 0), rd = mk(0, 0, 0), inv = mk(0, 0, 0);
+    uint32_t visits[2] = {0, 0};
+    bool exhausted = false;
+    while (true) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, ray == SRT_NO_RAY);
+        if (!exhausted && (__popc(idle) >= SRT_REFILL_LANES || idle == 0xffffffffu)) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(next_ray, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + (uint32_t)__popc(idle) >= n) exhausted = true;
+            const uint32_t mine = base + __popc(idle & ((1u << lane) - 1));
+            if (ray == SRT_NO_RAY && base < n && mine < n) {
+                ray = mine;
+                ro = mk(o[3ull * mine], o[3ull * mine + 1], o[3ull * mine + 2]);
+                rd = mk(d[3ull * mine], d[3ull * mine + 1], d[3ull * mine + 2]);
+                inv = mk(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+                closest = FLT_MAX; best = -1; best_prio = 0; sp = 0; node = 0;
+                // same early answers as closest_hit: empty scene, NaN ray (Q1), single triangle
+                bool done = sc.n_tris <= 0 || !(rd.x == rd.x && rd.y == rd.y && rd.z == rd.z && ro.x == ro.x && ro.y == ro.y && ro.z == ro.z);
+                if (!done && sc.n_tris == 1) {
+                    float t;
+                    if (tri_test(sc.tris, ro, rd, closest, t)) { closest = t; best = 0; }
+                    done = true;
+                }
+                if (done) {
+                    t_out[mine] = best >= 0 ? closest : -1.0f;
+                    tri_out[mine] = best >= 0 ? (int32_t)sorted_idx[best] : -1;
+                    ray = SRT_NO_RAY;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, ray == SRT_NO_RAY)) {
+            if (exhausted) break;
+            continue;
+        }
+        if (ray != SRT_NO_RAY) {
+            if (!lbvh_step(sc, ro, rd, inv, node, sp, stack, closest, best, best_prio, COUNT ? visits : nullptr)) {
+                t_out[ray] = best >= 0 ? closest : -1.0f;
+                tri_out[ray] = best >= 0 ? (int32_t)sorted_idx[best] : -1;
+                ray = SRT_NO_RAY;
+            }
+        }
     }
+    if (COUNT) { atomicAdd(counters, (unsigned long long)visits[0]); atomicAdd(counters + 1, (unsigned long long)visits[1]); }
 }
 
 // ------------------------------------------------------------------------------ launchers
@@ -787,9 +841,10 @@ LaunchTable make_launch_table() {
     t.resolve = [](const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,
                    cudaStream_t st) { k_resolve<<<(w * h + 255) / 256, 256, 0, st>>>(acc, plane, img_w, ox, oy, w, h, spp, rgb); };
     t.trace_rays = [](const WaveParams& P, uint32_t n, const float* o, const float* d, const uint32_t* sorted_idx, float* t_out, int32_t* tri_out,
-                      unsigned long long* counters, int grid, cudaStream_t st) {
-        if (counters) k_trace_rays<true><<<grid, SRT_BLOCK, 0, st>>>(P, n, o, d, sorted_idx, t_out, tri_out, counters);
-        else k_trace_rays<false><<<grid, SRT_BLOCK, 0, st>>>(P, n, o, d, sorted_idx, t_out, tri_out, nullptr);
+                      unsigned long long* counters, uint32_t* next_ray, int grid, cudaStream_t st) {
+        cudaMemsetAsync(next_ray, 0, sizeof(uint32_t), st);
+        if (counters) k_trace_rays<true><<<grid, SRT_BLOCK, 0, st>>>(P, n, o, d, sorted_idx, t_out, tri_out, counters, next_ray);
+        else k_trace_rays<false><<<grid, SRT_BLOCK, 0, st>>>(P, n, o, d, sorted_idx, t_out, tri_out, nullptr, next_ray);
     };
     return t;
 }

@@ -6,6 +6,7 @@
 #include "../common/srt_types.h"
 
 #define SRT_BLOCK 256
+#define SRT_REFILL_LANES 8  // k_trace_rays fetches new rays once this many lanes of a warp are idle
 #ifndef SRT_WAVE_BLOCK
 #define SRT_WAVE_BLOCK 256      // threads of a persistent wavefront block
 #define SRT_WAVE_MIN_BLOCKS 4   // resident blocks per SM the register allocation must allow
@@ -62,7 +63,7 @@ struct LaunchTable {
     void (*resolve)(const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,
                     cudaStream_t);
     void (*trace_rays)(const WaveParams&, uint32_t n, const float* o, const float* d, const uint32_t* sorted_idx, float* t_out, int32_t* tri_out,
-                       unsigned long long* counters, int grid, cudaStream_t);
+                       unsigned long long* counters, uint32_t* next_ray, int grid, cudaStream_t);
 };
 
 namespace fastfp { LaunchTable make_launch_table(); }
