@@ -170,7 +170,8 @@ __device__ __forceinline__ void consider_hit(const SrtTri* __restrict__ tris, in
 //            reference arithmetic (tri_test), nearest wins, ties by reference test order.
 // Phase 1 only ever rejects pairs the exact test rejects too, so the result equals testing every
 // triangle exactly -- which is what "closest hit" means in the reference (bvh.cu:98-166).
-__device__ __forceinline__ void flat_unit_test(const float4* __restrict__ up, int u, V3 o, V3 d, uint32_t bit_i, uint32_t& mask) {
+template <uint32_t BIT>
+__device__ __forceinline__ void flat_unit_test(const float4* __restrict__ up, int u, V3 o, V3 d, uint32_t& mask) {
     const float4 pl = up[4 * u], A = up[4 * u + 1], B = up[4 * u + 2], C = up[4 * u + 3];
     const float denom = __fmaf_rn(pl.z, d.z, __fmaf_rn(pl.y, d.y, pl.x * d.x));
     const float num = pl.w - __fmaf_rn(pl.z, o.z, __fmaf_rn(pl.y, o.y, pl.x * o.x));
@@ -179,22 +180,52 @@ __device__ __forceinline__ void flat_unit_test(const float4* __restrict__ up, in
     const float al = __fmaf_rn(A.z, pz, __fmaf_rn(A.y, py, __fmaf_rn(A.x, px, A.w)));
     const float be = __fmaf_rn(B.z, pz, __fmaf_rn(B.y, py, __fmaf_rn(B.x, px, B.w)));
     const float s = al + be;
-    // One "violation" value per half: positive means certainly outside.  fminf/fmaxf drop NaN operands
-    // and NaN > 0 is false, so NaN / inf can only ever keep a candidate (the exact test decides).
-    const float vi = fmaxf(-fminf(al, be), s - C.x);          // first half:  alpha',beta' >= 0, alpha'+beta' <= c1
-    const float vj = fmaxf(fmaxf(al, be) - C.y, C.z - s);     // second half: alpha',beta' <= c2, alpha'+beta' >= c3
-    const bool behind = (t < 0.0f) & (fabsf(num) > C.w);
-    if (!(behind | (vi > 0.0f))) mask |= bit_i;
-    if (!(behind | (vj > 0.0f))) mask |= bit_i << 1;
+    // "Certainly outside" per half as one chain of compare-and-combine predicate instructions:
+    //   behind = t < 0 & |num| > tol
+    //   out_i  = behind | alpha' < 0 | beta' < 0 | alpha'+beta' > c1       (first half)
+    //   out_j  = behind | alpha' > c2 | beta' > c2 | alpha'+beta' < c3     (second half)
+    // Every comparison is false for a NaN operand, so NaN / inf can only ever keep a candidate (the
+    // exact test decides).  Written in PTX because the compiler otherwise builds the two mask bits
+    // through chains of selects (twice the instructions).
+    asm("{\n\t"
+        ".reg .pred pb, pi, pj;\n\t"
+        ".reg .f32 an;\n\t"
+        "abs.f32 an, %2;\n\t"
+        "setp.lt.f32 pb, %1, 0f00000000;\n\t"
+        "setp.gt.and.f32 pb, an, %3, pb;\n\t"
+        "setp.lt.or.f32 pi, %4, 0f00000000, pb;\n\t"
+        "setp.gt.or.f32 pj, %4, %8, pb;\n\t"
+        "setp.lt.or.f32 pi, %5, 0f00000000, pi;\n\t"
+        "setp.gt.or.f32 pj, %5, %8, pj;\n\t"
+        "setp.gt.or.f32 pi, %6, %7, pi;\n\t"
+        "setp.lt.or.f32 pj, %6, %9, pj;\n\t"
+        "@!pi or.b32 %0, %0, %10;\n\t"
+        "@!pj or.b32 %0, %0, %11;\n\t"
+        "}"
+        : "+r"(mask)
+        : "f"(t), "f"(num), "f"(C.w), "f"(al), "f"(be), "f"(s), "f"(C.x), "f"(C.y), "f"(C.z), "n"(BIT), "n"(BIT << 1));
 }
 __device__ __forceinline__ int closest_hit_flat(const SceneRef& sc, V3 o, V3 d, float& t_hit) {
     const float4* __restrict__ up = reinterpret_cast<const float4*>(sc.units);
-    uint32_t m0 = 0, m1 = 0;
-    const int n = sc.n_units, n0 = n < 16 ? n : 16;
-#pragma unroll 4
-    for (int u = 0; u < n0; u++) flat_unit_test(up, u, o, d, 1u << (2 * u), m0);
-#pragma unroll 4
-    for (int u = 16; u < n; u++) flat_unit_test(up, u, o, d, 1u << (2 * (u - 16)), m1);
+    // groups of four units: inside a group the candidate bits are compile-time constants (predicated ORs
+    // of immediates), one shift per group places them in the 64-bit mask; the <= 3 left-over units follow
+    unsigned long long m = 0;
+    const int n = sc.n_units, groups = n >> 2;
+    for (int g = 0; g < groups; g++) {
+        uint32_t loc = 0;
+        flat_unit_test<1u>(up, 4 * g, o, d, loc);
+        flat_unit_test<4u>(up, 4 * g + 1, o, d, loc);
+        flat_unit_test<16u>(up, 4 * g + 2, o, d, loc);
+        flat_unit_test<64u>(up, 4 * g + 3, o, d, loc);
+        m |= (unsigned long long)loc << (8 * g);
+    }
+#pragma unroll 1
+    for (int u = 4 * groups; u < n; u++) {
+        uint32_t loc = 0;
+        flat_unit_test<1u>(up, u, o, d, loc);
+        m |= (unsigned long long)loc << (2 * u);
+    }
+    uint32_t m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
     float closest = FLT_MAX;
     int best = -1;
     uint32_t best_prio = 0;
