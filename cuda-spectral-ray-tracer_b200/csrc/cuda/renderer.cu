@@ -94,7 +94,7 @@ struct DeviceRenderer {
     RenderConfig cfg;
     WaveParams P{};
     size_t smem = 0;
-    int grid = 0, mode = 0;  // 0 global LBVH, 1 shared-memory LBVH, 2 shared-memory wide leaf
+    int grid = 0, wave_grid = 0, mode = 0;  // 0 global LBVH, 1 shared-memory LBVH, 2 shared-memory wide leaf
     // owned device memory
     float* d_cie = nullptr;
     float* d_bg = nullptr;
@@ -149,7 +149,7 @@ void collect_kernel_times(DeviceRenderer* r) {
 void device_renderer_destroy(DeviceRenderer* r) {
     if (!r) return;
     device_pool_free(r->d_cie); device_pool_free(r->d_bg); device_pool_free(r->d_tiles); device_pool_free(r->d_rays); device_pool_free(r->d_rgb);
-    device_pool_free(r->P.R0); device_pool_free(r->P.R1); device_pool_free(r->P.P0); device_pool_free(r->P.P1); device_pool_free(r->P.G0); device_pool_free(r->P.G1); device_pool_free(r->P.sidx); device_pool_free(r->P.acc);
+    device_pool_free(r->P.R0); device_pool_free(r->P.R1); device_pool_free(r->P.P0); device_pool_free(r->P.P1); device_pool_free(r->P.L0); device_pool_free(r->P.L1); device_pool_free(r->P.G0); device_pool_free(r->P.G1); device_pool_free(r->P.next_slot); device_pool_free(r->P.acc);
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
@@ -175,16 +175,14 @@ static bool renderer_setup(DeviceRenderer* r) {
     memcpy(P.cam.center, &c.cam.camera_center, 12); memcpy(P.cam.disk_u, &c.cam.defocus_disk_u, 12); memcpy(P.cam.disk_v, &c.cam.defocus_disk_v, 12);
     P.img_w = c.cam.width; P.img_h = c.cam.height;
     P.tile_w = (uint32_t)std::max(1, c.tile_w); P.tile_h = (uint32_t)std::max(1, c.tile_h);
-    P.block_slots = P.tile_w * P.tile_h;  // one wavefront block renders one tile
-    if (P.block_slots > 65536 || P.block_slots < 32 || (P.tile_w & (P.tile_w - 1)) || (P.tile_h & (P.tile_h - 1))) {
+    const uint32_t tile_slots = P.tile_w * P.tile_h;
+    if (tile_slots > 65536 || tile_slots < 32 || (P.tile_w & (P.tile_w - 1)) || (P.tile_h & (P.tile_h - 1))) {
         set_error("tile width and height must be powers of two with an area in [32, 65536]");
         return false;
     }
-    for (P.block_slots_log2 = 0; (1u << P.block_slots_log2) < P.block_slots; P.block_slots_log2++) {}
+    for (P.tile_slots_log2 = 0; (1u << P.tile_slots_log2) < tile_slots; P.tile_slots_log2++) {}
     for (P.tile_w_log2 = 0; (1u << P.tile_w_log2) < P.tile_w; P.tile_w_log2++) {}
     device_scene_bounds(r->scene, P.scene_lo, P.scene_hi);
-    // 256 threads per tile even for 16x16 tiles: a tile's bounce chain is serial, so fewer threads per tile only
-    // stretch it (measured: 128-thread blocks are 1.5x slower on a rank that owns 1/8 of the tiles)
     P.block_threads = c.block_threads > 0 ? (uint32_t)std::min(256, std::max(32, c.block_threads & ~31)) : 256u;
     P.tiles_x = (c.chunk_w + P.tile_w - 1) / P.tile_w;
     const uint32_t tiles_y = (c.chunk_h + P.tile_h - 1) / P.tile_h;
@@ -194,7 +192,7 @@ static bool renderer_setup(DeviceRenderer* r) {
     for (uint32_t t = 0; t < P.tiles_x * tiles_y; t++)
         if (((t % P.tiles_x) + 5u * (t / P.tiles_x)) % P.world == P.rank) r->h_tiles.push_back(t);
     P.n_tiles = (uint32_t)r->h_tiles.size();
-    P.nslots = P.n_tiles * P.block_slots;
+    P.nslots = P.n_tiles * tile_slots;
     P.ref_grid_x = c.chunk_w / 28u + 1u;  // render_manager.cu:93-96
     P.spp = c.spp & 0xFFFFu;              // short_uint kernel parameters (rendering.cu:154, Q14)
     P.bounce_limit = c.bounce_limit & 0xFFFFu;
@@ -207,13 +205,9 @@ static bool renderer_setup(DeviceRenderer* r) {
     SRT_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     SRT_CUDA(cudaEventCreate(&r->ev0));
     SRT_CUDA(cudaEventCreate(&r->ev1));
-    if (!device_pool_alloc((void**)&P.R0, ns * sizeof(float4))) return false;
-    if (!device_pool_alloc((void**)&P.R1, ns * sizeof(float4))) return false;
-    if (!device_pool_alloc((void**)&P.P0, ns * sizeof(float4))) return false;
-    if (!device_pool_alloc((void**)&P.P1, ns * sizeof(float4))) return false;
     if (!device_pool_alloc((void**)&P.G0, ns * sizeof(uint4))) return false;
     if (!device_pool_alloc((void**)&P.G1, ns * sizeof(uint2))) return false;
-    if (!device_pool_alloc((void**)&P.sidx, ns * sizeof(uint32_t))) return false;
+    if (!device_pool_alloc((void**)&P.next_slot, sizeof(uint32_t))) return false;
     if (!device_pool_alloc((void**)&P.acc, 3 * P.plane * sizeof(float))) return false;
     SRT_CUDA(cudaMemsetAsync(P.acc, 0, 3 * P.plane * sizeof(float), r->stream));
     if (!device_pool_alloc((void**)&r->d_rays, sizeof(unsigned long long))) return false;
@@ -243,12 +237,33 @@ static bool renderer_setup(DeviceRenderer* r) {
     size_t need = T.smem_bytes(P, r->mode);
     if (need > kSmemSceneLimit || c.traversal == 3) { r->mode = 0; need = 0; }
     r->smem = need;
-    P.queue_bytes = (2u * 4u * P.block_slots * (uint32_t)sizeof(uint16_t) + 15u) & ~15u;
-    SRT_CUDA(T.configure(r->smem + P.queue_bytes));
-    // persistent grid: a multiple of the SM count, enough blocks to fill every SM's thread slots
+    // megakernel grid: a multiple of the SM count, enough blocks to fill every SM's thread slots
     const int sms = sm_count();
     const int per_sm = r->smem ? std::max(1, std::min(8, (int)(200 * 1024 / (r->smem + 1024)))) : 8;
     r->grid = sms * per_sm;
+    // wavefront grid: one resident wave of persistent blocks, each with up to 1024 paths in flight
+    // (4 per thread); a rank with few pixels takes fewer paths per block so that every SM still gets work
+    uint32_t resident = 0;
+    for (P.block_slots = 1024;; P.block_slots >>= 1) {
+        P.queue_bytes = (22u * P.block_slots + 15u) & ~15u;  // queues [2][4][S] u16 | pixel slot [S] u32 | samples started [S] u16
+        SRT_CUDA(T.configure(r->smem + P.queue_bytes));
+        resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.block_threads, r->smem + P.queue_bytes));
+        if (P.block_slots <= P.block_threads || (uint64_t)resident * P.block_slots <= (uint64_t)P.nslots) break;
+    }
+    if (c.block_slots >= 32 && c.block_slots <= 4096 && !(c.block_slots & (c.block_slots - 1))) {
+        P.block_slots = (uint32_t)c.block_slots;
+        P.queue_bytes = (22u * P.block_slots + 15u) & ~15u;
+        SRT_CUDA(T.configure(r->smem + P.queue_bytes));
+        resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.block_threads, r->smem + P.queue_bytes));
+    }
+    r->wave_grid = (int)std::min<uint64_t>(resident, ((uint64_t)P.nslots + P.block_slots - 1) / P.block_slots);
+    const size_t nrec = std::max<size_t>(1, (size_t)std::max(1, r->wave_grid) * P.block_slots);
+    if (!device_pool_alloc((void**)&P.R0, nrec * sizeof(float4))) return false;
+    if (!device_pool_alloc((void**)&P.R1, nrec * sizeof(float4))) return false;
+    if (!device_pool_alloc((void**)&P.P0, nrec * sizeof(float4))) return false;
+    if (!device_pool_alloc((void**)&P.P1, nrec * sizeof(float4))) return false;
+    if (!device_pool_alloc((void**)&P.L0, nrec * sizeof(uint4))) return false;
+    if (!device_pool_alloc((void**)&P.L1, nrec * sizeof(uint2))) return false;
     SRT_CUDA(cudaStreamSynchronize(r->stream));
     return true;
 }
@@ -280,8 +295,8 @@ bool device_renderer_render_chunk(DeviceRenderer* r, unsigned off_x, unsigned of
         T.megakernel(P, r->mode, r->grid, r->smem, st);
     } else {  // one persistent-block launch renders the whole chunk
         KernelTimer kt(r, 1);
-        const int blocks = (int)P.n_tiles;
-        T.wavefront(P, r->mode, blocks, r->smem + P.queue_bytes, st);
+        SRT_CUDA(cudaMemsetAsync(P.next_slot, 0, sizeof(uint32_t), st));
+        T.wavefront(P, r->mode, r->wave_grid, r->smem + P.queue_bytes, st);
         r->iterations++;
     }
     r->launches++; count_launch();

@@ -536,12 +536,12 @@ __device__ __forceinline__ SceneRef load_scene(const WaveParams& P, unsigned cha
 }
 
 // ------------------------------------------------------------------------------ slot <-> pixel
-// Slots are grouped by image tile: slot = k * (tile_w*tile_h) + pixel-in-tile, where k indexes the
-// list of chunk-local tiles THIS rank owns (tile_id % world == rank).  A wavefront block therefore
-// renders one 2-D tile, and a rank only allocates state for its own pixels.
+// Pixel slots are grouped by image tile: slot = k * (tile_w*tile_h) + pixel-in-tile, where k indexes
+// the list of chunk-local tiles THIS rank owns.  Consecutive slots are one row of a tile, so a warp
+// that fetches 32 fresh slots renders a compact patch, and a rank only numbers its own pixels.
 __device__ __forceinline__ void slot_pixel(const WaveParams& P, uint32_t slot, uint32_t& ci, uint32_t& cj) {
     // tile_w and tile_w*tile_h are powers of two (checked on the host): shifts, not divisions
-    const uint32_t k = slot >> P.block_slots_log2, l = slot & (P.block_slots - 1u);
+    const uint32_t k = slot >> P.tile_slots_log2, l = slot & ((1u << P.tile_slots_log2) - 1u);
     const uint32_t tile = P.tiles[k];
     const uint32_t ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
     const uint32_t ly = l >> P.tile_w_log2, lx = l & (P.tile_w - 1u);
@@ -583,13 +583,13 @@ __device__ __forceinline__ void load_hit_state(const WaveParams& P, uint32_t slo
     p.hero = p1.w;
     tri = __float_as_int(r0.w);
 }
-__device__ __forceinline__ void store_rng(const WaveParams& P, uint32_t slot, const Rng& r) {
-    P.G0[slot] = make_uint4(r.d, r.v0, r.v1, r.v2);
-    P.G1[slot] = make_uint2(r.v3, r.v4);
+__device__ __forceinline__ void store_rng(uint4* __restrict__ g0, uint2* __restrict__ g1, uint32_t slot, const Rng& r) {
+    g0[slot] = make_uint4(r.d, r.v0, r.v1, r.v2);
+    g1[slot] = make_uint2(r.v3, r.v4);
 }
-__device__ __forceinline__ Rng load_rng(const WaveParams& P, uint32_t slot) {
-    const uint4 a = P.G0[slot];
-    const uint2 b = P.G1[slot];
+__device__ __forceinline__ Rng load_rng(const uint4* __restrict__ g0, const uint2* __restrict__ g1, uint32_t slot) {
+    const uint4 a = g0[slot];
+    const uint2 b = g1[slot];
     Rng r;
     r.d = a.x; r.v0 = a.y; r.v1 = a.z; r.v2 = a.w; r.v3 = b.x; r.v4 = b.y;
     return r;
@@ -606,37 +606,41 @@ __global__ void k_init_slots(WaveParams P) {  // init_random_states (rendering.c
     if (slot >= P.nslots) return;
     uint32_t ci, cj;
     slot_pixel(P, slot, ci, cj);
-    store_rng(P, slot, rng_seed(1984u + ref_thread_index(P, ci, cj)));
+    store_rng(P.G0, P.G1, slot, rng_seed(1984u + ref_thread_index(P, ci, cj)));
 }
 
-// Persistent-block wavefront.  A block owns P.block_slots consecutive pixel slots for the whole
-// render of a chunk and runs its own bounce loop: four queues of local slot ids in shared memory
-// (regenerate | lambertian | metallic | dielectric), double buffered.  Every pass lays the four
-// queues out back to back, each padded to a warp multiple, so a warp only ever executes one kind
-// of work; warps pull 32-item chunks from a shared counter (cheap items do not leave a warp idle);
-// results are pushed into the other buffer with warp-aggregated shared-memory atomics.  No global
-// atomics, no host round trips, one launch per chunk; blocks are scheduled dynamically, which
-// balances the uneven pixel costs over the SMs.  The ray trace (extend) has ONE call site so the
-// hot loop stays inside the instruction cache.
+// Persistent-block wavefront with pixel streaming.  A block keeps P.block_slots paths in flight and
+// runs its own bounce loop: four queues of local slot ids in shared memory (regenerate | lambertian |
+// metallic | dielectric), double buffered.  Every pass lays the four queues out back to back, each
+// padded to a warp multiple, so a warp only ever executes one kind of work; warps pull 32-item chunks
+// from a shared counter (cheap items do not leave a warp idle); results are pushed into the other
+// buffer with warp-aggregated shared-memory atomics.  A local slot renders one pixel at a time, all
+// its samples in order (the pixel's XORWOW stream is serial); when the pixel is finished the slot
+// fetches the next unrendered pixel slot from a global counter (one atomic per warp), so every block
+// stays full until the whole chunk runs out of pixels -- no per-tile tail, no wave quantisation, and
+// the state of the paths in flight (grid x block_slots records) stays L2 resident.  One launch per
+// chunk, no host round trips.  The ray trace (extend) has ONE call site so the hot loop stays inside
+// the instruction cache.
+#define SRT_NO_SLOT 0xFFFFFFFFu
 template <bool SMEM, bool FLAT>
 __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefront(WaveParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t S = P.block_slots;
-    uint16_t* qbuf = reinterpret_cast<uint16_t*>(smem);  // [2][4][S]
+    uint16_t* qbuf = reinterpret_cast<uint16_t*>(smem);                        // [2][4][S] queues of local slot ids
+    uint32_t* pslot = reinterpret_cast<uint32_t*>(smem + 16u * S);             // [S] pixel slot a local slot renders
+    uint16_t* started = reinterpret_cast<uint16_t*>(smem + 20u * S);           // [S] samples started of that pixel
     __shared__ int cnt[2][4];
     __shared__ int next_chunk;
     const SceneRef sc = load_scene<SMEM, FLAT>(P, smem + P.queue_bytes);
-    const uint32_t first = blockIdx.x * S;
+    const uint32_t first = blockIdx.x * S;  // this block's records in the in-flight state arrays
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < 8) (&cnt[0][0])[threadIdx.x] = 0;
-    if (threadIdx.x == 0) next_chunk = 0;
-    __syncthreads();
-    // pass 0 input: every slot of the block that this rank owns, samples reset
+    if (threadIdx.x == 0) { next_chunk = 0; cnt[0][0] = (int)S; }
+    // pass 0 input: every local slot asks for a pixel
     for (uint32_t l = threadIdx.x; l < S; l += blockDim.x) {
-        uint32_t ci, cj;
-        const bool mine = slot_owned(P, first + l, ci, cj);
-        if (mine) P.sidx[first + l] = 0;
-        queue_push(qbuf, &cnt[0][0], mine, l);
+        pslot[l] = SRT_NO_SLOT;
+        started[l] = 0;
+        qbuf[l] = (uint16_t)l;
     }
     __syncthreads();
     unsigned long long rays = 0;
@@ -663,43 +667,71 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
             const int have_n = kind == 0 ? nR : (kind == 1 ? nL : (kind == 2 ? nM : nD));
             const bool have = k < have_n;
             const uint32_t l = have ? qi[kind * S + k] : 0u;
-            const uint32_t slot = first + l;
+            const uint32_t rec = first + l;
+            uint32_t slot = have ? pslot[l] : SRT_NO_SLOT;
+            uint32_t s = started[l];
             uint32_t ci = 0, cj = 0;
             size_t pix = 0;
             Path p;
             Rng rng;
             int tri = -1, ev = EV_DONE;
-            uint32_t s = 0;
-            bool trace = false;
-            if (have) {
-                slot_pixel(P, slot, ci, cj);
-                pix = (size_t)(P.off_y + cj) * P.img_w + (P.off_x + ci);
-                rng = load_rng(P, slot);
-                s = P.sidx[slot];
-                if (kind == 0) {  // next sample of this pixel (rendering.cu:215-228)
-                    if (s < P.spp) {
+            bool trace = false, retired = false;
+            if (kind == 0) {  // warp-uniform
+                // slots without a pixel fetch the next unrendered pixel slots: one global atomic per warp
+                const bool fetch = have && slot == SRT_NO_SLOT;
+                const uint32_t fm = __ballot_sync(0xffffffffu, fetch);
+                if (fm) {
+                    uint32_t fbase = 0;
+                    if (lane == __ffs(fm) - 1) fbase = atomicAdd(P.next_slot, (uint32_t)__popc(fm));
+                    fbase = __shfl_sync(0xffffffffu, fbase, __ffs(fm) - 1);
+                    if (fetch) {
+                        const uint32_t cand = fbase + __popc(fm & ((1u << lane) - 1));
+                        if (cand >= P.nslots) retired = true;  // the chunk has no pixels left: this local slot is done
+                        else if (slot_owned(P, cand, ci, cj)) {  // edge tiles stick out of the chunk: such a slot asks again next pass
+                            slot = cand;
+                            pslot[l] = slot;
+                            s = 0;
+                            rng = load_rng(P.G0, P.G1, slot);
+                        }
+                    }
+                }
+                if (have && slot != SRT_NO_SLOT) {
+                    if (!fetch) {
+                        slot_pixel(P, slot, ci, cj);
+                        rng = load_rng(P.L0, P.L1, rec);
+                    }
+                    pix = (size_t)(P.off_y + cj) * P.img_w + (P.off_x + ci);
+                    if (s < P.spp) {  // next sample of this pixel (rendering.cu:215-228)
                         camera_ray(P.cam, P.off_x + ci, P.off_y + cj, rng, p);
                         s++;
-                        P.sidx[slot] = s;
+                        started[l] = (uint16_t)s;
                         trace = P.bounce_limit != 0;  // limit 0: the bounce loop never runs, valid = 0
                     }
-                } else {  // scatter at the stored hit (warp-uniform material)
-                    load_hit_state(P, slot, p, tri);
-                    const uint32_t mtype = kind == 2 ? SRT_METALLIC : (kind == 3 ? SRT_DIELECTRIC : SRT_LAMBERTIAN);
-                    const bool alive = scatter(sc, sc.tris + tri, mtype, p, rng);
-                    p.bounce++;
-                    trace = alive && p.bounce < P.bounce_limit;  // absorbed, or bounce limit: valid = 0 (rendering.cu:38)
                 }
+            } else if (have) {  // scatter at the stored hit (warp-uniform material)
+                slot_pixel(P, slot, ci, cj);
+                pix = (size_t)(P.off_y + cj) * P.img_w + (P.off_x + ci);
+                rng = load_rng(P.L0, P.L1, rec);
+                load_hit_state(P, rec, p, tri);
+                const uint32_t mtype = kind == 2 ? SRT_METALLIC : (kind == 3 ? SRT_DIELECTRIC : SRT_LAMBERTIAN);
+                const bool alive = scatter(sc, sc.tris + tri, mtype, p, rng);
+                p.bounce++;
+                trace = alive && p.bounce < P.bounce_limit;  // absorbed, or bounce limit: valid = 0 (rendering.cu:38)
             }
             if (trace) {
                 rays++;
                 ev = extend<FLAT>(sc, P, p, tri, P.acc, pix, kind == 0);
             }
-            if (have) {
-                store_rng(P, slot, rng);
-                if (ev != EV_DONE) store_hit_state(P, slot, p, tri);
+            if (have && slot != SRT_NO_SLOT) {
+                if (ev == EV_DONE && s >= P.spp) {  // pixel finished: its RNG state goes back to the pixel (carried into the next chunk)
+                    store_rng(P.G0, P.G1, slot, rng);
+                    pslot[l] = SRT_NO_SLOT;
+                } else {
+                    store_rng(P.L0, P.L1, rec, rng);
+                    if (ev != EV_DONE) store_hit_state(P, rec, p, tri);
+                }
             }
-            queue_push(qo, co + 0, have && ev == EV_DONE && s < P.spp, l);  // sample over, pixel not finished
+            queue_push(qo, co + 0, have && !retired && ev == EV_DONE, l);  // next sample, or next pixel
             queue_push(qo + S, co + 1, ev == 1, l);
             queue_push(qo + 2 * S, co + 2, ev == 2, l);
             queue_push(qo + 3 * S, co + 3, ev == 3, l);
@@ -724,7 +756,7 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_megakernel(WaveParams P) {
         if (!slot_owned(P, slot, ci, cj)) continue;
         const uint32_t x = P.off_x + ci, y = P.off_y + cj;
         const size_t pix = (size_t)y * P.img_w + x;
-        Rng rng = load_rng(P, slot);
+        Rng rng = load_rng(P.G0, P.G1, slot);
         for (uint32_t s = 0; s < P.spp; s++) {
             Path p;
             camera_ray(P.cam, x, y, rng, p);
@@ -740,7 +772,7 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_megakernel(WaveParams P) {
                 ev = extend<FLAT>(sc, P, p, tri, P.acc, pix);
             }
         }
-        store_rng(P, slot, rng);
+        store_rng(P.G0, P.G1, slot, rng);
     }
     if (P.ray_counter && rays) atomicAdd(P.ray_counter, rays);
 }
@@ -867,6 +899,14 @@ LaunchTable make_launch_table() {
         if (mode == 2) k_wavefront<true, true><<<grid, threads, smem, st>>>(P);
         else if (mode == 1) k_wavefront<true, false><<<grid, threads, smem, st>>>(P);
         else k_wavefront<false, false><<<grid, threads, smem, st>>>(P);
+    };
+    t.wavefront_blocks_per_sm = [](int mode, int threads, size_t smem) {
+        int n = 0;
+        cudaError_t e;
+        if (mode == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront<true, true>, threads, smem);
+        else if (mode == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront<true, false>, threads, smem);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront<false, false>, threads, smem);
+        return e == cudaSuccess ? n : 0;
     };
     t.megakernel = [](const WaveParams& P, int mode, int grid, size_t smem, cudaStream_t st) { SRT_DISPATCH(k_megakernel, mode, grid, smem, st, P); };
     t.resolve = [](const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,

@@ -29,26 +29,29 @@ struct WaveParams {
     SrtCamera cam;
     uint32_t off_x, off_y, cw, ch;   // current chunk (pixels)
     uint32_t img_w, img_h;
-    uint32_t nslots;                 // n_tiles * block_slots
+    uint32_t nslots;                 // pixel slots of this rank: n_tiles * tile_w * tile_h
     const uint32_t* tiles;           // chunk-local tile ids owned by this rank (tile_id % world == rank)
     uint32_t n_tiles;
     uint32_t ref_grid_x;             // nominal_chunk_w / 28 + 1 (reference launch geometry -> seeds)
     uint32_t spp, bounce_limit;
     int regen_loop;
     uint32_t tile_w, tile_h, tiles_x, rank, world;  // tiles_x: tiles per row of the nominal chunk
-    // per-slot path state, 16-byte vectors
+    // path state of the paths in flight, one record per (wavefront block, local slot), 16-byte vectors
     float4* R0;    // hit point xyz | triangle (leaf order)
     float4* R1;    // incoming direction xyz | valid[2:0] + bounce
     float4* P0;    // power 0..3
     float4* P1;    // power 4..6 | hero wavelength
-    uint4* G0;     // XORWOW d v0 v1 v2
-    uint2* G1;     // XORWOW v3 v4
-    uint32_t* sidx;  // samples started
+    uint4* L0;     // XORWOW state of the pixel a local slot is rendering: d v0 v1 v2
+    uint2* L1;     //                                                    v3 v4
+    // per pixel slot: XORWOW state between pixels / chunks (seeded once, carried across chunks)
+    uint4* G0;
+    uint2* G1;
+    uint32_t* next_slot;  // next pixel slot nobody renders yet (zeroed before every wavefront launch)
     float* acc;      // film: XYZ sums, 3 planes of `plane` floats, full-image raster
     size_t plane;
-    // persistent-block wavefront: slots per block and the shared-memory bytes its queues take
+    // persistent-block wavefront: paths in flight per block and the shared-memory bytes its queues take
     uint32_t block_slots, queue_bytes;
-    uint32_t block_slots_log2, tile_w_log2;
+    uint32_t tile_slots_log2, tile_w_log2;  // log2(tile_w * tile_h), log2(tile_w)
     uint32_t block_threads;  // threads of a wavefront block (128 or 256)
     float scene_lo[3], scene_hi[3];  // bounding box of all triangles (host)
     unsigned long long* ray_counter;
@@ -59,6 +62,7 @@ struct LaunchTable {
     cudaError_t (*configure)(size_t smem_bytes);
     void (*init_slots)(const WaveParams&, cudaStream_t);
     void (*wavefront)(const WaveParams&, int mode, int grid, size_t smem, cudaStream_t);
+    int (*wavefront_blocks_per_sm)(int mode, int threads, size_t smem);  // resident blocks the hardware grants
     void (*megakernel)(const WaveParams&, int mode, int grid, size_t smem, cudaStream_t);
     void (*resolve)(const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,
                     cudaStream_t);

@@ -144,7 +144,7 @@ struct RenderConfig {
     unsigned spp = 1, bounce_limit = 10;
     unsigned chunk_w = 0, chunk_h = 0;   // nominal chunk geometry (seeds depend on it, reference Q15)
     int fp_strict = 0, pipeline = 0, regen_loop = 4, kernel_timing = 0, tail_threshold = 0;
-    int block_slots = 1024;  // (unused) 
+    int block_slots = 0;     // paths in flight per wavefront block (power of two), 0 = automatic
     int block_threads = 0;   // threads per wavefront block, 0 = automatic
     int traversal = 0;  // 0 auto (wide leaf when <= 64 triangles), 1 force LBVH walk in shared memory, 3 force LBVH walk in global memory
     int tile_w = 0, tile_h = 0, rank = 0, world = 1;  // tile 0x0 = pick automatically

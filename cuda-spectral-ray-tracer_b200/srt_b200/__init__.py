@@ -356,8 +356,8 @@ def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=Fals
     if tiles is not None:
         tw, th, rank, world = tiles
         rm.set_option(OPT_TILE_W, tw); rm.set_option(OPT_TILE_H, th); rm.set_option(OPT_RANK, rank); rm.set_option(OPT_WORLD, world)
-    if block_slots is not None:  # legacy spelling: a tile of 32 x (block_slots/32) pixels per wavefront block
-        rm.set_option(OPT_TILE_W, 32); rm.set_option(OPT_TILE_H, max(1, block_slots // 32))
+    if block_slots is not None:  # paths in flight per wavefront block (power of two)
+        rm.set_option(OPT_BLOCK_SLOTS, block_slots)
     rm.init_device_params(*chunk)
     rm.render_all()
     return fb.rgb().copy(), rm.xyz(), rm.stats()

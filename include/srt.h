@@ -180,7 +180,7 @@ int srt_rm_render_all(srt_render_manager*);
 #define SRT_OPT_REGEN_LOOP 7   /* camera-ray regenerations a slot may do inside one wavefront pass (tuning) */
 #define SRT_OPT_KERNEL_TIMING 8 /* 1 = bracket every kernel launch with CUDA events (per-kernel totals in srt_stats) */
 #define SRT_OPT_TAIL_THRESHOLD 9 /* (unused since the persistent-block wavefront; kept for ABI stability) */
-#define SRT_OPT_BLOCK_SLOTS 11   /* (unused: a wavefront block renders one tile, see SRT_OPT_TILE_W/H) */
+#define SRT_OPT_BLOCK_SLOTS 11   /* paths in flight per wavefront block: power of two in [32, 4096], 0 = automatic */
 #define SRT_OPT_BLOCK_THREADS 12 /* threads per wavefront block: 0 = 256 */
 #define SRT_OPT_TRAVERSAL 10     /* 0 auto (wide-leaf closest hit when the scene has <= 64 triangles), 1 force the LBVH walk
                                     (scene in shared memory), 3 force the LBVH walk with the scene in global memory */
