@@ -1,6 +1,11 @@
 // srt_cli: drop-in for the reference executable (main.cpp:135-167) on top of the C-ABI.
 // Same flags (io/params.h:236-304); --no-show is implied (there is no display window), --save
 // writes renders/<title>.bmp like main.cpp:113-118, plus a .ppm next to it.
+// Extensions the reference does not have (stripped before the reference's parser sees the line):
+//   --stratified        stratified pixel sampler (spp must be a square number)
+//   --strict-fp         kernels built without FMA contraction (bit-identical to the reference's host build)
+//   --mesh <file>       render a .obj / .ply mesh (grey lambertian) with the scene's camera instead of scene <id>
+//   --xyz <file>        dump the film as raw float32 XYZ planes (X plane, Y plane, Z plane; mean per pixel)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -11,12 +16,35 @@
 #include "srt.h"
 
 int main(int argc, char** argv) {
+    bool stratified = false, strict_fp = false;
+    std::string mesh_path, xyz_path;
+    std::vector<char*> ref_args;
+    for (int i = 0; i < argc; i++) {
+        const std::string a(argv[i]);
+        if (i > 0 && a == "--stratified") stratified = true;
+        else if (i > 0 && a == "--strict-fp") strict_fp = true;
+        else if (i > 0 && a == "--mesh" && i + 1 < argc) mesh_path = argv[++i];
+        else if (i > 0 && a == "--xyz" && i + 1 < argc) xyz_path = argv[++i];
+        else ref_args.push_back(argv[i]);
+    }
+    argc = (int)ref_args.size();
+    argv = ref_args.data();
     srt_params* pm = srt_params_instance();
     srt_params_parse(pm, argc, argv);
     std::printf("Image Title: %s\nScene ID: %u\nX res: %u\nY res: %u\nAR: %g\nX chunk size: %u\nY chunk size: %u\n# samples: %u\n# max bounces: %u\n",
                 srt_params_img_title(pm), srt_params_scene_id(pm), srt_params_xres(pm), srt_params_yres(pm), srt_params_ar(pm),
                 srt_params_xcsize(pm), srt_params_ycsize(pm), srt_params_nsamples(pm), srt_params_bounce_limit(pm));
-    srt_scene* scene = srt_scene_create(srt_params_scene_id(pm));
+    srt_scene* scene = nullptr;
+    if (mesh_path.empty()) scene = srt_scene_create(srt_params_scene_id(pm));
+    else {
+        srt_material_desc grey{};
+        grey.type = SRT_MAT_LAMBERTIAN;
+        grey.color[0] = grey.color[1] = grey.color[2] = 0.73f;
+        grey.fuzz = 1.0f;
+        const bool ply = mesh_path.size() > 4 && mesh_path.compare(mesh_path.size() - 4, 4, ".ply") == 0;
+        scene = ply ? srt_scene_create_ply(mesh_path.c_str(), &grey, 1) : srt_scene_create_obj(mesh_path.c_str(), &grey, 1);
+        if (!scene) { std::fprintf(stderr, "%s\n", srt_last_error()); return 1; }
+    }
     const char* msg = nullptr;
     if (!srt_scene_result(scene, &msg)) { std::fprintf(stderr, "%s\n", msg); return 1; }
     std::printf("%s\n", msg);
@@ -25,6 +53,8 @@ int main(int argc, char** argv) {
     const size_t n = (size_t)cam.width * cam.height;
     std::vector<float> r(n), g(n), b(n);
     srt_render_manager* rm = srt_render_manager_create(scene, &cam, r.data(), g.data(), b.data());
+    if (stratified) srt_rm_set_option(rm, SRT_OPT_STRATIFIED, 1);
+    if (strict_fp) srt_rm_set_option(rm, SRT_OPT_FP_MODE, 1);
     if (srt_rm_init_renderer(rm, srt_params_bounce_limit(pm), srt_params_nsamples(pm)) != SRT_OK ||
         srt_rm_init_device_params(rm, srt_params_xcsize(pm), srt_params_ycsize(pm)) != SRT_OK) {
         std::fprintf(stderr, "%s\n", srt_last_error());
@@ -63,6 +93,14 @@ int main(int argc, char** argv) {
         mkdir("renders", 0755);
         srt_write_bmp(("renders/" + name + ".bmp").c_str(), r.data(), g.data(), b.data(), cam.width, cam.height);
         srt_write_ppm(("renders/" + name + ".ppm").c_str(), r.data(), g.data(), b.data(), cam.width, cam.height);
+    }
+    if (!xyz_path.empty()) {
+        std::vector<float> xyz(3 * n);
+        if (srt_rm_get_xyz(rm, xyz.data()) != SRT_OK) { std::fprintf(stderr, "%s\n", srt_last_error()); return 1; }
+        if (FILE* f = std::fopen(xyz_path.c_str(), "wb")) {
+            std::fwrite(xyz.data(), sizeof(float), xyz.size(), f);
+            std::fclose(f);
+        } else { std::fprintf(stderr, "cannot write %s\n", xyz_path.c_str()); return 1; }
     }
     srt_render_manager_destroy(rm);
     srt_scene_destroy(scene);

@@ -196,7 +196,15 @@ static bool renderer_setup(DeviceRenderer* r) {
     P.ref_grid_x = c.chunk_w / 28u + 1u;  // render_manager.cu:93-96
     P.spp = c.spp & 0xFFFFu;              // short_uint kernel parameters (rendering.cu:154, Q14)
     P.bounce_limit = c.bounce_limit & 0xFFFFu;
-    P.regen_loop = c.regen_loop < 1 ? 1 : c.regen_loop;
+    P.strat_n = 0; P.strat_recip = 0.0f;
+    if (c.stratified) {
+        while ((P.strat_n + 1) * (P.strat_n + 1) <= P.spp) P.strat_n++;
+        if (P.strat_n * P.strat_n != P.spp) {
+            set_error("stratified sampling needs a square number of samples per pixel");
+            return false;
+        }
+        P.strat_recip = 1.0f / (float)P.strat_n;
+    }
     P.plane = (size_t)P.img_w * P.img_h;
     const size_t ns = std::max<size_t>(P.nslots, 1);
     if (!device_pool_alloc((void**)&r->d_tiles, std::max<size_t>(1, r->h_tiles.size()) * sizeof(uint32_t))) return false;

@@ -323,12 +323,22 @@ struct Path {
 };
 
 // renderer::get_ray (rendering.cu:66-87) + ray ctor / init_spectrum (ray/ray.cuh:27-58)
-__device__ __forceinline__ void camera_ray(const SrtCamera& c, uint32_t i, uint32_t j, Rng& rng, Path& p) {
+// sample = index of this sample inside its pixel; only the opt-in stratified sampler looks at it
+// (pixel_stratified_sample_square rendering.cu:58-64: sub-cell (sample % n, sample / n) of an n x n grid)
+__device__ __forceinline__ void camera_ray(const WaveParams& P, uint32_t i, uint32_t j, uint32_t sample, Rng& rng, Path& p) {
+    const SrtCamera& c = P.cam;
     const V3 du = mk(c.du[0], c.du[1], c.du[2]), dv = mk(c.dv[0], c.dv[1], c.dv[2]);
     const V3 center = mk(c.center[0], c.center[1], c.center[2]);
     const V3 pixel_center = (mk(c.p00[0], c.p00[1], c.p00[2]) + ((float)i * du)) + ((float)j * dv);
-    const float px = -0.5f + rng_uniform(rng);
-    const float py = -0.5f + rng_uniform(rng);
+    float px, py;
+    if (P.strat_n) {
+        const uint32_t sy = sample / P.strat_n, sx = sample - sy * P.strat_n;
+        px = -0.5f + P.strat_recip * ((float)sx + rng_uniform(rng));
+        py = -0.5f + P.strat_recip * ((float)sy + rng_uniform(rng));
+    } else {
+        px = -0.5f + rng_uniform(rng);
+        py = -0.5f + rng_uniform(rng);
+    }
     const V3 pixel_sample = pixel_center + ((px * du) + (py * dv));
     V3 origin = center;
     if (!(c.defocus_angle <= 0.0f)) {  // defocus_disk_sample :42-47, random_in_unit_disk vec3.cuh:240-246
@@ -702,7 +712,7 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
                     }
                     pix = (size_t)(P.off_y + cj) * P.img_w + (P.off_x + ci);
                     if (s < P.spp) {  // next sample of this pixel (rendering.cu:215-228)
-                        camera_ray(P.cam, P.off_x + ci, P.off_y + cj, rng, p);
+                        camera_ray(P, P.off_x + ci, P.off_y + cj, s, rng, p);
                         s++;
                         started[l] = (uint16_t)s;
                         trace = P.bounce_limit != 0;  // limit 0: the bounce loop never runs, valid = 0
@@ -759,7 +769,7 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_megakernel(WaveParams P) {
         Rng rng = load_rng(P.G0, P.G1, slot);
         for (uint32_t s = 0; s < P.spp; s++) {
             Path p;
-            camera_ray(P.cam, x, y, rng, p);
+            camera_ray(P, x, y, s, rng, p);
             if (P.bounce_limit == 0) continue;
             int tri = -1;
             rays++;

@@ -34,7 +34,8 @@ struct WaveParams {
     uint32_t n_tiles;
     uint32_t ref_grid_x;             // nominal_chunk_w / 28 + 1 (reference launch geometry -> seeds)
     uint32_t spp, bounce_limit;
-    int regen_loop;
+    uint32_t strat_n;      // 0: the reference's sampler; n: stratified n x n sub-cells per pixel (n*n == spp)
+    float strat_recip;     // 1 / n
     uint32_t tile_w, tile_h, tiles_x, rank, world;  // tiles_x: tiles per row of the nominal chunk
     // path state of the paths in flight, one record per (wavefront block, local slot), 16-byte vectors
     float4* R0;    // hit point xyz | triangle (leaf order)

@@ -105,6 +105,11 @@ srt_scene* srt_scene_create_obj(const char* path, const srt_material_desc* mats,
     if (!path || !load_obj(path, v)) return nullptr;
     return srt_scene_create_mesh(v.data(), nullptr, (uint32_t)(v.size() / 9), mats, n_mats);
 }
+srt_scene* srt_scene_create_ply(const char* path, const srt_material_desc* mats, uint32_t n_mats) {
+    std::vector<float> v;
+    if (!path || !load_ply(path, v)) return nullptr;
+    return srt_scene_create_mesh(v.data(), nullptr, (uint32_t)(v.size() / 9), mats, n_mats);
+}
 void srt_scene_destroy(srt_scene* s) { delete s; }
 int srt_scene_result(const srt_scene* s, const char** msg) {
     if (!s) { if (msg) *msg = "null scene"; return 0; }

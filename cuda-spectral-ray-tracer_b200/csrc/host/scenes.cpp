@@ -178,4 +178,114 @@ bool load_obj(const char* path, std::vector<float>& verts9) {
     return true;
 }
 
+// Stanford PLY: ascii or binary_little_endian; element vertex with x y z (any scalar type, extra
+// properties skipped), element face with one list property (fan triangulation); other elements skipped
+// when they come after the faces, refused when they come before (their size may be unknown).
+namespace {
+int ply_type_size(const std::string& t) {
+    if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+    if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+    if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
+    if (t == "double" || t == "float64") return 8;
+    return 0;
+}
+double ply_read_scalar(std::istream& in, const std::string& t, bool ascii) {
+    if (ascii) { double v = 0; in >> v; return v; }
+    unsigned char b[8] = {0};
+    in.read(reinterpret_cast<char*>(b), ply_type_size(t));
+    if (t == "char" || t == "int8") return (double)(signed char)b[0];
+    if (t == "uchar" || t == "uint8") return (double)b[0];
+    if (t == "short" || t == "int16") { int16_t v; std::memcpy(&v, b, 2); return v; }
+    if (t == "ushort" || t == "uint16") { uint16_t v; std::memcpy(&v, b, 2); return v; }
+    if (t == "int" || t == "int32") { int32_t v; std::memcpy(&v, b, 4); return v; }
+    if (t == "uint" || t == "uint32") { uint32_t v; std::memcpy(&v, b, 4); return v; }
+    if (t == "float" || t == "float32") { float v; std::memcpy(&v, b, 4); return v; }
+    double v; std::memcpy(&v, b, 8); return v;
+}
+}  // namespace
+
+bool load_ply(const char* path, std::vector<float>& verts9) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) { set_error(std::string("cannot open PLY file ") + path); return false; }
+    std::string line;
+    if (!std::getline(in, line) || line.compare(0, 3, "ply") != 0) { set_error("not a PLY file"); return false; }
+    struct Prop { std::string name, type, count_type; bool is_list; };
+    struct Elem { std::string name; size_t count; std::vector<Prop> props; };
+    std::vector<Elem> elems;
+    bool ascii = true, header_done = false;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        std::istringstream ss(line);
+        std::string tag;
+        ss >> tag;
+        if (tag == "format") {
+            std::string f;
+            ss >> f;
+            if (f == "ascii") ascii = true;
+            else if (f == "binary_little_endian") ascii = false;
+            else { set_error("PLY format " + f + " is not supported"); return false; }
+        } else if (tag == "element") {
+            Elem e;
+            ss >> e.name >> e.count;
+            elems.push_back(e);
+        } else if (tag == "property" && !elems.empty()) {
+            Prop pr;
+            std::string t;
+            ss >> t;
+            pr.is_list = t == "list";
+            if (pr.is_list) ss >> pr.count_type >> pr.type >> pr.name;
+            else { pr.type = t; ss >> pr.name; }
+            if (!ply_type_size(pr.type) || (pr.is_list && !ply_type_size(pr.count_type))) { set_error("PLY property type not understood"); return false; }
+            elems.back().props.push_back(pr);
+        } else if (tag == "end_header") { header_done = true; break; }
+    }
+    if (!header_done) { set_error("PLY header has no end_header"); return false; }
+    std::vector<float> pos;
+    bool have_faces = false;
+    for (const Elem& e : elems) {
+        if (e.name == "vertex") {
+            int ix = -1, iy = -1, iz = -1;
+            for (size_t k = 0; k < e.props.size(); k++) {
+                if (e.props[k].is_list) { set_error("PLY vertex list properties are not supported"); return false; }
+                if (e.props[k].name == "x") ix = (int)k;
+                if (e.props[k].name == "y") iy = (int)k;
+                if (e.props[k].name == "z") iz = (int)k;
+            }
+            if (ix < 0 || iy < 0 || iz < 0) { set_error("PLY vertex element lacks x/y/z"); return false; }
+            pos.resize(3 * e.count);
+            for (size_t v = 0; v < e.count; v++)
+                for (size_t k = 0; k < e.props.size(); k++) {
+                    const double val = ply_read_scalar(in, e.props[k].type, ascii);
+                    if ((int)k == ix) pos[3 * v] = (float)val;
+                    if ((int)k == iy) pos[3 * v + 1] = (float)val;
+                    if ((int)k == iz) pos[3 * v + 2] = (float)val;
+                }
+        } else if (e.name == "face") {
+            const long nv = (long)(pos.size() / 3);
+            for (size_t f = 0; f < e.count; f++)
+                for (const Prop& pr : e.props) {
+                    if (!pr.is_list) { ply_read_scalar(in, pr.type, ascii); continue; }
+                    const long cnt = (long)ply_read_scalar(in, pr.count_type, ascii);
+                    std::vector<long> idx;
+                    for (long k = 0; k < cnt; k++) idx.push_back((long)ply_read_scalar(in, pr.type, ascii));
+                    if (pr.name != "vertex_indices" && pr.name != "vertex_index") continue;
+                    for (long v : idx)
+                        if (v < 0 || v >= nv) { set_error("PLY face references a missing vertex"); return false; }
+                    for (size_t k = 2; k < idx.size(); k++) {
+                        const long tri[3] = {idx[0], idx[k - 1], idx[k]};
+                        for (long v : tri)
+                            for (int c = 0; c < 3; c++) verts9.push_back(pos[3 * v + c]);
+                    }
+                }
+            have_faces = true;
+        } else if (!have_faces) {
+            set_error("PLY element '" + e.name + "' before the faces is not supported");
+            return false;
+        }
+        if (!in) { set_error("PLY file is truncated"); return false; }
+    }
+    if (!have_faces) { set_error("PLY file has no face element"); return false; }
+    return true;
+}
+
 }  // namespace srt

@@ -100,6 +100,7 @@ struct SceneDescription {
 SceneDescription make_reference_scene(unsigned scene_id, bool ref_compat);
 SceneDescription make_soup_scene(uint32_t n, uint64_t seed);
 bool load_obj(const char* path, std::vector<float>& verts9);
+bool load_ply(const char* path, std::vector<float>& verts9);
 
 // sRGB -> sigmoid-polynomial coefficients, computed on demand (replaces the 9.4 MB table)
 namespace rgb2spec {
@@ -143,7 +144,8 @@ struct RenderConfig {
     srt_camera cam;
     unsigned spp = 1, bounce_limit = 10;
     unsigned chunk_w = 0, chunk_h = 0;   // nominal chunk geometry (seeds depend on it, reference Q15)
-    int fp_strict = 0, pipeline = 0, regen_loop = 4, kernel_timing = 0, tail_threshold = 0;
+    int fp_strict = 0, pipeline = 0, kernel_timing = 0;
+    int stratified = 0;      // opt-in stratified pixel sampler (dormant in the reference, rendering.cu:58-64,89-118)
     int block_slots = 0;     // paths in flight per wavefront block (power of two), 0 = automatic
     int block_threads = 0;   // threads per wavefront block, 0 = automatic
     int traversal = 0;  // 0 auto (wide leaf when <= 64 triangles), 1 force LBVH walk in shared memory, 3 force LBVH walk in global memory

@@ -44,7 +44,7 @@ class Stats(C.Structure):
                 ("generate_launches", C.c_uint64), ("shade_launches", C.c_uint64), ("tail_launches", C.c_uint64)]
 
 
-OPT_FP_MODE, OPT_PIPELINE, OPT_TILE_W, OPT_TILE_H, OPT_RANK, OPT_WORLD, OPT_REGEN_LOOP, OPT_KERNEL_TIMING, OPT_TAIL_THRESHOLD, OPT_TRAVERSAL, OPT_BLOCK_SLOTS, OPT_BLOCK_THREADS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
+OPT_FP_MODE, OPT_PIPELINE, OPT_TILE_W, OPT_TILE_H, OPT_RANK, OPT_WORLD, OPT_REGEN_LOOP, OPT_KERNEL_TIMING, OPT_TAIL_THRESHOLD, OPT_TRAVERSAL, OPT_BLOCK_SLOTS, OPT_BLOCK_THREADS, OPT_STRATIFIED = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13
 MAT_LAMBERTIAN, MAT_METALLIC, MAT_DIELECTRIC, MAT_EMISSIVE = 0, 1, 2, 4
 
 # every symbol include/srt.h declares: (name, restype, argtypes)
@@ -76,6 +76,7 @@ _SIGS = [
     ("srt_scene_create_soup", _P, [C.c_uint32, C.c_uint64]),
     ("srt_scene_create_mesh", _P, [_P, _P, C.c_uint32, C.POINTER(MaterialDesc), C.c_uint32]),
     ("srt_scene_create_obj", _P, [C.c_char_p, C.POINTER(MaterialDesc), C.c_uint32]),
+    ("srt_scene_create_ply", _P, [C.c_char_p, C.POINTER(MaterialDesc), C.c_uint32]),
     ("srt_scene_destroy", None, [_P]),
     ("srt_scene_result", C.c_int, [_P, C.POINTER(C.c_char_p)]),
     ("srt_scene_camera", C.c_int, [_P, C.POINTER(Camera)]),
@@ -191,7 +192,7 @@ class CameraBuilder:
 class Scene:
     """scene_manager (reference scene/scene.cuh:103-176): builds triangles, materials and the device LBVH."""
 
-    def __init__(self, scene_id=None, soup=None, seed=1984, mesh=None, obj=None, host_only=False):
+    def __init__(self, scene_id=None, soup=None, seed=1984, mesh=None, obj=None, ply=None, host_only=False):
         """host_only=True keeps a scene whose device upload failed (no GPU): only the host-side
         dumps (tris(), materials(), camera()) work on it; rendering raises."""
         L = lib()
@@ -207,6 +208,10 @@ class Scene:
             path, mats = obj
             arr = (MaterialDesc * len(mats))(*mats)
             self.h = L.srt_scene_create_obj(str(path).encode(), arr, len(mats))
+        elif ply is not None:
+            path, mats = ply
+            arr = (MaterialDesc * len(mats))(*mats)
+            self.h = L.srt_scene_create_ply(str(path).encode(), arr, len(mats))
         else:
             self.h = L.srt_scene_create(scene_id)
         if not self.h:
@@ -334,7 +339,7 @@ class RenderManager:
 
 
 def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=False, pipeline=0, scene=None, tiles=None, regen_loop=None,
-           kernel_timing=False, tail_threshold=None, traversal=None, block_slots=None, block_threads=None):
+           kernel_timing=False, tail_threshold=None, traversal=None, block_slots=None, block_threads=None, stratified=False):
     """One-call helper: returns (rgb[3,h,w] float32 0..255, xyz[3,h,w] float32, stats dict)."""
     sc = scene if scene is not None else Scene(scene_id)
     cam = sc.camera(w, h)
@@ -353,6 +358,8 @@ def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=Fals
         rm.set_option(OPT_TRAVERSAL, traversal)
     if block_threads is not None:
         rm.set_option(OPT_BLOCK_THREADS, block_threads)
+    if stratified:
+        rm.set_option(OPT_STRATIFIED, 1)
     if tiles is not None:
         tw, th, rank, world = tiles
         rm.set_option(OPT_TILE_W, tw); rm.set_option(OPT_TILE_H, th); rm.set_option(OPT_RANK, rank); rm.set_option(OPT_WORLD, world)

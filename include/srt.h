@@ -108,6 +108,8 @@ srt_scene* srt_scene_create_mesh(const float* verts, const uint32_t* mat_index, 
                                  const srt_material_desc* mats, uint32_t n_mats);
 /* Wavefront OBJ (v / f records, fan triangulation), all faces get material 0 of `mats` */
 srt_scene* srt_scene_create_obj(const char* path, const srt_material_desc* mats, uint32_t n_mats);
+/* Stanford PLY (ascii or binary_little_endian; vertex x y z + face vertex_indices lists, fan triangulation) */
+srt_scene* srt_scene_create_ply(const char* path, const srt_material_desc* mats, uint32_t n_mats);
 void srt_scene_destroy(srt_scene*);
 /* getResult(): returns 1 when the world was created, *msg = "World created" or the error */
 int srt_scene_result(const srt_scene*, const char** msg);
@@ -177,11 +179,14 @@ int srt_rm_render_all(srt_render_manager*);
 #define SRT_OPT_TILE_H 4
 #define SRT_OPT_RANK 5         /* ... this process renders the tiles with (tile_x + 5 tile_y) % world == rank */
 #define SRT_OPT_WORLD 6
-#define SRT_OPT_REGEN_LOOP 7   /* camera-ray regenerations a slot may do inside one wavefront pass (tuning) */
+#define SRT_OPT_REGEN_LOOP 7   /* (retired tuning knob: accepted and ignored, kept for ABI stability) */
 #define SRT_OPT_KERNEL_TIMING 8 /* 1 = bracket every kernel launch with CUDA events (per-kernel totals in srt_stats) */
-#define SRT_OPT_TAIL_THRESHOLD 9 /* (unused since the persistent-block wavefront; kept for ABI stability) */
+#define SRT_OPT_TAIL_THRESHOLD 9 /* (retired tuning knob: accepted and ignored, kept for ABI stability) */
 #define SRT_OPT_BLOCK_SLOTS 11   /* paths in flight per wavefront block: power of two in [32, 4096], 0 = automatic */
 #define SRT_OPT_BLOCK_THREADS 12 /* threads per wavefront block: 0 = 256 */
+#define SRT_OPT_STRATIFIED 13    /* 1 = stratified pixel sampler (renderer::get_ray_stratified_sample, rendering/rendering.cu:58-64,89-118,
+                                    which the reference carries but never calls): sample k takes sub-cell (k % n, k / n) of an n x n
+                                    grid, spp must be n*n; 0 (default) = the reference's sampler */
 #define SRT_OPT_TRAVERSAL 10     /* 0 auto (wide-leaf closest hit when the scene has <= 64 triangles), 1 force the LBVH walk
                                     (scene in shared memory), 3 force the LBVH walk with the scene in global memory */
 int srt_rm_set_option(srt_render_manager*, int option, int value);

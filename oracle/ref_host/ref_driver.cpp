@@ -308,6 +308,19 @@ void srt_ref_get_ray(unsigned int i, unsigned int j, unsigned int* rng, float* o
     for (int a = 0; a < 3; ++a) { out[a] = r.orig[a]; out[3 + a] = r.dir[a]; }
     for (int k = 0; k < 7; ++k) out[6 + k] = r.wavelengths[k];
 }
+// renderer::get_ray_stratified_sample (rendering/rendering.cu:89-118; never called by the reference's own kernel)
+void srt_ref_get_ray_stratified(unsigned int i, unsigned int j, unsigned int sx, unsigned int sy, float recip_sqrt_spp, unsigned int* rng, float* out) {
+    camera* c = g->sm->getCamPtr();
+    curandState s{};
+    s.d = rng[0];
+    for (int k = 0; k < 5; ++k) s.v[k] = rng[1 + k];
+    ray r = renderer::get_ray_stratified_sample(i, j, c->getPixel00Loc(), c->getPixelDeltaU(), c->getPixelDeltaV(), sx, sy, recip_sqrt_spp,
+                                                c->getCenter(), c->getDefocusAngle(), c->getDefocusDiskU(), c->getDefocusDiskV(), &s);
+    rng[0] = s.d;
+    for (int k = 0; k < 5; ++k) rng[1 + k] = s.v[k];
+    for (int a = 0; a < 3; ++a) { out[a] = r.orig[a]; out[3 + a] = r.dir[a]; }
+    for (int k = 0; k < 7; ++k) out[6 + k] = r.wavelengths[k];
+}
 // the sRGB -> reflectance table sampling of material::compute_spectral_distr for one colour
 void srt_ref_color_spectrum(float r, float gg, float b, int emissive, float power, float* out95) {
     material m = emissive ? material::emissive(color(r, gg, b), power) : material::lambertian(color(r, gg, b));

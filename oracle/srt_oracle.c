@@ -832,10 +832,18 @@ void srt_oracle_spectrum_to_xyz(const float wl[7], const float pw[7], int nvalid
 }
 
 /* ------------------------------------------------------------------ render (rendering/rendering.cu) */
-static oray get_ray(const ocam* c, uint32_t i, uint32_t j, rngc* s) { /* :66-87, :49-56, ray.cuh:27-58 */
+/* strat_n = 0: get_ray :66-87 (pixel_sample_square :49-56); strat_n > 0: get_ray_stratified_sample :89-118
+ * (pixel_stratified_sample_square :58-64) for sub-cell (sx, sy) of a strat_n x strat_n grid */
+static oray get_ray_s(const ocam* c, uint32_t i, uint32_t j, uint32_t sx, uint32_t sy, float recip_sqrt_spp, int strat, rngc* s) { /* ray.cuh:27-58 */
     ov3 pixel_center = vadd(vadd(c->p00, vscale((float)i, c->du)), vscale((float)j, c->dv));
-    float px = -0.5f + rnd(s);
-    float py = -0.5f + rnd(s);
+    float px, py;
+    if (strat) {
+        px = -0.5f + recip_sqrt_spp * ((float)sx + rnd(s));
+        py = -0.5f + recip_sqrt_spp * ((float)sy + rnd(s));
+    } else {
+        px = -0.5f + rnd(s);
+        py = -0.5f + rnd(s);
+    }
     ov3 pixel_sample = vadd(pixel_center, vadd(vscale(px, c->du), vscale(py, c->dv)));
     ov3 origin = c->center;
     if (!(c->defocus_angle <= 0.0f)) { /* defocus_disk_sample :42-47, random_in_unit_disk vec3.cuh:240-246 */
@@ -856,6 +864,7 @@ static oray get_ray(const ocam* c, uint32_t i, uint32_t j, rngc* s) { /* :66-87,
     r.valid = N_WL;
     return r;
 }
+static oray get_ray(const ocam* c, uint32_t i, uint32_t j, rngc* s) { return get_ray_s(c, i, j, 0, 0, 0.0f, 0, s); }
 static void ray_bounce(const oscene* sc, const float* bg, oray* r, int bounce_limit, rngc* s) { /* :12-40 */
     ohit rec;
     for (int n = 0; n < bounce_limit; n++) {
@@ -883,8 +892,20 @@ static void counters_add(ocounters* a, const ocounters* b) {
 
 int srt_oracle_render(const oscene* sc, const ocam* cam, int spp, int bounce_limit, int chunk_w, int chunk_h, float* rgb,
                       float* xyz, ocounters* counters, int nthreads) {
+    return srt_oracle_render_opts(sc, cam, spp, bounce_limit, chunk_w, chunk_h, 0, rgb, xyz, counters, nthreads);
+}
+int srt_oracle_render_opts(const oscene* sc, const ocam* cam, int spp, int bounce_limit, int chunk_w, int chunk_h, int stratified,
+                           float* rgb, float* xyz, ocounters* counters, int nthreads) {
     const int W = cam->w, H = cam->h;
     spp = (int)(unsigned short)spp;                   /* short_uint kernel parameters, rendering.cu:154 (Q14) */
+    /* opt-in stratified pixel sampling: the reference carries the sampler (rendering.cu:58-64, 89-118) but its kernel
+     * never calls it.  Sample k of a pixel takes sub-cell (k % n, k / n) of an n x n grid, n*n = spp (required). */
+    int strat_n = 0;
+    if (stratified) {
+        while ((strat_n + 1) * (strat_n + 1) <= spp) strat_n++;
+        if (strat_n * strat_n != spp) return -2;
+    }
+    const float recip_sqrt_spp = strat_n ? 1.0f / (float)strat_n : 0.0f;
     bounce_limit = (int)(unsigned short)bounce_limit;
     if (chunk_w <= 0 && chunk_h > 0) chunk_w = chunk_h; /* io/params.h:53-63 */
     if (chunk_h <= 0 && chunk_w > 0) chunk_h = chunk_w;
@@ -919,7 +940,8 @@ int srt_oracle_render(const oscene* sc, const ocam* cam, int spp, int bounce_lim
                     ov3 acc = V(0, 0, 0);
                     if (sc->valid) {
                         for (int k = 0; k < (int)(unsigned short)spp; k++) {
-                            oray r = get_ray(cam, (uint32_t)(off_x + i), (uint32_t)(off_y + j), &s);
+                            oray r = get_ray_s(cam, (uint32_t)(off_x + i), (uint32_t)(off_y + j), strat_n ? (uint32_t)(k % strat_n) : 0u,
+                                               strat_n ? (uint32_t)(k / strat_n) : 0u, recip_sqrt_spp, strat_n != 0, &s);
                             ray_bounce(sc, bg, &r, (int)(unsigned short)bounce_limit, &s);
                             ov3 c3 = spectrum_to_xyz(r.wl, r.pw, r.valid, s.c);
                             acc = vadd(acc, c3);
@@ -1058,6 +1080,19 @@ void srt_oracle_get_ray(const ocam* cam, uint32_t i, uint32_t j, uint32_t rng[6]
     st.r.d = rng[0];
     for (int k = 0; k < 5; k++) st.r.v[k] = rng[1 + k];
     oray r = get_ray(cam, i, j, &st);
+    rng[0] = st.r.d;
+    for (int k = 0; k < 5; k++) rng[1 + k] = st.r.v[k];
+    out[0] = r.o.x; out[1] = r.o.y; out[2] = r.o.z;
+    out[3] = r.d.x; out[4] = r.d.y; out[5] = r.d.z;
+    for (int k = 0; k < 7; k++) out[6 + k] = r.wl[k];
+}
+void srt_oracle_get_ray_stratified(const ocam* cam, uint32_t i, uint32_t j, uint32_t sx, uint32_t sy, float recip_sqrt_spp, uint32_t rng[6],
+                                   float out[13]) {
+    rngc st;
+    st.c = NULL;
+    st.r.d = rng[0];
+    for (int k = 0; k < 5; k++) st.r.v[k] = rng[1 + k];
+    oray r = get_ray_s(cam, i, j, sx, sy, recip_sqrt_spp, 1, &st);
     rng[0] = st.r.d;
     for (int k = 0; k < 5; k++) rng[1 + k] = st.r.v[k];
     out[0] = r.o.x; out[1] = r.o.y; out[2] = r.o.z;

@@ -100,6 +100,13 @@ void srt_oracle_color_spectrum(float r, float g, float b, int emissive, float po
 int srt_oracle_render(const oscene*, const ocam*, int spp, int bounce_limit, int chunk_w, int chunk_h,
                       float* rgb, float* xyz, ocounters* counters, int nthreads);
 
+/* same, with the opt-in stratified pixel sampler (rendering.cu:58-64, 89-118; dormant in the reference):
+ * sample k -> sub-cell (k % n, k / n), n*n == spp required (returns -2 otherwise) */
+int srt_oracle_render_opts(const oscene*, const ocam*, int spp, int bounce_limit, int chunk_w, int chunk_h, int stratified,
+                           float* rgb, float* xyz, ocounters* counters, int nthreads);
+void srt_oracle_get_ray_stratified(const ocam* cam, uint32_t i, uint32_t j, uint32_t sx, uint32_t sy, float recip_sqrt_spp,
+                                   uint32_t rng[6], float out[13]);
+
 /* render only the pixels whose (x/tile_w + 5*(y/tile_h)) % world == rank (multi-GPU
  * tile ownership test); other pixels are left zero.  Single full-image chunk. */
 int srt_oracle_render_tiles(const oscene*, const ocam*, int spp, int bounce_limit, int tile_w, int tile_h,

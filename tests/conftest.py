@@ -18,4 +18,4 @@ def golden():
     import numpy as np
 
     d = ROOT / "tests" / "golden"
-    return {name: np.load(d / (name + ".npz")) for name in ("ref_scene0", "ref_scene1", "ref_scene2", "ref_kat")}
+    return {name: np.load(d / (name + ".npz")) for name in ("ref_scene0", "ref_scene1", "ref_scene2", "ref_kat", "ref_stratified_kat")}

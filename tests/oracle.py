@@ -75,6 +75,8 @@ def lib():
         L.srt_oracle_brute_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.srt_oracle_scatter.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.srt_oracle_get_ray.argtypes = [C.POINTER(OCam), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.srt_oracle_get_ray_stratified.argtypes = [C.POINTER(OCam), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
+        L.srt_oracle_render_opts.argtypes = [C.c_void_p, C.POINTER(OCam)] + [C.c_int] * 5 + [C.c_void_p] * 3 + [C.c_int]
         L.srt_oracle_sellmeier.restype = C.c_float
         L.srt_oracle_sellmeier.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
         L.srt_oracle_spectrum_interp.restype = C.c_float
@@ -182,13 +184,15 @@ def camera_array(cam):
                     + v(cam.disk_u) + v(cam.disk_v), np.float32)
 
 
-def render(scene, cam, spp, bounce=10, chunk_w=0, chunk_h=0, counters=False, nthreads=0):
+def render(scene, cam, spp, bounce=10, chunk_w=0, chunk_h=0, counters=False, nthreads=0, stratified=False):
     n = cam.w * cam.h
     rgb = np.zeros(3 * n, np.float32)
     xyz = np.zeros(3 * n, np.float32)
     cnt = OCounters()
-    lib().srt_oracle_render(scene.h, C.byref(cam), spp, bounce, chunk_w, chunk_h, rgb.ctypes.data, xyz.ctypes.data,
-                            C.byref(cnt) if counters else None, nthreads)
+    rc = lib().srt_oracle_render_opts(scene.h, C.byref(cam), spp, bounce, chunk_w, chunk_h, 1 if stratified else 0, rgb.ctypes.data,
+                                      xyz.ctypes.data, C.cast(C.byref(cnt), C.c_void_p) if counters else None, nthreads)
+    if rc != 0:
+        raise ValueError("srt_oracle_render_opts failed: %d" % rc)
     out = (rgb.reshape(3, cam.h, cam.w), xyz.reshape(3, cam.h, cam.w))
     return out + (cnt.as_dict(),) if counters else out
 

@@ -98,6 +98,11 @@ class RefHost:
         self.lib.srt_ref_get_ray(C.c_uint(i), C.c_uint(j), rng.ctypes, out.ctypes)
         return out, rng
 
+    def get_ray_stratified(self, i, j, sx, sy, recip, rng):
+        rng = np.array(rng, np.uint32); out = np.zeros(13, np.float32)
+        self.lib.srt_ref_get_ray_stratified(C.c_uint(i), C.c_uint(j), C.c_uint(sx), C.c_uint(sy), C.c_float(recip), rng.ctypes, out.ctypes)
+        return out, rng
+
 
 def write_ppm(path, rgb):
     h, w = rgb.shape[1:]

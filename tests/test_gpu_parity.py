@@ -299,3 +299,22 @@ def test_against_the_reference_cuda_build(srt):
     assert abs(rgb.mean() - ref.mean()) / ref.mean() < 0.03
     box = lambda a: a[:, :224, :].reshape(3, 28, 8, 50, 8).mean((2, 4))  # 8x8 box filter
     assert np.abs(box(rgb) - box(ref)).mean() < 0.05 * box(ref).mean() + 0.5
+
+
+def test_stratified_sampler_matches_oracle(srt):
+    """opt-in stratified pixel sampler (rendering.cu:58-64,89-118): strict build == oracle bit for bit, both pipelines agree,
+    n = 1 equals the plain sampler, a non-square spp is refused"""
+    S = oracle.Scene(0)
+    cam = oracle.camera(96, 54)
+    _, want = oracle.render(S, cam, 9, 10, stratified=True)
+    got = srt.render(scene_id=0, w=96, h=54, spp=9, bounce=10, strict=True, stratified=True)
+    assert np.array_equal(got[1].view(np.uint32), want.view(np.uint32))
+    mega = srt.render(scene_id=0, w=96, h=54, spp=9, bounce=10, strict=True, stratified=True, pipeline=1)
+    assert np.array_equal(got[1].view(np.uint32), mega[1].view(np.uint32))
+    plain = srt.render(scene_id=0, w=96, h=54, spp=9, bounce=10, strict=True)
+    assert not np.array_equal(plain[1], got[1])
+    one_a = srt.render(scene_id=0, w=96, h=54, spp=1, bounce=10, strict=True, stratified=True)
+    one_b = srt.render(scene_id=0, w=96, h=54, spp=1, bounce=10, strict=True)
+    assert np.array_equal(one_a[1].view(np.uint32), one_b[1].view(np.uint32))
+    with pytest.raises(Exception):
+        srt.render(scene_id=0, w=96, h=54, spp=8, bounce=10, stratified=True)

@@ -143,6 +143,39 @@ def test_obj_loader_and_image_writers(srt, tmp_path):
     assert bmp[:2] == b"BM" and len(bmp) == 54 + 12 * 2
 
 
+def test_ply_loader(srt, tmp_path):
+    """ascii and binary_little_endian PLY give the same triangles as the equivalent OBJ (fan triangulation, extra
+    vertex properties and double coordinates skipped / converted); broken files are refused with a message"""
+    import struct
+
+    m = srt.MaterialDesc(type=srt.MAT_LAMBERTIAN, color=(0.5, 0.5, 0.5), fuzz=1.0)
+    obj = tmp_path / "q.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0.5\nv 0 1 0\nf 1 2 3 4\nf 2 3 4\n")
+    want = srt.Scene(obj=(obj, [m]), host_only=True).tris()[0]
+    a = tmp_path / "a.ply"
+    a.write_text("ply\nformat ascii 1.0\ncomment made by hand\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\n"
+                 "property uchar red\nelement face 2\nproperty list uchar int vertex_indices\nend_header\n"
+                 "0 0 0 255\n1 0 0 255\n1 1 0.5 0\n0 1 0 7\n4 0 1 2 3\n3 1 2 3\n")
+    sa = srt.Scene(ply=(a, [m]), host_only=True)
+    assert sa.ntris == 3 and np.array_equal(sa.tris()[0], want)
+    b = tmp_path / "b.ply"
+    hdr = ("ply\nformat binary_little_endian 1.0\nelement vertex 4\nproperty double x\nproperty double y\nproperty double z\n"
+           "element face 2\nproperty list uchar uint vertex_index\nend_header\n").encode()
+    body = b"".join(struct.pack("<3d", *v) for v in [(0, 0, 0), (1, 0, 0), (1, 1, 0.5), (0, 1, 0)])
+    body += struct.pack("<B4I", 4, 0, 1, 2, 3) + struct.pack("<B3I", 3, 1, 2, 3)
+    b.write_bytes(hdr + body)
+    sb = srt.Scene(ply=(b, [m]), host_only=True)
+    assert sb.ntris == 3 and np.array_equal(sb.tris()[0], want)
+    bad = tmp_path / "bad.ply"
+    bad.write_bytes(hdr + body[:40])
+    with pytest.raises(srt.SrtError):
+        srt.Scene(ply=(bad, [m]), host_only=True)
+    bad.write_text("ply\nformat ascii 1.0\nelement vertex 1\nproperty float x\nproperty float y\nproperty float z\nelement face 1\n"
+                   "property list uchar int vertex_indices\nend_header\n0 0 0\n3 0 1 2\n")
+    with pytest.raises(srt.SrtError):
+        srt.Scene(ply=(bad, [m]), host_only=True)
+
+
 GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, os.path.join(%(root)r, "tests"))

@@ -83,6 +83,34 @@ def test_ray_and_scatter_kats(golden, scene):
         assert np.array_equal(bits(out), bits(g["gr_out"][k]))
 
 
+def test_stratified_sampler_kat(golden):
+    """renderer::get_ray_stratified_sample (rendering.cu:89-118), dormant in the reference: the restatement must give the
+    reference's rays and leave the RNG in the reference's state, bit for bit."""
+    g = golden["ref_stratified_kat"]
+    cam = oracle.camera(400, 225)
+    for k in range(len(g["ij"])):
+        rng = g["rng_in"][k].copy()
+        out = np.zeros(13, np.float32)
+        oracle.lib().srt_oracle_get_ray_stratified(C.byref(cam), int(g["ij"][k, 0]), int(g["ij"][k, 1]), int(g["sxy"][k, 0]), int(g["sxy"][k, 1]),
+                                                   float(g["recip"][k]), rng.ctypes.data, out.ctypes.data)
+        assert np.array_equal(rng, g["rng_out"][k])
+        assert np.array_equal(bits(out), bits(g["out"][k]))
+
+
+def test_stratified_render_oracle():
+    """n = 1 stratification is the plain sampler (same draws, recip = 1, cell 0); non-square spp is refused"""
+    S = oracle.Scene(0)
+    cam = oracle.camera(48, 27)
+    a = oracle.render(S, cam, 1, 10)
+    b = oracle.render(S, cam, 1, 10, stratified=True)
+    assert np.array_equal(bits(a[1]), bits(b[1]))
+    c = oracle.render(S, cam, 4, 10)
+    d = oracle.render(S, cam, 4, 10, stratified=True)
+    assert not np.array_equal(c[1], d[1])
+    with pytest.raises(ValueError):
+        oracle.render(S, cam, 5, 10, stratified=True)
+
+
 def test_scalar_kats(golden):
     g = golden["ref_kat"]
     L = oracle.lib()
