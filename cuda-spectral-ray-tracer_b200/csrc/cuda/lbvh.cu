@@ -55,7 +55,7 @@ struct DeviceScene {
     SrtTri* tris_in = nullptr;    // n, original order
     SrtMaterial* mats = nullptr;
     // build products
-    float* leaf_boxes = nullptr;  // n x 6 (xmin xmax ymin ymax zmin zmax), original order
+    float4* leaf_boxes = nullptr;  // n x (lo.xyz -, hi.xyz -), original order: one 32-byte sector per leaf for the refit's gather
     float* centroids = nullptr;   // n x 3
     float* scene_box = nullptr;   // 6 floats (as ordered ints during the reduction)
     uint32_t* codes = nullptr;    // n, original order
@@ -89,12 +89,16 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
 
-__global__ void k_init_scene_box(uint32_t* box) {
-    if (threadIdx.x < 6) box[threadIdx.x] = (threadIdx.x & 1) ? f2ord(-INFINITY) : f2ord(INFINITY);
+// resets everything small the build accumulates into: scene box, digit histograms, the sort's tile tickets
+__global__ void k_reset_build(uint32_t* box, uint32_t* hist, uint32_t n_hist, uint32_t* tickets, uint32_t n_tickets) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 6) box[i] = (i & 1) ? f2ord(-INFINITY) : f2ord(INFINITY);
+    if (i < n_hist) hist[i] = 0;
+    if (i < n_tickets) tickets[i] = 0;
 }
 
 // leaf box (bvh/aabb.cuh:49-57 + pad :93-102), centroid (primitives/tri.cuh:73-77), scene box
-__global__ void __launch_bounds__(256) k_bounds(const float* __restrict__ verts, uint32_t n, float* __restrict__ leaf_boxes,
+__global__ void __launch_bounds__(256) k_bounds(const float* __restrict__ verts, uint32_t n, float4* __restrict__ leaf_boxes,
                                                 float* __restrict__ centroids, uint32_t* __restrict__ scene_box) {
     __shared__ uint32_t sbox[6];
     if (threadIdx.x < 6) sbox[threadIdx.x] = (threadIdx.x & 1) ? f2ord(-INFINITY) : f2ord(INFINITY);
@@ -105,6 +109,7 @@ __global__ void __launch_bounds__(256) k_bounds(const float* __restrict__ verts,
 #pragma unroll
         for (int k = 0; k < 9; k++) v[k] = verts[9ull * i + k];
         const float third = 1 / 3.f;
+        float bl[3], bh[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             float mn = fminf(v[a], fminf(v[3 + a], v[6 + a]));
@@ -114,12 +119,14 @@ __global__ void __launch_bounds__(256) k_bounds(const float* __restrict__ verts,
                 mn = mn - padding;
                 mx = mx + padding;
             }
-            leaf_boxes[6ull * i + 2 * a] = mn;
-            leaf_boxes[6ull * i + 2 * a + 1] = mx;
+            bl[a] = mn;
+            bh[a] = mx;
             centroids[3ull * i + a] = third * ((v[a] + v[3 + a]) + v[6 + a]);
             lo[a] = fminf(lo[a], mn);
             hi[a] = fmaxf(hi[a], mx);
         }
+        leaf_boxes[2ull * i] = make_float4(bl[0], bl[1], bl[2], 0.f);
+        leaf_boxes[2ull * i + 1] = make_float4(bh[0], bh[1], bh[2], 0.f);
     }
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(256) k_hierarchy(const uint32_t* __restrict__ 
 // the 64-byte traversal node right there.  Boxes travel as two 16-byte vectors (lo.xyz, hi.xyz).
 __device__ __forceinline__ float widen_lo(float v) { return v - fabsf(v) * 2.4e-7f; }
 __device__ __forceinline__ float widen_hi(float v) { return v + fabsf(v) * 2.4e-7f; }
-__global__ void __launch_bounds__(256) k_refit_emit(int n, const uint32_t* __restrict__ sorted_idx, const float* __restrict__ leaf_boxes,
+__global__ void __launch_bounds__(256) k_refit_emit(int n, const uint32_t* __restrict__ sorted_idx, const float4* __restrict__ leaf_boxes,
                                                     const int32_t* __restrict__ left, const int32_t* __restrict__ right,
                                                     const int32_t* __restrict__ parent, float4* node_box_lo, float4* node_box_hi, uint32_t* visit,
                                                     const SrtTri* __restrict__ tris_in, SrtNode* __restrict__ nodes, SrtTri* __restrict__ tris) {
@@ -365,8 +372,7 @@ __global__ void __launch_bounds__(256) k_refit_emit(int n, const uint32_t* __res
     if (k >= n) return;
     const uint32_t src = sorted_idx[k];
     tris[k] = tris_in[src];
-    float4 lo = make_float4(leaf_boxes[6ull * src], leaf_boxes[6ull * src + 2], leaf_boxes[6ull * src + 4], 0.f);
-    float4 hi = make_float4(leaf_boxes[6ull * src + 1], leaf_boxes[6ull * src + 3], leaf_boxes[6ull * src + 5], 0.f);
+    float4 lo = leaf_boxes[2ull * src], hi = leaf_boxes[2ull * src + 1];
     int from = n - 1 + k;
     node_box_lo[from] = lo;
     node_box_hi[from] = hi;
@@ -427,7 +433,7 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
         packed[i] = tris[i].pack(mt, prio[i]);
     }
     s->tiles = (n + SORT_TILE - 1) / SORT_TILE;
-    bool ok = dalloc(s->verts, 9ull * n) && dalloc(s->tris_in, n) && dalloc(s->mats, mats.size()) && dalloc(s->leaf_boxes, 6ull * n) &&
+    bool ok = dalloc(s->verts, 9ull * n) && dalloc(s->tris_in, n) && dalloc(s->mats, mats.size()) && dalloc(s->leaf_boxes, 2ull * n) &&
               dalloc(s->centroids, 3ull * n) && dalloc(s->scene_box, 6) && dalloc(s->codes, n) && dalloc(s->keys[0], n) && dalloc(s->keys[1], n) &&
               dalloc(s->vals[0], n) && dalloc(s->vals[1], n) && dalloc(s->hist, SORT_PASSES * RADIX) &&
               dalloc(s->lookback, (size_t)SORT_PASSES * (s->tiles ? s->tiles : 1) * RADIX) && dalloc(s->tile_counter, SORT_PASSES) &&
@@ -482,16 +488,15 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
     const int sms = sm_count();
     const int grid_stride = (int)min((uint32_t)(sms * 8), (n + 255) / 256);
     const int grid_n = (int)((n + 255) / 256);
-    for (int rep = 0; rep < repeats; rep++) {
-        cudaStream_t st = s->stream;
-        SRT_CUDA(cudaEventRecord(s->ev[0], st));
-        k_init_scene_box<<<1, 32, 0, st>>>((uint32_t*)s->scene_box);
+    cudaStream_t st = s->stream;
+    // every launch of one build.  (Replaying the sequence as a CUDA graph was measured: 0.362 -> 0.359 ms at 1M triangles,
+    // the launches already queue back to back, so the plain stream stays.)
+    auto enqueue = [&]() -> bool {
+        k_reset_build<<<(SORT_PASSES * RADIX + 255) / 256, 256, 0, st>>>((uint32_t*)s->scene_box, s->hist, SORT_PASSES * RADIX, s->tile_counter, SORT_PASSES);
+        SRT_CUDA(cudaMemsetAsync(s->lookback, 0, (size_t)SORT_PASSES * s->tiles * RADIX * sizeof(uint32_t), st));
+        SRT_CUDA(cudaMemsetAsync(s->visit, 0, n * sizeof(uint32_t), st));
         k_bounds<<<grid_stride, 256, 0, st>>>(s->verts, n, s->leaf_boxes, s->centroids, (uint32_t*)s->scene_box);
         k_decode_scene_box<<<1, 32, 0, st>>>((uint32_t*)s->scene_box);
-        SRT_CUDA(cudaMemsetAsync(s->hist, 0, SORT_PASSES * RADIX * sizeof(uint32_t), st));
-        SRT_CUDA(cudaMemsetAsync(s->lookback, 0, (size_t)SORT_PASSES * s->tiles * RADIX * sizeof(uint32_t), st));
-        SRT_CUDA(cudaMemsetAsync(s->tile_counter, 0, SORT_PASSES * sizeof(uint32_t), st));
-        SRT_CUDA(cudaMemsetAsync(s->visit, 0, n * sizeof(uint32_t), st));
         k_morton_hist<<<grid_stride, 256, 0, st>>>(s->centroids, s->scene_box, n, s->codes, s->keys[0], s->vals[0], s->hist);
         SRT_CUDA(cudaEventRecord(s->ev[1], st));
         k_scan_hist<<<1, RADIX, 0, st>>>(s->hist);
@@ -505,8 +510,13 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
         SRT_CUDA(cudaEventRecord(s->ev[3], st));
         k_refit_emit<<<grid_n, 256, 0, st>>>((int)n, s->vals[0], s->leaf_boxes, s->left, s->right, s->parent, s->node_box_lo, s->node_box_hi, s->visit,
                                              s->tris_in, s->nodes, s->tris);
+        return true;
+    };
+    for (int rep = 0; rep < repeats; rep++) {
+        SRT_CUDA(cudaEventRecord(s->ev[0], st));
+        if (!enqueue()) return false;
         SRT_CUDA(cudaEventRecord(s->ev[4], st));
-        count_launch(6 + SORT_PASSES + (n > 1 ? 1 : 0));
+        count_launch(4 + SORT_PASSES + (n > 1 ? 1 : 0));
         SRT_CUDA_LAST();
     }
     SRT_CUDA(cudaEventSynchronize(s->ev[4]));
