@@ -228,12 +228,9 @@ def main():
                 self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
         film = torch.as_tensor(_Film(rm.device_film(), 3 * w * h), device="cuda")
 
-    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # 2x the 126 MB L2
-
     def one_step():
         """returns device milliseconds of this rank (render kernels [+ film reduce])"""
-        l2_flush.zero_()  # untimed: evicts the previous step's film / RNG / path state from L2
-        torch.cuda.synchronize()
+        S.lib().srt_measure_copy_gbs(256)  # untimed 256 MB device copy (2x + 2x the 126 MB L2): evicts the previous step's film / RNG / path state
         rm.restart()
         while rm.step():
             pass
@@ -413,7 +410,7 @@ def main():
         "config": {"workload": wl_name, "scene": scene_id, "width": w, "height": h, "spp": spp, "depth": depth,
                    "fp_mode": "strict(-fmad=false)" if a.strict else "fast(fma, as the reference's nvcc build)",
                    "parallelism": "image tiles (auto size) interleaved over %d ranks + nccl film reduce" % world if world > 1 else "single gpu",
-                   "l2": "flushed before every step (256 MB device memset, untimed); film, RNG and path state are re-initialised every step"},
+                   "l2": "flushed before every step (untimed 256 MB device-to-device copy); film, RNG and path state are re-initialised every step"},
         "clocks": clocks,
         "e2e": {"value": total_samples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches),

@@ -101,6 +101,8 @@ struct DeviceRenderer {
     uint32_t* d_tiles = nullptr;
     std::vector<uint32_t> h_tiles;  // chunk-local tiles this rank owns
     unsigned long long* d_rays = nullptr;
+    void* d_state = nullptr;        // in-flight path records (R0 R1 P0 P1 L0 L1 carved out of one block)
+    size_t state_bytes = 0;
     unsigned char* d_rgb = nullptr; // resolve staging (device), 3 byte planes of one chunk
     unsigned char* h_stage = nullptr;  // pinned: 3 byte planes of one chunk, or 3 float planes of the whole film (get_xyz)
     cudaStream_t stream = nullptr;
@@ -149,7 +151,7 @@ void collect_kernel_times(DeviceRenderer* r) {
 void device_renderer_destroy(DeviceRenderer* r) {
     if (!r) return;
     device_pool_free(r->d_cie); device_pool_free(r->d_bg); device_pool_free(r->d_tiles); device_pool_free(r->d_rays); device_pool_free(r->d_rgb);
-    device_pool_free(r->P.R0); device_pool_free(r->P.R1); device_pool_free(r->P.P0); device_pool_free(r->P.P1); device_pool_free(r->P.L0); device_pool_free(r->P.L1); device_pool_free(r->P.G0); device_pool_free(r->P.G1); device_pool_free(r->P.next_slot); device_pool_free(r->P.acc);
+    device_pool_free(r->d_state); device_pool_free(r->P.G0); device_pool_free(r->P.G1); device_pool_free(r->P.next_slot); device_pool_free(r->P.acc);
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
@@ -265,13 +267,32 @@ static bool renderer_setup(DeviceRenderer* r) {
         resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.block_threads, r->smem + P.queue_bytes));
     }
     r->wave_grid = (int)std::min<uint64_t>(resident, ((uint64_t)P.nslots + P.block_slots - 1) / P.block_slots);
-    const size_t nrec = std::max<size_t>(1, (size_t)std::max(1, r->wave_grid) * P.block_slots);
-    if (!device_pool_alloc((void**)&P.R0, nrec * sizeof(float4))) return false;
-    if (!device_pool_alloc((void**)&P.R1, nrec * sizeof(float4))) return false;
-    if (!device_pool_alloc((void**)&P.P0, nrec * sizeof(float4))) return false;
-    if (!device_pool_alloc((void**)&P.P1, nrec * sizeof(float4))) return false;
-    if (!device_pool_alloc((void**)&P.L0, nrec * sizeof(uint4))) return false;
-    if (!device_pool_alloc((void**)&P.L1, nrec * sizeof(uint2))) return false;
+    // state of the paths in flight: ONE allocation (88 B per record, six arrays) so that a single L2 access-policy
+    // window can keep it resident -- it is rewritten every pass for the whole launch and never needs to reach DRAM
+    const size_t nrec = (std::max<size_t>(1, (size_t)std::max(1, r->wave_grid) * P.block_slots) + 15) & ~(size_t)15;
+    r->state_bytes = nrec * 88;
+    if (!device_pool_alloc((void**)&r->d_state, r->state_bytes)) return false;
+    unsigned char* sb = (unsigned char*)r->d_state;
+    P.R0 = (float4*)sb; P.R1 = (float4*)(sb + nrec * 16); P.P0 = (float4*)(sb + nrec * 32); P.P1 = (float4*)(sb + nrec * 48);
+    P.L0 = (uint4*)(sb + nrec * 64); P.L1 = (uint2*)(sb + nrec * 80);
+    {
+        int dev = 0, max_persist = 0, max_window = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        if (max_persist > 0 && max_window > 0) {
+            const size_t persist = std::min<size_t>((size_t)max_persist, r->state_bytes);
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = r->d_state;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)max_window, r->state_bytes);
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)av.accessPolicyWindow.num_bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) != cudaSuccess ||
+                cudaStreamSetAttribute(r->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess)
+                cudaGetLastError();  // a hint only: rendering does not depend on it
+        }
+    }
     SRT_CUDA(cudaStreamSynchronize(r->stream));
     return true;
 }
