@@ -152,6 +152,7 @@ void device_renderer_destroy(DeviceRenderer* r) {
     if (!r) return;
     device_pool_free(r->d_cie); device_pool_free(r->d_bg); device_pool_free(r->d_tiles); device_pool_free(r->d_rays); device_pool_free(r->d_rgb);
     device_pool_free(r->d_state); device_pool_free(r->P.G0); device_pool_free(r->P.G1); device_pool_free(r->P.next_slot); device_pool_free(r->P.acc);
+    if (r->d_state) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }  // hand the pinned L2 lines back
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
