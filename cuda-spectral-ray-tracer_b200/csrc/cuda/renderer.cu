@@ -372,21 +372,24 @@ bool device_renderer_resolve(DeviceRenderer* r, unsigned off_x, unsigned off_y, 
     SRT_CUDA(cudaStreamSynchronize(r->stream));
     float* dst[3] = {fr, fg, fb};
     const unsigned char* stage = r->h_stage;
-    auto widen = [&](int c) {  // frame_buffer holds 0..255 as float (frame_buffer.cuh:6-44)
-        if (!dst[c]) return;
-        for (unsigned y = 0; y < h; y++) {
-            const unsigned char* src = stage + c * n + (size_t)y * w;
-            float* o = dst[c] + (size_t)(off_y + y) * img_w + off_x;
-            for (unsigned x = 0; x < w; x++) o[x] = (float)src[x];
+    auto widen = [&](unsigned y0, unsigned y1) {  // frame_buffer holds 0..255 as float (frame_buffer.cuh:6-44)
+        for (int c = 0; c < 3; c++) {
+            if (!dst[c]) continue;
+            for (unsigned y = y0; y < y1; y++) {
+                const unsigned char* src = stage + c * n + (size_t)y * w;
+                float* o = dst[c] + (size_t)(off_y + y) * img_w + off_x;
+                for (unsigned x = 0; x < w; x++) o[x] = (float)src[x];
+            }
         }
     };
-    if (n >= (1u << 18)) {  // big chunks: one host thread per colour plane
-        std::thread tg(widen, 1), tb(widen, 2);
-        widen(0);
-        tg.join();
-        tb.join();
+    if (n >= (1u << 18)) {  // big chunks: the 4x wider float planes are written by several host threads, one band of rows each
+        const unsigned nt = std::max(1u, std::min({8u, std::thread::hardware_concurrency(), h}));
+        std::vector<std::thread> pool;
+        for (unsigned k = 1; k < nt; k++) pool.emplace_back(widen, (unsigned)((uint64_t)h * k / nt), (unsigned)((uint64_t)h * (k + 1) / nt));
+        widen(0, h / nt);
+        for (std::thread& th : pool) th.join();
     } else {
-        for (int c = 0; c < 3; c++) widen(c);
+        widen(0, h);
     }
     return true;
 }

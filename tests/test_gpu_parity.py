@@ -318,3 +318,13 @@ def test_stratified_sampler_matches_oracle(srt):
     assert np.array_equal(one_a[1].view(np.uint32), one_b[1].view(np.uint32))
     with pytest.raises(Exception):
         srt.render(scene_id=0, w=96, h=54, spp=8, bounce=10, stratified=True)
+
+
+def test_paths_in_flight_do_not_change_the_film(srt):
+    """the number of paths a wavefront block keeps in flight and its thread count only change the schedule: every pixel
+    still consumes its own RNG stream in order, so the film is bit-identical (chunked render with an odd image size, so
+    edge tiles, refetches and the RNG carry-over between chunks are all on the path)"""
+    base = srt.render(scene_id=1, w=203, h=117, spp=5, bounce=10, chunk=(96, 64), strict=True)
+    for kw in (dict(block_slots=32), dict(block_slots=256, block_threads=128), dict(block_slots=4096), dict(block_slots=512, block_threads=64)):
+        other = srt.render(scene_id=1, w=203, h=117, spp=5, bounce=10, chunk=(96, 64), strict=True, **kw)
+        assert np.array_equal(base[1].view(np.uint32), other[1].view(np.uint32)), kw
