@@ -6,8 +6,8 @@
 
 Metric (BASELINE.json): spectral path samples/s.  One "step" = one full render of the workload.
 Workload at every N: BASELINE.json configs[1] -- reference Cornell scene (id 0), 1920x1080, 64 spp,
-depth 10 -- split over the ranks by interleaved 32x32 image tiles (strong scaling), per-rank XYZ films
-summed with one NCCL reduce to rank 0 which tonemaps.
+depth 10 -- split over the ranks by interleaved image tiles (strong scaling), per-rank XYZ films
+summed with one NCCL reduce to rank 0 which tonemaps.  L2 is flushed before every timed step.
 
   value      samples / device time, scene + state resident in HBM (CUDA events inside libsrt around
              the render kernels; at N>1 plus the NCCL film reduce; max over ranks)
@@ -18,6 +18,9 @@ summed with one NCCL reduce to rank 0 which tonemaps.
              SURVEY.md 8d) / its CUDA-event duration against the FP32 issue peak measured in this run
   cpu_baseline  the reference's own host-compiled code (oracle/_ref) or the C port (oracle/), timed on the
              box's host cores on a bounded sample of the same workload
+  c5         extra, same N GPUs: BASELINE configs[4] (Cornell 3840x2160, 1024 spp), 1 warm-up + 2 timed steps
+  reference_cuda / strict_fp / lbvh   (N=1) the reference's CUDA renderer on this GPU, our -fmad=false kernels,
+             the 1M-triangle LBVH build and soup ray queries with their rooflines
 """
 import argparse
 import json
@@ -181,6 +184,7 @@ def main():
     ap.add_argument("--tile-h", type=int, default=0)
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the extra BASELINE configs[4] measurement (4K, 1024 spp)")
     a = ap.parse_args()
     # torchrun exports OMP_NUM_THREADS=1; the CPU reference legs must use every host core (the OpenMP
     # runtime reads the variable when the oracle library is loaded, which happens later)
@@ -275,6 +279,46 @@ def main():
         rm.resolve_film()
     total_samples = w * h * spp
     value = total_samples / (step_ms * 1e-3)
+
+    # ---- BASELINE configs[4] next to the headline: Cornell 3840x2160, 1024 spp on the same N GPUs (device time incl.
+    # the film reduce, max over ranks).  Its per-pixel chains are 16x longer than C2's, so it shows how the tile split
+    # scales when the end-of-kernel drain is amortised; 1 warm-up + 2 timed steps keep it to seconds.
+    c5_info = None
+    if wl_name == "c2" and not a.no_c5 and not a.strict:
+        s5, w5, h5, spp5, d5 = WORKLOADS["c5"]
+        sc5 = S.Scene(s5)
+        fb5 = S.FrameBuffer(w5, h5)
+        rm5 = S.RenderManager(sc5, sc5.camera(w5, h5), fb5)
+        rm5.init_renderer(d5, spp5)
+        rm5.set_option(S.OPT_TILE_W, a.tile_w); rm5.set_option(S.OPT_TILE_H, a.tile_h)
+        if world > 1:
+            rm5.set_option(S.OPT_RANK, rank); rm5.set_option(S.OPT_WORLD, world)
+        rm5.init_device_params(0, 0)
+        film5 = torch.as_tensor(_Film(rm5.device_film(), 3 * w5 * h5), device="cuda") if world > 1 else None
+        ms5 = []
+        for i in range(3):
+            S.lib().srt_measure_copy_gbs(256)
+            rm5.restart()
+            while rm5.step():
+                pass
+            ms = rm5.stats()["render_ms"]
+            if world > 1:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                dist.reduce(film5, dst=0, op=dist.ReduceOp.SUM)
+                e1.record()
+                e1.synchronize()
+                ms += e0.elapsed_time(e1)
+            if i >= 1:
+                ms5.append(ms)
+        m5 = float(np.mean(ms5))
+        if world > 1:
+            tmax = torch.tensor([m5], device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            m5 = float(tmax.item())
+        c5_info = {"workload": "c5", "width": w5, "height": h5, "spp": spp5, "depth": d5, "value": w5 * h5 * spp5 / (m5 * 1e-3), "unit": UNIT,
+                   "ms_per_step": m5, "steps": 2, "warmup": 1, "what": "BASELINE configs[4] on the same GPUs, device time incl. the film reduce, max over ranks"}
+        del rm5, sc5, film5, fb5
 
     # ---- the same resident-state measurement in strict FP mode (-fmad=false kernels: the mode whose film is
     # bit-identical to the reference's host-compiled image); reported next to the headline, single GPU only
@@ -415,7 +459,7 @@ def main():
         "e2e": {"value": total_samples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "cpu_baseline": cpu_base,
+        "cpu_baseline": cpu_base, "c5": c5_info,
         "reference_cuda": ref_cuda,
         "strict_fp": strict_info,
         "lbvh": lb,
