@@ -517,8 +517,17 @@ static int tri_hit(const otri* t, const oray* r, float mn, float mx, ohit* rec, 
 static int node_hit(const oscene* s, int n, const oray* r, float mn, float mx, ohit* rec, ocounters* c) { /* bvh.cu:73-76 */
     return s->nodes[n].is_leaf ? tri_hit(&s->tris[s->nodes[n].prim], r, mn, mx, rec, c) : aabb_hit(s->nodes[n].bb, r, mn, mx, c);
 }
+static int g_debug_brute = 0; /* srt_oracle_debug_pixel only: closest hit over ALL triangles instead of the reference's pruned walk */
 static int bvh_hit(const oscene* s, const oray* r, float mn, float mx, ohit* rec, ocounters* c) { /* bvh.cu:98-166 */
     if (!s->valid) return 0;
+    if (g_debug_brute) {
+        int h = 0;
+        float cl = mx;
+        ohit tmp;
+        for (int i = 0; i < s->ntris; i++)
+            if (tri_hit(&s->tris[i], r, mn, cl, &tmp, NULL)) { h = 1; cl = tmp.t; *rec = tmp; }
+        return h;
+    }
     if (c) c->rays++;
     int hit_anything = 0;
     float closest = mx;
@@ -1098,6 +1107,26 @@ void srt_oracle_get_ray_stratified(const ocam* cam, uint32_t i, uint32_t j, uint
     out[0] = r.o.x; out[1] = r.o.y; out[2] = r.o.z;
     out[3] = r.d.x; out[4] = r.d.y; out[5] = r.d.z;
     for (int k = 0; k < 7; k++) out[6 + k] = r.wl[k];
+}
+/* debugging aid for parity investigations: XYZ of every sample of ONE pixel of a single-chunk render, either through the
+ * reference's BVH walk (brute = 0) or with a closest hit over all triangles (brute = 1; not thread safe) */
+int srt_oracle_debug_pixel(const oscene* sc, const ocam* cam, int spp, int bounce_limit, int i, int j, int brute, float* xyz_per_sample) {
+    const uint32_t tx = 28, ty = 16, gx = (uint32_t)cam->w / tx + 1;
+    const uint32_t idx = ((uint32_t)j % ty) * tx + ((uint32_t)i % tx) + tx * ty * (((uint32_t)j / ty) * gx + (uint32_t)i / tx);
+    rngc s;
+    s.c = NULL;
+    srt_oracle_rng_init(1984u + idx, &s.r);
+    float bg[NS];
+    background_spectrum(cam->background, bg);
+    g_debug_brute = brute;
+    for (int k = 0; k < spp; k++) {
+        oray r = get_ray(cam, (uint32_t)i, (uint32_t)j, &s);
+        ray_bounce(sc, bg, &r, bounce_limit, &s);
+        ov3 c3 = spectrum_to_xyz(r.wl, r.pw, r.valid, NULL);
+        xyz_per_sample[3 * k] = c3.x; xyz_per_sample[3 * k + 1] = c3.y; xyz_per_sample[3 * k + 2] = c3.z;
+    }
+    g_debug_brute = 0;
+    return 0;
 }
 /* the reference sorts its tri* array in place while building (bvh.cu:262); order[k] = original
  * index of the triangle that ends up at position k of that array */

@@ -107,6 +107,10 @@ int srt_oracle_render_opts(const oscene*, const ocam*, int spp, int bounce_limit
 void srt_oracle_get_ray_stratified(const ocam* cam, uint32_t i, uint32_t j, uint32_t sx, uint32_t sy, float recip_sqrt_spp,
                                    uint32_t rng[6], float out[13]);
 
+/* parity debugging: per-sample XYZ (3*spp floats) of one pixel of a single-chunk render; brute = 1 replaces the reference's
+ * pruned BVH walk by a closest hit over all triangles */
+int srt_oracle_debug_pixel(const oscene*, const ocam*, int spp, int bounce_limit, int i, int j, int brute, float* xyz_per_sample);
+
 /* render only the pixels whose (x/tile_w + 5*(y/tile_h)) % world == rank (multi-GPU
  * tile ownership test); other pixels are left zero.  Single full-image chunk. */
 int srt_oracle_render_tiles(const oscene*, const ocam*, int spp, int bounce_limit, int tile_w, int tile_h,

@@ -77,6 +77,7 @@ def lib():
         L.srt_oracle_get_ray.argtypes = [C.POINTER(OCam), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.srt_oracle_get_ray_stratified.argtypes = [C.POINTER(OCam), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
         L.srt_oracle_render_opts.argtypes = [C.c_void_p, C.POINTER(OCam)] + [C.c_int] * 5 + [C.c_void_p] * 3 + [C.c_int]
+        L.srt_oracle_debug_pixel.argtypes = [C.c_void_p, C.POINTER(OCam), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.srt_oracle_sellmeier.restype = C.c_float
         L.srt_oracle_sellmeier.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
         L.srt_oracle_spectrum_interp.restype = C.c_float

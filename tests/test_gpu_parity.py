@@ -11,6 +11,8 @@ Tolerances (grounded in measurements there):
   * image means: within 1 % of the oracle's mean XYZ.
   * wavefront vs megakernel pipeline, same FP mode: bit-identical films.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -328,3 +330,29 @@ def test_paths_in_flight_do_not_change_the_film(srt):
     for kw in (dict(block_slots=32), dict(block_slots=256, block_threads=128), dict(block_slots=4096), dict(block_slots=512, block_threads=64)):
         other = srt.render(scene_id=1, w=203, h=117, spp=5, bounce=10, chunk=(96, 64), strict=True, **kw)
         assert np.array_equal(base[1].view(np.uint32), other[1].view(np.uint32)), kw
+
+
+def test_full_bench_size_bitwise_vs_oracle(srt):
+    """The whole bench workload (BASELINE configs[1]: Cornell 1920x1080, 64 spp, depth 10; 435 M rays) in strict FP mode
+    against the CPU oracle (which equals the real reference host build on this frame bit for bit, checked in the
+    authoring container).  Measured: 1 pixel of 2 073 600 differs -- one sample path of 1.3e8 whose hit triangle the
+    reference's own AABB pruning culls by rounding (bvh/aabb.cu:7-39, `mx <= mn` on a 1e-4 thick box); the oracle's
+    srt_oracle_debug_pixel(brute=1), a closest hit over all triangles, reproduces the GPU value exactly.
+    Tolerance: at most 10 pixels (5e-6 of the image) may differ in their XYZ bits."""
+    w, h, spp = 1920, 1080, 64
+    rgb, xyz, st = srt.render(scene_id=0, w=w, h=h, spp=spp, bounce=10, strict=True)
+    _, oxyz = oracle.render(oracle.Scene(0), oracle.camera(w, h), spp, 10)
+    diff = (xyz.view(np.uint32) != oxyz.view(np.uint32)).any(axis=0)
+    print("full-size strict vs oracle: %d of %d pixels differ" % (int(diff.sum()), w * h))
+    assert int(diff.sum()) <= 10
+    ys, xs = np.nonzero(diff)
+    S = oracle.Scene(0)
+    cam = oracle.camera(w, h)
+    for x, y in zip(xs.tolist(), ys.tolist()):  # every differing pixel must be explained by the reference's pruning artefact
+        per_sample = np.zeros(3 * spp, np.float32)
+        oracle.lib().srt_oracle_debug_pixel(C.c_void_p(S.h), C.byref(cam), spp, 10, x, y, 1, C.c_void_p(per_sample.ctypes.data))
+        acc = np.zeros(3, np.float32)
+        for k in range(spp):
+            acc = (acc + per_sample[3 * k:3 * k + 3]).astype(np.float32)
+        want = (np.float32(1.0) / np.float32(spp)) * acc
+        assert np.array_equal(want.view(np.uint32), xyz[:, y, x].view(np.uint32)), (x, y)
