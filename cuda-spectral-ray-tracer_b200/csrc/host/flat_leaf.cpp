@@ -70,8 +70,18 @@ bool build_flat_leaf(const std::vector<HostTri>& tris, const std::vector<HostMat
         if (partner[i] < 0 || partner[i] > i) units++;
     if (units > 32) return false;
     const double O1 = origin_l1_bound;
-    for (int i = 0; i < n; i++) {
-        if (partner[i] >= 0 && partner[i] < i) continue;
+    // Unit order = the order phase 2 runs the exact tests in.  Small things first (light, box faces), big walls last:
+    // a ray that pierces an inner object and the wall behind it then finds the near hit first, and the wall's exact test
+    // ends at its `t <= closest` check instead of running to the end.  The result does not depend on the order.
+    std::vector<int> heads;
+    for (int i = 0; i < n; i++)
+        if (partner[i] < 0 || partner[i] > i) heads.push_back(i);
+    auto area2 = [&](int i) {
+        const D3 a = dv(tris[i].v[0]), c = cross(sub(dv(tris[i].v[1]), a), sub(dv(tris[i].v[2]), a));
+        return dot(c, c);
+    };
+    std::stable_sort(heads.begin(), heads.end(), [&](int a, int b) { return area2(a) < area2(b); });
+    for (int i : heads) {
         const HostTri& T = tris[i];
         const Frame f = frame_of(T);
         SrtFlatUnit u{};
