@@ -18,7 +18,8 @@ summed with one NCCL reduce to rank 0 which tonemaps.  L2 is flushed before ever
              SURVEY.md 8d) / its CUDA-event duration against the FP32 issue peak measured in this run
   cpu_baseline  the reference's own host-compiled code (oracle/_ref) or the C port (oracle/), timed on the
              box's host cores on a bounded sample of the same workload
-  c5         extra, same N GPUs: BASELINE configs[4] (Cornell 3840x2160, 1024 spp), 1 warm-up + 2 timed steps
+  c5, soup   extra, same N GPUs: BASELINE configs[4] (Cornell 3840x2160, 1024 spp) and whole renders of the
+             1M-triangle soup of configs[3] (1920x1080, 8 spp); 1 warm-up + 2 timed steps each
   reference_cuda / strict_fp / lbvh   (N=1) the reference's CUDA renderer on this GPU, our -fmad=false kernels,
              the 1M-triangle LBVH build and soup ray queries with their rooflines
 """
@@ -283,42 +284,55 @@ def main():
     # ---- BASELINE configs[4] next to the headline: Cornell 3840x2160, 1024 spp on the same N GPUs (device time incl.
     # the film reduce, max over ranks).  Its per-pixel chains are 16x longer than C2's, so it shows how the tile split
     # scales when the end-of-kernel drain is amortised; 1 warm-up + 2 timed steps keep it to seconds.
-    c5_info = None
-    if wl_name == "c2" and not a.no_c5 and not a.strict:
-        s5, w5, h5, spp5, d5 = WORKLOADS["c5"]
-        sc5 = S.Scene(s5)
-        fb5 = S.FrameBuffer(w5, h5)
-        rm5 = S.RenderManager(sc5, sc5.camera(w5, h5), fb5)
-        rm5.init_renderer(d5, spp5)
-        rm5.set_option(S.OPT_TILE_W, a.tile_w); rm5.set_option(S.OPT_TILE_H, a.tile_h)
+    def resident_leg(scene_obj, w_, h_, spp_, d_, warm=1, steps=2):
+        """device ms per step (render [+ film reduce], max over ranks) of one more workload on the same N GPUs"""
+        fb_ = S.FrameBuffer(w_, h_)
+        rm_ = S.RenderManager(scene_obj, scene_obj.camera(w_, h_), fb_)
+        rm_.init_renderer(d_, spp_)
+        rm_.set_option(S.OPT_TILE_W, a.tile_w); rm_.set_option(S.OPT_TILE_H, a.tile_h)
         if world > 1:
-            rm5.set_option(S.OPT_RANK, rank); rm5.set_option(S.OPT_WORLD, world)
-        rm5.init_device_params(0, 0)
-        film5 = torch.as_tensor(_Film(rm5.device_film(), 3 * w5 * h5), device="cuda") if world > 1 else None
-        ms5 = []
-        for i in range(3):
+            rm_.set_option(S.OPT_RANK, rank); rm_.set_option(S.OPT_WORLD, world)
+        rm_.init_device_params(0, 0)
+        film_ = torch.as_tensor(_Film(rm_.device_film(), 3 * w_ * h_), device="cuda") if world > 1 else None
+        ms_ = []
+        for i in range(warm + steps):
             S.lib().srt_measure_copy_gbs(256)
-            rm5.restart()
-            while rm5.step():
+            rm_.restart()
+            while rm_.step():
                 pass
-            ms = rm5.stats()["render_ms"]
+            ms = rm_.stats()["render_ms"]
             if world > 1:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-                dist.reduce(film5, dst=0, op=dist.ReduceOp.SUM)
+                dist.reduce(film_, dst=0, op=dist.ReduceOp.SUM)
                 e1.record()
                 e1.synchronize()
                 ms += e0.elapsed_time(e1)
-            if i >= 1:
-                ms5.append(ms)
-        m5 = float(np.mean(ms5))
+            if i >= warm:
+                ms_.append(ms)
+        m = float(np.mean(ms_))
+        rays_per_sample = rm_.stats()["rays"] / max(1, rm_.stats()["samples"])
         if world > 1:
-            tmax = torch.tensor([m5], device="cuda")
+            tmax = torch.tensor([m], device="cuda")
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            m5 = float(tmax.item())
+            m = float(tmax.item())
+        del rm_, film_, fb_
+        return m, rays_per_sample
+
+    c5_info = None
+    soup_info = None
+    if wl_name == "c2" and not a.no_c5 and not a.strict:
+        s5, w5, h5, spp5, d5 = WORKLOADS["c5"]
+        m5, _ = resident_leg(S.Scene(s5), w5, h5, spp5, d5)
         c5_info = {"workload": "c5", "width": w5, "height": h5, "spp": spp5, "depth": d5, "value": w5 * h5 * spp5 / (m5 * 1e-3), "unit": UNIT,
                    "ms_per_step": m5, "steps": 2, "warmup": 1, "what": "BASELINE configs[4] on the same GPUs, device time incl. the film reduce, max over ranks"}
-        del rm5, sc5, film5, fb5
+        # BASELINE configs[3] as a render: the seeded 1M-triangle soup (LBVH walk from global memory), 1920x1080, 8 spp
+        soup_sc = S.Scene(soup=1 << 20, seed=1984)
+        ms_s, rps = resident_leg(soup_sc, 1920, 1080, 8, 10)
+        soup_info = {"workload": "c4-render", "n_tris": 1 << 20, "generator": "SplitMix64 seed 1984 (srt_scene_create_soup)", "width": 1920, "height": 1080, "spp": 8,
+                     "depth": 10, "value": 1920 * 1080 * 8 / (ms_s * 1e-3), "unit": UNIT, "rays_per_s": 1920 * 1080 * 8 * rps / (ms_s * 1e-3),
+                     "ms_per_step": ms_s, "steps": 2, "warmup": 1, "what": "whole renders of the 1M-triangle soup on the same GPUs (every rank holds the full LBVH)"}
+        del soup_sc
 
     # ---- the same resident-state measurement in strict FP mode (-fmad=false kernels: the mode whose film is
     # bit-identical to the reference's host-compiled image); reported next to the headline, single GPU only
@@ -459,7 +473,7 @@ def main():
         "e2e": {"value": total_samples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "cpu_baseline": cpu_base, "c5": c5_info,
+        "cpu_baseline": cpu_base, "c5": c5_info, "soup": soup_info,
         "reference_cuda": ref_cuda,
         "strict_fp": strict_info,
         "lbvh": lb,
