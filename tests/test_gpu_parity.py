@@ -12,11 +12,14 @@ Tolerances (grounded in measurements there):
   * wavefront vs megakernel pipeline, same FP mode: bit-identical films.
 """
 import ctypes as C
+import pathlib
 
 import numpy as np
 import pytest
 
 import oracle
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
 
 pytestmark = pytest.mark.gpu
 
@@ -356,3 +359,24 @@ def test_full_bench_size_bitwise_vs_oracle(srt):
             acc = (acc + per_sample[3 * k:3 * k + 3]).astype(np.float32)
         want = (np.float32(1.0) / np.float32(spp)) * acc
         assert np.array_equal(want.view(np.uint32), xyz[:, y, x].view(np.uint32)), (x, y)
+
+
+def test_cli_drop_in(srt, tmp_path):
+    """srt_cli: the reference's flags (io/params.h:236-304) plus the extensions; --save writes renders/<title>.bmp/.ppm like
+    main.cpp:113-118, --xyz dumps the raw film, and the picture equals the library's own render of the same arguments"""
+    import subprocess
+
+    exe = ROOT / "cuda-spectral-ray-tracer_b200" / "srt_cli"
+    assert exe.exists(), "srt_cli was not built"
+    xyz_file = tmp_path / "film.f32"
+    out = subprocess.run([str(exe), "-s", "1", "-xr", "96", "-ar", "16/9", "-ns", "4", "-bl", "10", "-t", "Cli Test", "--no-show", "--save", "--do-log", "--strict-fp",
+                          "--xyz", str(xyz_file)], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stdout[-1000:] + out.stderr[-1000:]
+    assert "World created" in out.stdout and "Scene ID: 1" in out.stdout
+    assert (tmp_path / "renders" / "cli_test.bmp").exists() and (tmp_path / "renders" / "cli_test.ppm").exists()
+    assert list((tmp_path / "logs").glob("*_cli_test_log.txt"))
+    film = np.fromfile(xyz_file, np.float32).reshape(3, 54, 96)
+    _, want, _ = srt.render(scene_id=1, w=96, h=54, spp=4, bounce=10, strict=True)
+    assert np.array_equal(film.view(np.uint32), want.view(np.uint32))
+    bad = subprocess.run([str(exe), "-s", "0", "-xr", "64", "-ns", "5", "--no-show", "--stratified"], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert bad.returncode != 0 and "square" in (bad.stdout + bad.stderr)

@@ -176,6 +176,32 @@ def test_ply_loader(srt, tmp_path):
         srt.Scene(ply=(bad, [m]), host_only=True)
 
 
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver times next to ours) runs on the host alone and prints ONE JSON line
+    with the contract's keys; under a multi-rank launch only rank 0 prints"""
+    import json
+    import subprocess
+
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-spp", "1", "--workload", "c1"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "impl", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in j, key
+    assert j["impl"] == "reference" and j["value"] > 0 and j["unit"] == "samples/s" and j["config"]["workload"] == "c1"
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "c1"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+
+
 GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, os.path.join(%(root)r, "tests"))
