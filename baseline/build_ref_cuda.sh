@@ -11,8 +11,10 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${SRT_REFERENCE_DIR:-/root/reference}"
 OUT="$HERE/_ref"
-if [[ ! -d "$REF" ]]; then echo "build_ref_cuda.sh: $REF not present -- keeping prebuilt baseline/_ref" >&2; exit 0; fi
 mkdir -p "$OUT"
+# library sort next to our onesweep (timing context only); needs no reference sources
+nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -w "$HERE/cub_sort_main.cu" -o "$OUT/cub_sort_bench"
+if [[ ! -d "$REF" ]]; then echo "build_ref_cuda.sh: $REF not present -- keeping prebuilt baseline/_ref" >&2; exit 0; fi
 STAGE="$(mktemp -d /tmp/srt_refcuda_stage.XXXXXX)"
 trap 'rm -rf "$STAGE"' EXIT
 for d in materials primitives bvh utils rendering refraction color spectrum ray math io scene _log_; do cp -r "$REF/$d" "$STAGE/$d"; done

@@ -432,7 +432,16 @@ def main():
         ms = [soup.rebuild_lbvh(1)["total"] for _ in range(10)]
         t = float(np.median(ms))
         ach = 256.0 * (1 << 20) / (t * 1e-3) / 1e9
-        lb = {"n_tris": 1 << 20, "build_ms": t, "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+        phases = soup.rebuild_lbvh(1)
+        cub = None
+        exe = ROOT / "baseline" / "_ref" / "cub_sort_bench"
+        if exe.exists():  # library sort of the same pairs, timing context only
+            try:
+                out = subprocess.run([str(exe), str(1 << 20), "20"], capture_output=True, text=True, timeout=120).stdout
+                cub = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
+            except Exception as e:  # pragma: no cover
+                cub = {"error": str(e)}
+        lb = {"n_tris": 1 << 20, "build_ms": t, "phases_ms": phases, "sort_baseline_cub": cub, "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                                                               "peak_source": hbm_src, "algorithmic_bytes_per_tri": 256}}
         # BASELINE.json configs[3]: closest-hit rays/s through the device LBVH of the same soup
         # (primary = the reference camera at 1920x1080, secondary = one random bounce off the primary hits)
