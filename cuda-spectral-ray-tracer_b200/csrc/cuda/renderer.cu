@@ -4,6 +4,7 @@
 #include "cuda_common.cuh"
 #include "trace_params.h"
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <cmath>
 #include <vector>
@@ -89,6 +90,8 @@ static float* pinned_staging(size_t bytes) {
     return buf;
 }
 
+static std::atomic<int> g_l2_windows{0};
+
 struct DeviceRenderer {
     const DeviceScene* scene = nullptr;
     RenderConfig cfg;
@@ -101,6 +104,7 @@ struct DeviceRenderer {
     uint32_t* d_tiles = nullptr;
     std::vector<uint32_t> h_tiles;  // chunk-local tiles this rank owns
     unsigned long long* d_rays = nullptr;
+    bool l2_window = false;         // this renderer holds a persisting-L2 window (set-aside released with the last one)
     void* d_state = nullptr;        // in-flight path records (R0 R1 P0 P1 L0 L1 carved out of one block)
     size_t state_bytes = 0;
     unsigned char* d_rgb = nullptr; // resolve staging (device), 3 byte planes of one chunk
@@ -152,7 +156,11 @@ void device_renderer_destroy(DeviceRenderer* r) {
     if (!r) return;
     device_pool_free(r->d_cie); device_pool_free(r->d_bg); device_pool_free(r->d_tiles); device_pool_free(r->d_rays); device_pool_free(r->d_rgb);
     device_pool_free(r->d_state); device_pool_free(r->P.G0); device_pool_free(r->P.G1); device_pool_free(r->P.next_slot); device_pool_free(r->P.acc);
-    if (r->d_state) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }  // hand the pinned L2 lines back
+    if (r->l2_window) {  // hand the pinned L2 lines back; the last renderer also returns the set-aside to the normal cache
+        cudaCtxResetPersistingL2Cache();
+        if (--g_l2_windows == 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+        cudaGetLastError();
+    }
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
@@ -292,6 +300,7 @@ static bool renderer_setup(DeviceRenderer* r) {
             if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) != cudaSuccess ||
                 cudaStreamSetAttribute(r->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess)
                 cudaGetLastError();  // a hint only: rendering does not depend on it
+            else { r->l2_window = true; ++g_l2_windows; }
         }
     }
     SRT_CUDA(cudaStreamSynchronize(r->stream));
