@@ -191,6 +191,10 @@ static bool renderer_setup(DeviceRenderer* r) {
         set_error("tile width and height must be powers of two with an area in [32, 65536]");
         return false;
     }
+    if (c.chunk_w > 65535u || c.chunk_h > 65535u) {  // a pixel's chunk coordinates travel as y << 16 | x
+        set_error("chunks larger than 65535 pixels in one dimension are not supported");
+        return false;
+    }
     for (P.tile_slots_log2 = 0; (1u << P.tile_slots_log2) < tile_slots; P.tile_slots_log2++) {}
     for (P.tile_w_log2 = 0; (1u << P.tile_w_log2) < P.tile_w; P.tile_w_log2++) {}
     device_scene_bounds(r->scene, P.scene_lo, P.scene_hi);
@@ -264,14 +268,14 @@ static bool renderer_setup(DeviceRenderer* r) {
     // (4 per thread); a rank with few pixels takes fewer paths per block so that every SM still gets work
     uint32_t resident = 0;
     for (P.block_slots = 1024;; P.block_slots >>= 1) {
-        P.queue_bytes = (22u * P.block_slots + 15u) & ~15u;  // queues [2][4][S] u16 | pixel slot [S] u32 | samples started [S] u16
+        P.queue_bytes = (28u * P.block_slots + 15u) & ~15u;  // queues [2][4][S] u16 | pixel slot [S] u32 | samples started [S] u16 (padded to 4 B) | pixel xy [S] u32
         SRT_CUDA(T.configure(r->smem + P.queue_bytes));
         resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.block_threads, r->smem + P.queue_bytes));
         if (P.block_slots <= P.block_threads || (uint64_t)resident * P.block_slots <= (uint64_t)P.nslots) break;
     }
     if (c.block_slots >= 32 && c.block_slots <= 4096 && !(c.block_slots & (c.block_slots - 1))) {
         P.block_slots = (uint32_t)c.block_slots;
-        P.queue_bytes = (22u * P.block_slots + 15u) & ~15u;
+        P.queue_bytes = (28u * P.block_slots + 15u) & ~15u;
         SRT_CUDA(T.configure(r->smem + P.queue_bytes));
         resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.block_threads, r->smem + P.queue_bytes));
     }

@@ -639,6 +639,7 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
     uint16_t* qbuf = reinterpret_cast<uint16_t*>(smem);                        // [2][4][S] queues of local slot ids
     uint32_t* pslot = reinterpret_cast<uint32_t*>(smem + 16u * S);             // [S] pixel slot a local slot renders
     uint16_t* started = reinterpret_cast<uint16_t*>(smem + 20u * S);           // [S] samples started of that pixel
+    uint32_t* pxy = reinterpret_cast<uint32_t*>(smem + 24u * S);               // [S] that pixel's chunk coordinates, y << 16 | x
     __shared__ int cnt[2][4];
     __shared__ int next_chunk;
     const SceneRef sc = load_scene<SMEM, FLAT>(P, smem + P.queue_bytes);
@@ -700,6 +701,7 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
                         else if (slot_owned(P, cand, ci, cj)) {  // edge tiles stick out of the chunk: such a slot asks again next pass
                             slot = cand;
                             pslot[l] = slot;
+                            pxy[l] = (cj << 16) | ci;  // tile look-up and divisions once per pixel, not once per pass
                             s = 0;
                             rng = load_rng(P.G0, P.G1, slot);
                         }
@@ -707,7 +709,8 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
                 }
                 if (have && slot != SRT_NO_SLOT) {
                     if (!fetch) {
-                        slot_pixel(P, slot, ci, cj);
+                        const uint32_t xy = pxy[l];
+                        ci = xy & 0xFFFFu; cj = xy >> 16;
                         rng = load_rng(P.L0, P.L1, rec);
                     }
                     pix = (size_t)(P.off_y + cj) * P.img_w + (P.off_x + ci);
@@ -719,7 +722,8 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
                     }
                 }
             } else if (have) {  // scatter at the stored hit (warp-uniform material)
-                slot_pixel(P, slot, ci, cj);
+                const uint32_t xy = pxy[l];
+                ci = xy & 0xFFFFu; cj = xy >> 16;
                 pix = (size_t)(P.off_y + cj) * P.img_w + (P.off_x + ci);
                 rng = load_rng(P.L0, P.L1, rec);
                 load_hit_state(P, rec, p, tri);
