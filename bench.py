@@ -7,7 +7,7 @@
 Metric (BASELINE.json): spectral path samples/s.  One "step" = one full render of the workload.
 Workload at every N: BASELINE.json configs[1] -- reference Cornell scene (id 0), 1920x1080, 64 spp,
 depth 10 -- split over the ranks by interleaved image tiles (strong scaling), per-rank XYZ films
-summed with one NCCL all-reduce (in-switch reduction on NVSwitch); rank 0 tonemaps.  L2 is flushed before every timed step.
+summed with one NCCL reduce to rank 0 which tonemaps.  L2 is flushed before every timed step.
 
   value      samples / device time, scene + state resident in HBM (CUDA events inside libsrt around
              the render kernels; at N>1 plus the NCCL film reduce; max over ranks)
@@ -244,7 +244,7 @@ def main():
         if world > 1:
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            dist.all_reduce(film, op=dist.ReduceOp.SUM)  # NVLS in-switch reduction: 0.14 ms for the 1080p film at 8 GPUs vs 0.27 ms for reduce->0
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
             e1.record()
             e1.synchronize()
             ms += e0.elapsed_time(e1)
@@ -304,7 +304,7 @@ def main():
             if world > 1:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-                dist.all_reduce(film_, op=dist.ReduceOp.SUM)
+                dist.reduce(film_, dst=0, op=dist.ReduceOp.SUM)
                 e1.record()
                 e1.synchronize()
                 ms += e0.elapsed_time(e1)
@@ -370,7 +370,7 @@ def main():
             while rm2.step():
                 pass
             f2 = torch.as_tensor(_Film(rm2.device_film(), 3 * w * h), device="cuda")
-            dist.all_reduce(f2, op=dist.ReduceOp.SUM)
+            dist.reduce(f2, dst=0, op=dist.ReduceOp.SUM)
             torch.cuda.synchronize()
             if rank == 0:
                 rm2.resolve_film()
@@ -477,7 +477,7 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl_name, "scene": scene_id, "width": w, "height": h, "spp": spp, "depth": depth,
                    "fp_mode": "strict(-fmad=false)" if a.strict else "fast(fma, as the reference's nvcc build)",
-                   "parallelism": "image tiles (auto size) interleaved over %d ranks + nccl film all-reduce" % world if world > 1 else "single gpu",
+                   "parallelism": "image tiles (auto size) interleaved over %d ranks + nccl film reduce" % world if world > 1 else "single gpu",
                    "l2": "flushed before every step (untimed 256 MB device-to-device copy); film, RNG and path state are re-initialised every step"},
         "clocks": clocks,
         "e2e": {"value": total_samples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
