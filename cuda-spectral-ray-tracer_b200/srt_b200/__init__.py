@@ -338,8 +338,8 @@ class RenderManager:
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
 
-def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=False, pipeline=0, scene=None, tiles=None, regen_loop=None,
-           kernel_timing=False, tail_threshold=None, traversal=None, block_slots=None, block_threads=None, stratified=False):
+def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=False, pipeline=0, scene=None, tiles=None,
+           kernel_timing=False, traversal=None, block_slots=None, block_threads=None, stratified=False):
     """One-call helper: returns (rgb[3,h,w] float32 0..255, xyz[3,h,w] float32, stats dict)."""
     sc = scene if scene is not None else Scene(scene_id)
     cam = sc.camera(w, h)
@@ -348,12 +348,8 @@ def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=Fals
     rm.init_renderer(bounce, spp)
     rm.set_option(OPT_FP_MODE, 1 if strict else 0)
     rm.set_option(OPT_PIPELINE, pipeline)
-    if regen_loop is not None:
-        rm.set_option(OPT_REGEN_LOOP, regen_loop)
     if kernel_timing:
         rm.set_option(OPT_KERNEL_TIMING, 1)
-    if tail_threshold is not None:
-        rm.set_option(OPT_TAIL_THRESHOLD, tail_threshold)
     if traversal is not None:
         rm.set_option(OPT_TRAVERSAL, traversal)
     if block_threads is not None:

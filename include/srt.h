@@ -175,7 +175,7 @@ int srt_rm_render_all(srt_render_manager*);
 /* additions needed for grading / multi-GPU (no reference counterpart) */
 #define SRT_OPT_FP_MODE 1      /* 0 = fast (FMA contraction, like the reference's nvcc build), 1 = strict (-fmad=false, matches the host oracle) */
 #define SRT_OPT_PIPELINE 2     /* 0 = wavefront (default), 1 = per-pixel persistent megakernel */
-#define SRT_OPT_TILE_W 3       /* image tile rendered by one wavefront block and unit of multi-GPU ownership (default 0 = automatic: 32x32, 32x16 or 16x16 by pixels per rank) */
+#define SRT_OPT_TILE_W 3       /* image tile: the unit of multi-GPU ownership and of pixel numbering (powers of two; default 0 = automatic: 32x32, 32x16 or 16x16 by pixels per rank) */
 #define SRT_OPT_TILE_H 4
 #define SRT_OPT_RANK 5         /* ... this process renders the tiles with (tile_x + 5 tile_y) % world == rank */
 #define SRT_OPT_WORLD 6

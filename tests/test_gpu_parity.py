@@ -107,7 +107,7 @@ def test_c1_image_fast(srt, scene, golden):
 def test_pipelines_bit_identical(srt, strict):
     a = srt.render(scene_id=0, w=200, h=112, spp=6, bounce=10, strict=strict, pipeline=0)
     b = srt.render(scene_id=0, w=200, h=112, spp=6, bounce=10, strict=strict, pipeline=1)
-    c = srt.render(scene_id=0, w=200, h=112, spp=6, bounce=10, strict=strict, pipeline=0, regen_loop=1)
+    c = srt.render(scene_id=0, w=200, h=112, spp=6, bounce=10, strict=strict, pipeline=0, block_slots=64)
     assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
     assert np.array_equal(a[1].view(np.uint32), c[1].view(np.uint32))
     assert np.array_equal(a[0], b[0])

@@ -31,8 +31,6 @@ for v in a.variants.split(","):
     elif v == "strict": run("wavefront strict", pipeline=0, strict=True)
     elif v == "bvh": run("wavefront lbvh-walk smem", pipeline=0, traversal=1)
     elif v == "bvhg": run("wavefront lbvh-walk global", pipeline=0, traversal=3)
-    elif v.startswith("bs"): run("wavefront tile 32x%d" % (int(v[2:]) // 32), pipeline=0, block_slots=int(v[2:]))
+    elif v.startswith("bs"): run("wavefront %s paths per block" % v[2:], pipeline=0, block_slots=int(v[2:]))
     elif v.startswith("tile"):
         tw, th = v[4:].split("x"); run("wavefront tile %sx%s" % (tw, th), pipeline=0, tiles=(int(tw), int(th), 0, 1))
-    elif v.startswith("tail"): run("wavefront tail=%s" % v[4:], pipeline=0, tail_threshold=int(v[4:]))
-    elif v.startswith("regen"): run("wavefront regen=%s" % v[5:], pipeline=0, regen_loop=int(v[5:]))
