@@ -30,7 +30,7 @@ struct WaveParams {
     uint32_t off_x, off_y, cw, ch;   // current chunk (pixels)
     uint32_t img_w, img_h;
     uint32_t nslots;                 // pixel slots of this rank: n_tiles * tile_w * tile_h
-    const uint32_t* tiles;           // chunk-local tile ids owned by this rank (tile_id % world == rank)
+    const uint32_t* tiles;           // chunk-local tile ids owned by this rank ((tx + 5 ty) % world == rank)
     uint32_t n_tiles;
     uint32_t ref_grid_x;             // nominal_chunk_w / 28 + 1 (reference launch geometry -> seeds)
     uint32_t spp, bounce_limit;
