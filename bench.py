@@ -267,7 +267,7 @@ def main():
     for _ in range(a.steps):
         ms, st = one_step()
         dev_ms.append(ms)
-        kern_ms.append(st["shade_ms"] if st["shade_ms"] > 0 else st["render_ms"])
+        kern_ms.append(st["wavefront_ms"] if st["wavefront_ms"] > 0 else st["render_ms"])
     launches = S.kernel_launch_count() - launches_timed0
     barrier()
     clocks = sampler.summary() if sampler else None

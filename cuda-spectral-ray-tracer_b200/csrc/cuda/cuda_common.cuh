@@ -12,6 +12,11 @@ bool cuda_ok(cudaError_t e, const char* what, const char* file, int line);
 // process-wide cache of device buffers (renderer.cu): a freed block is handed to the next request of a similar size
 bool device_pool_alloc(void** out, size_t bytes);
 void device_pool_free(void* p);
+// cost-ordered pixel slot lists for the wavefront renderer's rounds (lbvh.cu, next to the radix sort it reuses)
+struct PixelOrder;
+PixelOrder* pixel_order_create(uint32_t max_slots);
+void pixel_order_destroy(PixelOrder*);
+const uint32_t* pixel_order_build(PixelOrder*, const uint32_t* cost, uint32_t n, uint32_t samples, cudaStream_t st);
 }  // namespace srt
 
 #define SRT_CUDA(call)                                                   \

@@ -186,9 +186,9 @@ __global__ void __launch_bounds__(256) k_morton_hist(const float* __restrict__ c
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 // exclusive scan of each pass' 256 digit counts (one block, one warp-scan per 32 digits)
-__global__ void k_scan_hist(uint32_t* hist) {
+__global__ void k_scan_hist(uint32_t* hist, int rows) {
     __shared__ uint32_t warp_tot[RADIX / 32];
-    for (int p = 0; p < SORT_PASSES; p++) {
+    for (int p = 0; p < rows; p++) {
         const uint32_t v = hist[p * RADIX + threadIdx.x];
         uint32_t inc = v;
 #pragma unroll
@@ -318,6 +318,66 @@ __global__ void __launch_bounds__(SORT_THREADS) k_onesweep(const uint32_t* __res
         keys_out[dst] = k;
         vals_out[dst] = s_vals[j];
     }
+}
+
+// ---- pixel order of the wavefront renderer (renderer.cu) -------------------------------------
+// Between two rounds of samples the renderer re-orders the pixel slots of a chunk so that the pixels
+// with the most passes per sample so far are handed out first (longest processing time first): the
+// end of the launch then consists of the cheapest pixels and the persistent blocks drain together.
+// One stable onesweep pass over an 8-bit key: 254 - min(254, 23 * passes / samples) for rendered
+// slots (1 pass per sample -> 231, 11 -> 1), 255 for slots nobody rendered (tile overhang; they sort
+// behind the n_order owned slots and are never read).  Stable, so equal-cost neighbours stay neighbours.
+__global__ void __launch_bounds__(256) k_cost_keys(const uint32_t* __restrict__ cost, uint32_t n, uint32_t samples, uint32_t* __restrict__ keys,
+                                                   uint32_t* __restrict__ vals, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[RADIX];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = cost[i];
+        const uint32_t key = c ? 254u - min(254u, (uint32_t)(((unsigned long long)c * 23u) / samples)) : 255u;
+        keys[i] = key;
+        vals[i] = i;
+        atomicAdd(&sh[key], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+struct PixelOrder {
+    uint32_t cap = 0, tiles = 0;
+    uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+    uint32_t* small = nullptr;  // hist[RADIX] | tile ticket | lookback[tiles * RADIX]
+};
+PixelOrder* pixel_order_create(uint32_t max_slots) {
+    auto* o = new PixelOrder();
+    o->cap = max_slots ? max_slots : 1;
+    o->tiles = (o->cap + SORT_TILE - 1) / SORT_TILE;
+    bool ok = true;
+    for (int k = 0; k < 2; k++) ok = ok && device_pool_alloc((void**)&o->keys[k], o->cap * sizeof(uint32_t)) && device_pool_alloc((void**)&o->vals[k], o->cap * sizeof(uint32_t));
+    ok = ok && device_pool_alloc((void**)&o->small, ((size_t)RADIX + 64 + (size_t)o->tiles * RADIX) * sizeof(uint32_t));
+    if (!ok) { pixel_order_destroy(o); return nullptr; }
+    return o;
+}
+void pixel_order_destroy(PixelOrder* o) {
+    if (!o) return;
+    for (int k = 0; k < 2; k++) { device_pool_free(o->keys[k]); device_pool_free(o->vals[k]); }
+    device_pool_free(o->small);
+    delete o;
+}
+// enqueues the sort on `st`; the returned device array (n entries, owned slots first) is valid until the next call
+const uint32_t* pixel_order_build(PixelOrder* o, const uint32_t* cost, uint32_t n, uint32_t samples, cudaStream_t st) {
+    if (!o || n == 0 || n > o->cap || samples == 0) return nullptr;
+    const uint32_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    uint32_t* hist = o->small;
+    uint32_t* ticket = o->small + RADIX;
+    uint32_t* lookback = o->small + RADIX + 64;
+    if (cudaMemsetAsync(o->small, 0, ((size_t)RADIX + 64 + (size_t)tiles * RADIX) * sizeof(uint32_t), st) != cudaSuccess) return nullptr;
+    const int grid = (int)min((uint32_t)(148 * 8), (n + 255) / 256);
+    k_cost_keys<<<grid, 256, 0, st>>>(cost, n, samples, o->keys[0], o->vals[0], hist);
+    k_scan_hist<<<1, RADIX, 0, st>>>(hist, 1);
+    k_onesweep<<<tiles, SORT_THREADS, 0, st>>>(o->keys[0], o->vals[0], o->keys[1], o->vals[1], n, 0, hist, lookback, ticket);
+    count_launch(3);
+    return o->vals[1];
 }
 
 // ---- hierarchy ------------------------------------------------------------------------------
@@ -499,7 +559,7 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
         k_decode_scene_box<<<1, 32, 0, st>>>((uint32_t*)s->scene_box);
         k_morton_hist<<<grid_stride, 256, 0, st>>>(s->centroids, s->scene_box, n, s->codes, s->keys[0], s->vals[0], s->hist);
         SRT_CUDA(cudaEventRecord(s->ev[1], st));
-        k_scan_hist<<<1, RADIX, 0, st>>>(s->hist);
+        k_scan_hist<<<1, RADIX, 0, st>>>(s->hist, SORT_PASSES);
         for (int p = 0; p < SORT_PASSES; p++) {
             k_onesweep<<<s->tiles, SORT_THREADS, 0, st>>>(s->keys[p & 1], s->vals[p & 1], s->keys[(p + 1) & 1], s->vals[(p + 1) & 1], n, p * RADIX_BITS,
                                                          s->hist + p * RADIX, s->lookback + (size_t)p * s->tiles * RADIX, s->tile_counter + p);

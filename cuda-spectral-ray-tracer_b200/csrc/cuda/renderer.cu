@@ -1,5 +1,6 @@
-// Host side of the device renderer: per-slot state and queues in HBM, the wavefront iteration
-// loop, film resolve, and the standalone ray-query entry.  Replaces the reference's renderer
+// Host side of the device renderer: per-pixel RNG state, the state of the paths in flight and the
+// film in HBM; the rounds of k_wavefront launches that render a chunk (with the cost-ordered pixel
+// lists between them); film resolve; and the standalone ray-query entry.  Replaces the reference's renderer
 // class (rendering/rendering.cuh:39-155, rendering.cu:244-357).
 #include "cuda_common.cuh"
 #include "trace_params.h"
@@ -26,6 +27,8 @@ uint32_t device_scene_nmats(const DeviceScene* s);
 const uint32_t* device_scene_sorted_idx(const DeviceScene* s);
 
 namespace {
+constexpr int kMaxRounds = 8;
+constexpr size_t kMinOrderedSlots = 8192;  // chunks with fewer pixel slots are rendered in slot order (the sort would cost more than it saves)
 const LaunchTable& table(int strict) {
     static LaunchTable fast = fastfp::make_launch_table();
     static LaunchTable strict_t = strictfp_::make_launch_table();
@@ -104,6 +107,11 @@ struct DeviceRenderer {
     uint32_t* d_tiles = nullptr;
     std::vector<uint32_t> h_tiles;  // chunk-local tiles this rank owns
     unsigned long long* d_rays = nullptr;
+    uint32_t* d_cost = nullptr;          // per pixel slot: passes spent so far in the current chunk (rounds > 1)
+    PixelOrder* order = nullptr;         // sort scratch + the ordered slot list of the current round
+    uint4* d_pass_log = nullptr;
+    unsigned long long* d_drain = nullptr;  // kMaxRounds x {first slot retired, last block exit} globaltimer stamps
+    std::vector<uint32_t> round_end;     // sample index where each round of a chunk ends (last = spp)
     bool l2_window = false;         // this renderer holds a persisting-L2 window (set-aside released with the last one)
     void* d_state = nullptr;        // in-flight path records (R0 R1 P0 P1 L0 L1 carved out of one block)
     size_t state_bytes = 0;
@@ -113,10 +121,10 @@ struct DeviceRenderer {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // stats
     uint64_t launches = 0, iterations = 0, samples = 0, rays = 0;
-    double render_ms = 0;
+    double render_ms = 0, drain_ms = 0;
     bool slots_inited = false;
     size_t chunk_px = 0;
-    // optional per-kernel timing: event pairs tagged with a category (0 generate, 1 shade, 2 tail, 3 other)
+    // optional per-kernel timing: event pairs tagged with a category (0 pixel order, 1 k_wavefront, 2 k_megakernel, 3 other)
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_tag;
     size_t ev_used = 0;
@@ -155,6 +163,8 @@ void collect_kernel_times(DeviceRenderer* r) {
 void device_renderer_destroy(DeviceRenderer* r) {
     if (!r) return;
     device_pool_free(r->d_cie); device_pool_free(r->d_bg); device_pool_free(r->d_tiles); device_pool_free(r->d_rays); device_pool_free(r->d_rgb);
+    device_pool_free(r->d_pass_log);
+    device_pool_free(r->d_cost); device_pool_free(r->d_drain); pixel_order_destroy(r->order);
     device_pool_free(r->d_state); device_pool_free(r->P.G0); device_pool_free(r->P.G1); device_pool_free(r->P.next_slot); device_pool_free(r->P.acc);
     if (r->l2_window) {  // hand the pinned L2 lines back; the last renderer also returns the set-aside to the normal cache
         cudaCtxResetPersistingL2Cache();
@@ -220,8 +230,17 @@ static bool renderer_setup(DeviceRenderer* r) {
         }
         P.strat_recip = 1.0f / (float)P.strat_n;
     }
+    P.s_begin = 0; P.s_end = P.spp; P.order = nullptr; P.n_order = 0; P.cost = nullptr; P.drain_clock = nullptr;
     P.plane = (size_t)P.img_w * P.img_h;
     const size_t ns = std::max<size_t>(P.nslots, 1);
+    P.pass_log = nullptr;
+    if (c.pass_log) {
+        if (!device_pool_alloc((void**)&r->d_pass_log, (size_t)SRT_PASS_LOG_BLOCKS * SRT_PASS_LOG_PASSES * sizeof(uint4))) return false;
+        P.pass_log = r->d_pass_log;
+    }
+    if (c.kernel_timing) {
+        if (!device_pool_alloc((void**)&r->d_drain, 2 * kMaxRounds * sizeof(unsigned long long))) return false;
+    }
     if (!device_pool_alloc((void**)&r->d_tiles, std::max<size_t>(1, r->h_tiles.size()) * sizeof(uint32_t))) return false;
     if (!r->h_tiles.empty()) SRT_CUDA(cudaMemcpy(r->d_tiles, r->h_tiles.data(), r->h_tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     P.tiles = r->d_tiles;
@@ -280,6 +299,29 @@ static bool renderer_setup(DeviceRenderer* r) {
         resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.block_threads, r->smem + P.queue_bytes));
     }
     r->wave_grid = (int)std::min<uint64_t>(resident, ((uint64_t)P.nslots + P.block_slots - 1) / P.block_slots);
+    // rounds of samples: K launches per chunk that render samples [0,b1) [b1,b2) ... [b_{K-1},spp), each 8x longer than
+    // the one before.  The first round hands the pixels out by a first guess of their cost (k_prior_cost), the later
+    // ones by the passes they really took.  Automatic choice (measured, tools/drain_probe.py): a second round pays when
+    // the per-pixel chains are long (>= 128 spp) or when a path slot renders several pixels in a row.
+    {
+        int K = c.rounds;
+        if (K <= 0) {
+            const double generations = (double)P.nslots / std::max<double>(1.0, (double)r->wave_grid * P.block_slots);
+            K = (P.spp >= 128 || (P.spp >= 16 && generations >= 2.5)) ? 2 : 1;
+        }
+        K = std::min(K, kMaxRounds);
+        if (c.pipeline == 1) K = 1;
+        for (int i = 1; i < K; i++) {
+            const uint32_t b = P.spp >> (3 * (K - i));
+            if (b > 0 && (r->round_end.empty() || b > r->round_end.back())) r->round_end.push_back(b);
+        }
+        r->round_end.push_back(P.spp);
+    }
+    if (c.pipeline != 1 && (r->round_end.size() > 1 || ns >= kMinOrderedSlots)) {
+        if (!device_pool_alloc((void**)&r->d_cost, ns * sizeof(uint32_t))) return false;
+        r->order = pixel_order_create((uint32_t)ns);
+        if (!r->order) return false;
+    }
     // state of the paths in flight: ONE allocation (88 B per record, six arrays) so that a single L2 access-policy
     // window can keep it resident -- it is rewritten every pass for the whole launch and never needs to reach DRAM
     const size_t nrec = (std::max<size_t>(1, (size_t)std::max(1, r->wave_grid) * P.block_slots) + 15) & ~(size_t)15;
@@ -293,7 +335,7 @@ static bool renderer_setup(DeviceRenderer* r) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        if (max_persist > 0 && max_window > 0) {
+        if (c.l2_persist && max_persist > 0 && max_window > 0) {
             const size_t persist = std::min<size_t>((size_t)max_persist, r->state_bytes);
             cudaStreamAttrValue av{};
             av.accessPolicyWindow.base_ptr = r->d_state;
@@ -331,18 +373,63 @@ bool device_renderer_render_chunk(DeviceRenderer* r, unsigned off_x, unsigned of
         r->launches++; count_launch();
         r->slots_inited = true;
     }
-    if (P.n_tiles == 0) {
-        // this rank owns no tile of the image: nothing to launch
+    // owned pixels of this chunk: the owned tiles clipped to the chunk
+    uint64_t owned = 0;
+    for (uint32_t tile : r->h_tiles) {
+        const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+        const uint32_t x0 = tx * P.tile_w, y0 = ty * P.tile_h;
+        if (x0 >= w || y0 >= h) continue;
+        owned += (uint64_t)(std::min(w, x0 + P.tile_w) - x0) * (std::min(h, y0 + P.tile_h) - y0);
+    }
+    size_t timed_rounds = 0;
+    if (P.n_tiles == 0 || owned == 0) {
+        // this rank owns no pixel of the chunk: nothing to launch
     } else if (r->cfg.pipeline == 1) {
         KernelTimer kt(r, 2);
         T.megakernel(P, r->mode, r->grid, r->smem, st);
-    } else {  // one persistent-block launch renders the whole chunk
-        KernelTimer kt(r, 1);
-        SRT_CUDA(cudaMemsetAsync(P.next_slot, 0, sizeof(uint32_t), st));
-        T.wavefront(P, r->mode, r->wave_grid, r->smem + P.queue_bytes, st);
-        r->iterations++;
+        r->launches++; count_launch();
+    } else {  // one persistent-block launch per round of samples renders the whole chunk
+        const size_t K = r->round_end.size();
+        P.sched_flags = (uint32_t)r->cfg.sched_flags;
+        const uint32_t* order0 = nullptr;
+        if (r->order && P.nslots >= kMinOrderedSlots && !(P.sched_flags & 1u)) {  // first round: expensive-looking pixels first (k_prior_cost)
+            KernelTimer kt(r, 0);
+            P.cost = r->d_cost;
+            T.prior_cost(P, st);
+            order0 = pixel_order_build(r->order, r->d_cost, P.nslots, 1, st);
+            if (!order0) { set_error("pixel order build failed"); return false; }
+            r->launches += 4; count_launch();
+        }
+        if (K > 1) SRT_CUDA(cudaMemsetAsync(r->d_cost, 0, (size_t)P.nslots * sizeof(uint32_t), st));
+        if (r->d_drain) SRT_CUDA(cudaMemsetAsync(r->d_drain, 0xFF, 2 * kMaxRounds * sizeof(unsigned long long), st));  // min slots; max slots are zeroed below
+        uint32_t s0 = 0;
+        for (size_t k = 0; k < K; k++) {
+            P.s_begin = s0; P.s_end = r->round_end[k];
+            P.cost = K > 1 ? r->d_cost : nullptr;
+            P.order = order0; P.n_order = order0 ? (uint32_t)owned : P.nslots;
+            if (k > 0) {  // most passes per sample first
+                KernelTimer kt(r, 0);
+                P.order = pixel_order_build(r->order, r->d_cost, P.nslots, s0, st);
+                if (!P.order) { set_error("pixel order build failed"); return false; }
+                P.n_order = (uint32_t)owned;
+                r->launches += 3;
+            }
+            if (r->d_drain) {
+                P.drain_clock = r->d_drain + 2 * k;
+                SRT_CUDA(cudaMemsetAsync(r->d_drain + 2 * k + 1, 0, sizeof(unsigned long long), st));
+            }
+            SRT_CUDA(cudaMemsetAsync(P.next_slot, 0, sizeof(uint32_t), st));
+            if (P.pass_log) SRT_CUDA(cudaMemsetAsync(P.pass_log, 0, (size_t)SRT_PASS_LOG_BLOCKS * SRT_PASS_LOG_PASSES * sizeof(uint4), st));
+            {
+                KernelTimer kt(r, 1);
+                T.wavefront(P, r->mode, r->wave_grid, r->smem + P.queue_bytes, st);
+            }
+            r->launches++; count_launch();
+            r->iterations++;
+            s0 = P.s_end;
+        }
+        timed_rounds = K;
     }
-    r->launches++; count_launch();
     SRT_CUDA_LAST();
     SRT_CUDA(cudaEventRecord(r->ev1, st));
     SRT_CUDA(cudaEventSynchronize(r->ev1));
@@ -350,13 +437,11 @@ bool device_renderer_render_chunk(DeviceRenderer* r, unsigned off_x, unsigned of
     SRT_CUDA(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
     r->render_ms += ms;
     collect_kernel_times(r);
-    // owned pixels of this chunk for the sample count: the owned tiles clipped to the chunk
-    uint64_t owned = 0;
-    for (uint32_t tile : r->h_tiles) {
-        const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
-        const uint32_t x0 = tx * P.tile_w, y0 = ty * P.tile_h;
-        if (x0 >= w || y0 >= h) continue;
-        owned += (uint64_t)(std::min(w, x0 + P.tile_w) - x0) * (std::min(h, y0 + P.tile_h) - y0);
+    if (r->d_drain && timed_rounds) {  // per launch: last block exit - first local slot that found no pixel left
+        unsigned long long stamps[2 * kMaxRounds];
+        SRT_CUDA(cudaMemcpy(stamps, r->d_drain, sizeof stamps, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < timed_rounds; k++)
+            if (stamps[2 * k] != ~0ull && stamps[2 * k + 1] > stamps[2 * k]) r->drain_ms += (double)(stamps[2 * k + 1] - stamps[2 * k]) * 1e-6;
     }
     r->samples += owned * P.spp;
     unsigned long long rays = 0;
@@ -420,6 +505,11 @@ bool device_renderer_download_xyz(DeviceRenderer* r, float* xyz) {
 }
 
 float* device_renderer_film(DeviceRenderer* r) { return r->P.acc; }
+bool device_renderer_pass_log(DeviceRenderer* r, uint32_t* out) {
+    if (!r->d_pass_log) { set_error("SRT_OPT_PASS_LOG was not set"); return false; }
+    SRT_CUDA(cudaMemcpy(out, r->d_pass_log, (size_t)SRT_PASS_LOG_BLOCKS * SRT_PASS_LOG_PASSES * sizeof(uint4), cudaMemcpyDeviceToHost));
+    return true;
+}
 
 bool device_renderer_reset(DeviceRenderer* r) {  // back to the state right after creation: empty film, unseeded RNG slots
     SRT_CUDA(cudaMemsetAsync(r->P.acc, 0, 3 * r->P.plane * sizeof(float), r->stream));
@@ -427,7 +517,7 @@ bool device_renderer_reset(DeviceRenderer* r) {  // back to the state right afte
     SRT_CUDA(cudaStreamSynchronize(r->stream));
     r->slots_inited = false;
     r->samples = r->rays = 0;
-    r->render_ms = 0;
+    r->render_ms = 0; r->drain_ms = 0;
     for (int k = 0; k < 4; k++) { r->cat_ms[k] = 0; r->cat_launches[k] = 0; }
     return true;
 }
@@ -436,11 +526,12 @@ void device_renderer_stats(const DeviceRenderer* r, srt_stats* s) {
     s->samples = r->samples;
     s->rays = r->rays;
     s->kernel_launches = r->launches;
-    s->wavefront_iterations = r->iterations;
+    s->wavefront_launches = r->iterations;
+    s->rounds = r->round_end.size();
+    s->drain_ms = r->drain_ms;
     s->render_ms = r->render_ms;
     s->lbvh_ms = device_scene_lbvh_ms(r->scene);
-    s->generate_ms = r->cat_ms[0]; s->shade_ms = r->cat_ms[1]; s->tail_ms = r->cat_ms[2]; s->other_ms = r->cat_ms[3];
-    s->generate_launches = r->cat_launches[0]; s->shade_launches = r->cat_launches[1]; s->tail_launches = r->cat_launches[2];
+    s->order_ms = r->cat_ms[0]; s->wavefront_ms = r->cat_ms[1]; s->megakernel_ms = r->cat_ms[2]; s->other_ms = r->cat_ms[3];
 }
 
 bool device_scene_trace(const DeviceScene* s, uint32_t n, const float* o, const float* d, float* t, int32_t* tri, float* ms, uint64_t* visits) {

@@ -3,15 +3,15 @@
 // (-fmad=false: rounds exactly like the host oracle) -- inside namespace SRT_FP_NS.
 //
 // Pipelines
-//   wavefront (default): two kernels per iteration over queues of pixel slots
-//       k_generate : slots that need a new sample: camera ray -> traverse -> classify
-//       k_shade    : slots sorted by the material type they hit (lambertian | metallic |
-//                    dielectric segments, warp-uniform): scatter -> traverse -> classify
-//     "classify" finishes the sample on miss / emitter / absorption / bounce limit (XYZ added to
-//     the film) and pushes the slot to the regenerate queue, or pushes it to the queue of the
-//     material it hit.  Queue pushes are warp-aggregated (ballot + one atomicAdd per warp).
-//     Exactly one sample is in flight per pixel, so every pixel consumes its XORWOW stream in the
-//     reference's order (rendering/rendering.cu:215-228).
+//   wavefront (default): k_wavefront, ONE persistent-block kernel per round of samples.  Every block
+//     keeps block_slots paths in flight in four shared-memory queues (regenerate | lambertian |
+//     metallic | dielectric, warp-uniform work) and loops over passes: regenerate = camera ray ->
+//     closest hit -> classify; material queues = scatter -> closest hit -> classify.  "classify"
+//     finishes the sample on miss / emitter / absorption / bounce limit (XYZ added to the film) and
+//     pushes the slot to the regenerate queue, or to the queue of the material it hit.  Queue pushes
+//     are warp-aggregated (ballot + one atomicAdd per warp).  Exactly one sample is in flight per
+//     pixel, so every pixel consumes its XORWOW stream in the reference's order
+//     (rendering/rendering.cu:215-228).
 //   megakernel: one thread per pixel looping over samples and bounces with the same device
 //     functions (used as a cross-check: it must produce bit-identical films).
 //
@@ -619,12 +619,34 @@ __global__ void k_init_slots(WaveParams P) {  // init_random_states (rendering.c
     store_rng(P.G0, P.G1, slot, rng_seed(1984u + ref_thread_index(P, ci, cj)));
 }
 
+// First guess of a pixel's cost before any of it is rendered: the un-jittered ray through the pixel centre misses
+// everything or ends on an emitter (1 pass per sample), or starts a bounce chain (counted as 6).  Only used to hand
+// out the expensive pixels first in the first round of a chunk; later rounds use the passes really spent.
+__global__ void __launch_bounds__(256) k_prior_cost(WaveParams P) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= P.nslots) return;
+    uint32_t ci, cj, c = 0;
+    if (slot_owned(P, slot, ci, cj)) {
+        const SrtCamera& cam = P.cam;
+        const V3 du = mk(cam.du[0], cam.du[1], cam.du[2]), dv = mk(cam.dv[0], cam.dv[1], cam.dv[2]);
+        const V3 o = mk(cam.center[0], cam.center[1], cam.center[2]);
+        const V3 d = ((mk(cam.p00[0], cam.p00[1], cam.p00[2]) + ((float)(P.off_x + ci) * du)) + ((float)(P.off_y + cj) * dv)) - o;
+        SceneRef sc;
+        sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
+        float t;
+        const int tri = closest_hit<false>(sc, o, d, t);
+        c = 1;
+        if (tri >= 0 && SRT_TRI_MTYPE(__float_as_uint((reinterpret_cast<const float4*>(sc.tris + tri) + 2)->z)) != SRT_EMISSIVE) c = 6;
+    }
+    P.cost[slot] = c;
+}
+
 // Persistent-block wavefront with pixel streaming.  A block keeps P.block_slots paths in flight and
 // runs its own bounce loop: four queues of local slot ids in shared memory (regenerate | lambertian |
-// metallic | dielectric), double buffered.  Every pass lays the four queues out back to back, each
-// padded to a warp multiple, so a warp only ever executes one kind of work; warps pull 32-item chunks
-// from a shared counter (cheap items do not leave a warp idle); results are pushed into the other
-// buffer with warp-aggregated shared-memory atomics.  A local slot renders one pixel at a time, all
+// metallic | dielectric), double buffered.  Every pass cuts the four queues into 32-item tasks -- the
+// full warps of each queue (one kind of work per warp), then the four remainders pooled into mixed
+// warps -- and warps pull tasks from a shared counter (cheap items do not leave a warp idle); results
+// are pushed into the other buffer with warp-aggregated shared-memory atomics.  A local slot renders one pixel at a time, all
 // its samples in order (the pixel's XORWOW stream is serial); when the pixel is finished the slot
 // fetches the next unrendered pixel slot from a global counter (one atomic per warp), so every block
 // stays full until the whole chunk runs out of pixels -- no per-tile tail, no wave quantisation, and
@@ -639,109 +661,147 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
     uint16_t* qbuf = reinterpret_cast<uint16_t*>(smem);                        // [2][4][S] queues of local slot ids
     uint32_t* pslot = reinterpret_cast<uint32_t*>(smem + 16u * S);             // [S] pixel slot a local slot renders
     uint16_t* started = reinterpret_cast<uint16_t*>(smem + 20u * S);           // [S] samples started of that pixel
+    uint16_t* passes = reinterpret_cast<uint16_t*>(smem + 22u * S);            // [S] passes spent on that pixel in this launch
     uint32_t* pxy = reinterpret_cast<uint32_t*>(smem + 24u * S);               // [S] that pixel's chunk coordinates, y << 16 | x
     __shared__ int cnt[2][4];
-    __shared__ int next_chunk;
+    __shared__ int next_task;
     const SceneRef sc = load_scene<SMEM, FLAT>(P, smem + P.queue_bytes);
     const uint32_t first = blockIdx.x * S;  // this block's records in the in-flight state arrays
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < 8) (&cnt[0][0])[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { next_chunk = 0; cnt[0][0] = (int)S; }
+    if (threadIdx.x == 0) { next_task = 0; cnt[0][0] = (int)S; }
     // pass 0 input: every local slot asks for a pixel
     for (uint32_t l = threadIdx.x; l < S; l += blockDim.x) {
         pslot[l] = SRT_NO_SLOT;
         started[l] = 0;
+        passes[l] = 0;
         qbuf[l] = (uint16_t)l;
     }
     __syncthreads();
     unsigned long long rays = 0;
     int cur = 0;
+    uint32_t npass = 0;
     while (true) {
         const int nR = cnt[cur][0], nL = cnt[cur][1], nM = cnt[cur][2], nD = cnt[cur][3];
         if ((nR | nL | nM | nD) == 0) break;
-        const int eR = (nR + 31) & ~31, eL = eR + ((nL + 31) & ~31), eM = eL + ((nM + 31) & ~31), eD = eM + ((nD + 31) & ~31);
+        if (P.pass_log && blockIdx.x < SRT_PASS_LOG_BLOCKS && threadIdx.x == 0 && npass < SRT_PASS_LOG_PASSES) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            P.pass_log[blockIdx.x * SRT_PASS_LOG_PASSES + npass] = make_uint4((uint32_t)now, (uint32_t)nR, (uint32_t)nL, (uint32_t)nM | ((uint32_t)nD << 16));
+        }
+        // tasks of this pass (32 items each): the full warps of every queue first -- one kind of work per warp --, then the
+        // queues' remainders (< 32 items each) pooled into mixed warps, so that S items never need more than S / 32 tasks
+        const int fR = nR >> 5, fL = nL >> 5, fM = nM >> 5, fD = nD >> 5;
+        const int rR = nR & 31, rL = nL & 31, rM = nM & 31, rD = nD & 31;
+        const int tL = fR + fL, tM = tL + fM, tF = tM + fD, rem = rR + rL + rM + rD;
+        const bool pooled = !(P.sched_flags & 4u);
+        const int n_tasks = tF + (pooled ? ((rem + 31) >> 5) : ((rR > 0) + (rL > 0) + (rM > 0) + (rD > 0)));
         const uint16_t* qi = qbuf + (size_t)cur * 4 * S;
         uint16_t* qo = qbuf + (size_t)(cur ^ 1) * 4 * S;
         int* co = cnt[cur ^ 1];
         while (true) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&next_chunk, 32);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= eD) break;
-            const int v = base + lane;
-            // which queue does this warp serve (uniform), and does this lane have an item?
+            int task = 0;
+            if (lane == 0) task = atomicAdd(&next_task, 1);
+            task = __shfl_sync(0xffffffffu, task, 0);
+            if (task >= n_tasks) break;
             int kind, k;
-            if (base < eR) { kind = 0; k = v; }
-            else if (base < eL) { kind = 1; k = v - eR; }
-            else if (base < eM) { kind = 2; k = v - eL; }
-            else { kind = 3; k = v - eM; }
-            const int have_n = kind == 0 ? nR : (kind == 1 ? nL : (kind == 2 ? nM : nD));
-            const bool have = k < have_n;
+            bool have = true;
+            if (task < tF) {  // warp-uniform kind
+                if (task < fR) { kind = 0; k = task * 32 + lane; }
+                else if (task < tL) { kind = 1; k = (task - fR) * 32 + lane; }
+                else if (task < tM) { kind = 2; k = (task - tL) * 32 + lane; }
+                else { kind = 3; k = (task - tM) * 32 + lane; }
+            } else if (!pooled) {  // one partial warp per non-empty remainder
+                int j = task - tF;
+                if (rR > 0 && j-- == 0) { kind = 0; k = fR * 32 + lane; have = lane < rR; }
+                else if (rL > 0 && j-- == 0) { kind = 1; k = fL * 32 + lane; have = lane < rL; }
+                else if (rM > 0 && j-- == 0) { kind = 2; k = fM * 32 + lane; have = lane < rM; }
+                else { kind = 3; k = fD * 32 + lane; have = lane < rD; }
+            } else {
+                const int v = (task - tF) * 32 + lane;
+                have = v < rem;
+                if (v < rR) { kind = 0; k = fR * 32 + v; }
+                else if (v < rR + rL) { kind = 1; k = fL * 32 + (v - rR); }
+                else if (v < rR + rL + rM) { kind = 2; k = fM * 32 + (v - rR - rL); }
+                else { kind = 3; k = fD * 32 + (v - rR - rL - rM); }
+            }
             const uint32_t l = have ? qi[kind * S + k] : 0u;
             const uint32_t rec = first + l;
             uint32_t slot = have ? pslot[l] : SRT_NO_SLOT;
             uint32_t s = started[l];
+            uint32_t np = passes[l] + 1u;
             uint32_t ci = 0, cj = 0;
             size_t pix = 0;
             Path p;
             Rng rng;
             int tri = -1, ev = EV_DONE;
             bool trace = false, retired = false;
-            if (kind == 0) {  // warp-uniform
-                // slots without a pixel fetch the next unrendered pixel slots: one global atomic per warp
-                const bool fetch = have && slot == SRT_NO_SLOT;
-                const uint32_t fm = __ballot_sync(0xffffffffu, fetch);
-                if (fm) {
-                    uint32_t fbase = 0;
-                    if (lane == __ffs(fm) - 1) fbase = atomicAdd(P.next_slot, (uint32_t)__popc(fm));
-                    fbase = __shfl_sync(0xffffffffu, fbase, __ffs(fm) - 1);
-                    if (fetch) {
-                        const uint32_t cand = fbase + __popc(fm & ((1u << lane) - 1));
-                        if (cand >= P.nslots) retired = true;  // the chunk has no pixels left: this local slot is done
-                        else if (slot_owned(P, cand, ci, cj)) {  // edge tiles stick out of the chunk: such a slot asks again next pass
+            // local slots without a pixel take the next entries of the hand-out order: one global atomic per warp
+            const bool fetch = have && kind == 0 && slot == SRT_NO_SLOT;
+            const uint32_t fm = __ballot_sync(0xffffffffu, fetch);
+            if (fm) {
+                uint32_t fbase = 0;
+                if (lane == __ffs(fm) - 1) fbase = atomicAdd(P.next_slot, (uint32_t)__popc(fm));
+                fbase = __shfl_sync(0xffffffffu, fbase, __ffs(fm) - 1);
+                const uint32_t idx = fbase + __popc(fm & ((1u << lane) - 1));
+                if (fetch) {
+                    if (idx >= P.n_order) retired = true;  // the chunk has no pixels left: this local slot is done
+                    else {
+                        const uint32_t cand = P.order ? P.order[idx] : idx;
+                        if (slot_owned(P, cand, ci, cj)) {  // edge tiles stick out of the chunk: such a slot asks again next pass
                             slot = cand;
                             pslot[l] = slot;
                             pxy[l] = (cj << 16) | ci;  // tile look-up and divisions once per pixel, not once per pass
-                            s = 0;
+                            s = P.s_begin;
+                            np = 1;
                             rng = load_rng(P.G0, P.G1, slot);
                         }
                     }
                 }
-                if (have && slot != SRT_NO_SLOT) {
+                if (P.drain_clock && __any_sync(0xffffffffu, retired) && lane == 0) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    atomicMin(P.drain_clock, now);
+                }
+            }
+            if (have && slot != SRT_NO_SLOT) {
+                if (kind == 0) {
                     if (!fetch) {
                         const uint32_t xy = pxy[l];
                         ci = xy & 0xFFFFu; cj = xy >> 16;
                         rng = load_rng(P.L0, P.L1, rec);
                     }
                     pix = (size_t)(P.off_y + cj) * P.img_w + (P.off_x + ci);
-                    if (s < P.spp) {  // next sample of this pixel (rendering.cu:215-228)
+                    if (s < P.s_end) {  // next sample of this pixel (rendering.cu:215-228)
                         camera_ray(P, P.off_x + ci, P.off_y + cj, s, rng, p);
                         s++;
                         started[l] = (uint16_t)s;
                         trace = P.bounce_limit != 0;  // limit 0: the bounce loop never runs, valid = 0
                     }
+                } else {  // scatter at the stored hit
+                    const uint32_t xy = pxy[l];
+                    ci = xy & 0xFFFFu; cj = xy >> 16;
+                    pix = (size_t)(P.off_y + cj) * P.img_w + (P.off_x + ci);
+                    rng = load_rng(P.L0, P.L1, rec);
+                    load_hit_state(P, rec, p, tri);
+                    const uint32_t mtype = kind == 2 ? SRT_METALLIC : (kind == 3 ? SRT_DIELECTRIC : SRT_LAMBERTIAN);
+                    const bool alive = scatter(sc, sc.tris + tri, mtype, p, rng);
+                    p.bounce++;
+                    trace = alive && p.bounce < P.bounce_limit;  // absorbed, or bounce limit: valid = 0 (rendering.cu:38)
                 }
-            } else if (have) {  // scatter at the stored hit (warp-uniform material)
-                const uint32_t xy = pxy[l];
-                ci = xy & 0xFFFFu; cj = xy >> 16;
-                pix = (size_t)(P.off_y + cj) * P.img_w + (P.off_x + ci);
-                rng = load_rng(P.L0, P.L1, rec);
-                load_hit_state(P, rec, p, tri);
-                const uint32_t mtype = kind == 2 ? SRT_METALLIC : (kind == 3 ? SRT_DIELECTRIC : SRT_LAMBERTIAN);
-                const bool alive = scatter(sc, sc.tris + tri, mtype, p, rng);
-                p.bounce++;
-                trace = alive && p.bounce < P.bounce_limit;  // absorbed, or bounce limit: valid = 0 (rendering.cu:38)
             }
             if (trace) {
                 rays++;
                 ev = extend<FLAT>(sc, P, p, tri, P.acc, pix, kind == 0);
             }
             if (have && slot != SRT_NO_SLOT) {
-                if (ev == EV_DONE && s >= P.spp) {  // pixel finished: its RNG state goes back to the pixel (carried into the next chunk)
+                if (ev == EV_DONE && s >= P.s_end) {  // pixel finished: its RNG state goes back to the pixel (carried into the next round / chunk)
                     store_rng(P.G0, P.G1, slot, rng);
+                    if (P.cost) P.cost[slot] += np;
                     pslot[l] = SRT_NO_SLOT;
                 } else {
                     store_rng(P.L0, P.L1, rec, rng);
+                    passes[l] = (uint16_t)np;
                     if (ev != EV_DONE) store_hit_state(P, rec, p, tri);
                 }
             }
@@ -752,11 +812,17 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
         }
         __syncthreads();
         if (threadIdx.x < 4) cnt[cur][threadIdx.x] = 0;  // becomes the output buffer of the next pass
-        if (threadIdx.x == 0) next_chunk = 0;
+        if (threadIdx.x == 0) next_task = 0;
         cur ^= 1;
+        npass++;
         __syncthreads();
     }
     if (P.ray_counter && rays) atomicAdd(P.ray_counter, rays);
+    if (P.drain_clock && threadIdx.x == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMax(P.drain_clock + 1, now);
+    }
 }
 
 // per-pixel persistent kernel: same device functions, no queues (cross-check / comparison)
@@ -771,7 +837,7 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_megakernel(WaveParams P) {
         const uint32_t x = P.off_x + ci, y = P.off_y + cj;
         const size_t pix = (size_t)y * P.img_w + x;
         Rng rng = load_rng(P.G0, P.G1, slot);
-        for (uint32_t s = 0; s < P.spp; s++) {
+        for (uint32_t s = P.s_begin; s < P.s_end; s++) {
             Path p;
             camera_ray(P, x, y, s, rng, p);
             if (P.bounce_limit == 0) continue;
@@ -907,6 +973,7 @@ LaunchTable make_launch_table() {
         return e;
     };
     t.init_slots = [](const WaveParams& P, cudaStream_t st) { k_init_slots<<<(P.nslots + 255) / 256, 256, 0, st>>>(P); };
+    t.prior_cost = [](const WaveParams& P, cudaStream_t st) { k_prior_cost<<<(P.nslots + 255) / 256, 256, 0, st>>>(P); };
     t.wavefront = [](const WaveParams& P, int mode, int grid, size_t smem, cudaStream_t st) {
         // the queues always live in shared memory, also when the scene does not
         const int threads = (int)P.block_threads;  // <= SRT_WAVE_BLOCK, the launch bound the registers were allocated for

@@ -34,6 +34,14 @@ struct WaveParams {
     uint32_t n_tiles;
     uint32_t ref_grid_x;             // nominal_chunk_w / 28 + 1 (reference launch geometry -> seeds)
     uint32_t spp, bounce_limit;
+    // one wavefront launch renders samples [s_begin, s_end) of every pixel it is handed (a "round"); the pixel's
+    // XORWOW state waits in G0/G1 between rounds exactly as it does between chunks (rendering.cu:209,232)
+    uint32_t s_begin, s_end;
+    const uint32_t* order;   // pixel slots in the order they are handed out (most passes per sample first); null = 0..nslots-1
+    uint32_t n_order;        // entries of `order` (all owned), or nslots
+    uint32_t sched_flags;    // debug (SRT_OPT_SCHED_FLAGS): 1 no first-guess order, 4 no pooled remainders
+    uint32_t* cost;          // per pixel slot: wavefront passes spent on it so far in this chunk (null = not recorded)
+    unsigned long long* drain_clock;  // [0] globaltimer when the first local slot found no pixel left (min), [1] last block exit (max); null = off
     uint32_t strat_n;      // 0: the reference's sampler; n: stratified n x n sub-cells per pixel (n*n == spp)
     float strat_recip;     // 1 / n
     uint32_t tile_w, tile_h, tiles_x, rank, world;  // tiles_x: tiles per row of the nominal chunk
@@ -56,12 +64,16 @@ struct WaveParams {
     uint32_t block_threads;  // threads of a wavefront block (128 or 256)
     float scene_lo[3], scene_hi[3];  // bounding box of all triangles (host)
     unsigned long long* ray_counter;
+    uint4* pass_log;  // debug (SRT_OPT_PASS_LOG): blocks 0..7 record {globaltimer ns (low 32 bits), regenerate, lambertian, metallic | dielectric << 16} per pass
 };
+#define SRT_PASS_LOG_BLOCKS 8
+#define SRT_PASS_LOG_PASSES 8192
 
 struct LaunchTable {
     size_t (*smem_bytes)(const WaveParams&, int mode);
     cudaError_t (*configure)(size_t smem_bytes);
     void (*init_slots)(const WaveParams&, cudaStream_t);
+    void (*prior_cost)(const WaveParams&, cudaStream_t);
     void (*wavefront)(const WaveParams&, int mode, int grid, size_t smem, cudaStream_t);
     int (*wavefront_blocks_per_sm)(int mode, int threads, size_t smem);  // resident blocks the hardware grants
     void (*megakernel)(const WaveParams&, int mode, int grid, size_t smem, cudaStream_t);

@@ -211,6 +211,7 @@ int srt_rm_get_xyz(srt_render_manager* h, float* xyz) { return xyz ? h->rm->get_
 float* srt_rm_device_film(srt_render_manager* h) { return h->rm->device_film(); }
 int srt_rm_resolve_film(srt_render_manager* h) { return h->rm->resolve_film(); }
 int srt_rm_restart(srt_render_manager* h) { return h->rm->restart(); }
+int srt_rm_get_pass_log(srt_render_manager* h, uint32_t* out) { return out ? h->rm->get_pass_log(out) : SRT_ERR_ARG; }
 int srt_rm_get_stats(const srt_render_manager* h, srt_stats* out) { return out ? h->rm->stats(out) : SRT_ERR_ARG; }
 
 double srt_measure_fp32_tflops(void) { return measure_fp32_tflops(); }

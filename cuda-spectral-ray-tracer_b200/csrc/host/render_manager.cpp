@@ -47,9 +47,11 @@ int RenderManager::set_option(int opt, int value) {
         case SRT_OPT_TILE_H: cfg_.tile_h = value; break;
         case SRT_OPT_RANK: cfg_.rank = value; break;
         case SRT_OPT_WORLD: cfg_.world = value; break;
-        case SRT_OPT_REGEN_LOOP: break;  // retired tuning knobs: accepted and ignored
         case SRT_OPT_KERNEL_TIMING: cfg_.kernel_timing = value ? 1 : 0; break;
-        case SRT_OPT_TAIL_THRESHOLD: break;
+        case SRT_OPT_SCHED_FLAGS: cfg_.sched_flags = value; break;
+        case SRT_OPT_PASS_LOG: cfg_.pass_log = value ? 1 : 0; break;
+        case SRT_OPT_ROUNDS: cfg_.rounds = value; break;
+        case SRT_OPT_L2_PERSIST: cfg_.l2_persist = value ? 1 : 0; break;
         case SRT_OPT_STRATIFIED: cfg_.stratified = value ? 1 : 0; break;
         case SRT_OPT_TRAVERSAL: cfg_.traversal = value; break;
         case SRT_OPT_BLOCK_SLOTS: cfg_.block_slots = value; break;

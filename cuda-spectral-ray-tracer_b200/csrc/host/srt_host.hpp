@@ -148,6 +148,10 @@ struct RenderConfig {
     int stratified = 0;      // opt-in stratified pixel sampler (dormant in the reference, rendering.cu:58-64,89-118)
     int block_slots = 0;     // paths in flight per wavefront block (power of two), 0 = automatic
     int block_threads = 0;   // threads per wavefront block, 0 = automatic
+    int sched_flags = 0;     // debug: switches single scheduling features off (SRT_OPT_SCHED_FLAGS)
+    int pass_log = 0;        // debug: per-pass log of the first blocks (SRT_OPT_PASS_LOG)
+    int rounds = 0;          // wavefront launches per chunk, 0 = automatic (SRT_OPT_ROUNDS)
+    int l2_persist = 1;      // persisting-L2 window over the in-flight path state (SRT_OPT_L2_PERSIST)
     int traversal = 0;  // 0 auto (wide leaf when <= 64 triangles), 1 force LBVH walk in shared memory, 3 force LBVH walk in global memory
     int tile_w = 0, tile_h = 0, rank = 0, world = 1;  // tile 0x0 = pick automatically
     float bg_spectrum[SRT_NS];
@@ -163,6 +167,7 @@ bool device_renderer_resolve(DeviceRenderer*, unsigned off_x, unsigned off_y, un
 bool device_renderer_download_xyz(DeviceRenderer*, float* xyz);
 float* device_renderer_film(DeviceRenderer*);
 bool device_renderer_reset(DeviceRenderer*);
+bool device_renderer_pass_log(DeviceRenderer*, uint32_t* out);
 void device_renderer_stats(const DeviceRenderer*, srt_stats* s);
 
 uint64_t kernel_launches();
@@ -194,6 +199,7 @@ public:
     int end_render();
     int set_option(int opt, int value);
     int get_xyz(float* xyz);
+    int get_pass_log(uint32_t* out) { return dev_ && device_renderer_pass_log(dev_, out) ? SRT_OK : SRT_ERR_STATE; }
     float* device_film();
     int resolve_film();
     int restart();

@@ -39,12 +39,12 @@ class MaterialDesc(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("wavefront_iterations", C.c_uint64), ("render_ms", C.c_double), ("lbvh_ms", C.c_double),
-                ("generate_ms", C.c_double), ("shade_ms", C.c_double), ("tail_ms", C.c_double), ("other_ms", C.c_double),
-                ("generate_launches", C.c_uint64), ("shade_launches", C.c_uint64), ("tail_launches", C.c_uint64)]
+                ("wavefront_launches", C.c_uint64), ("rounds", C.c_uint64), ("render_ms", C.c_double), ("lbvh_ms", C.c_double),
+                ("wavefront_ms", C.c_double), ("megakernel_ms", C.c_double), ("order_ms", C.c_double), ("other_ms", C.c_double),
+                ("drain_ms", C.c_double)]
 
 
-OPT_FP_MODE, OPT_PIPELINE, OPT_TILE_W, OPT_TILE_H, OPT_RANK, OPT_WORLD, OPT_REGEN_LOOP, OPT_KERNEL_TIMING, OPT_TAIL_THRESHOLD, OPT_TRAVERSAL, OPT_BLOCK_SLOTS, OPT_BLOCK_THREADS, OPT_STRATIFIED = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13
+OPT_FP_MODE, OPT_PIPELINE, OPT_TILE_W, OPT_TILE_H, OPT_RANK, OPT_WORLD, OPT_KERNEL_TIMING, OPT_TRAVERSAL, OPT_BLOCK_SLOTS, OPT_BLOCK_THREADS, OPT_STRATIFIED, OPT_ROUNDS, OPT_L2_PERSIST, OPT_PASS_LOG, OPT_SCHED_FLAGS = 1, 2, 3, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16, 17
 MAT_LAMBERTIAN, MAT_METALLIC, MAT_DIELECTRIC, MAT_EMISSIVE = 0, 1, 2, 4
 
 # every symbol include/srt.h declares: (name, restype, argtypes)
@@ -102,6 +102,7 @@ _SIGS = [
     ("srt_rm_resolve_film", C.c_int, [_P]),
     ("srt_rm_restart", C.c_int, [_P]),
     ("srt_rm_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
+    ("srt_rm_get_pass_log", C.c_int, [_P, _P]),
     ("srt_measure_fp32_tflops", C.c_double, []),
     ("srt_measure_copy_gbs", C.c_double, [C.c_uint32]),
     ("srt_write_ppm", C.c_int, [C.c_char_p, _P, _P, _P, C.c_uint32, C.c_uint32]),
@@ -332,6 +333,11 @@ class RenderManager:
         _check(lib().srt_rm_get_xyz(self.h, out.ctypes.data))
         return out.reshape(3, self.cam.height, self.cam.width)
 
+    def pass_log(self):
+        out = np.zeros((8, 8192, 4), np.uint32)
+        _check(lib().srt_rm_get_pass_log(self.h, out.ctypes.data))
+        return out
+
     def stats(self):
         s = Stats()
         _check(lib().srt_rm_get_stats(self.h, C.byref(s)))
@@ -339,7 +345,7 @@ class RenderManager:
 
 
 def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=False, pipeline=0, scene=None, tiles=None,
-           kernel_timing=False, traversal=None, block_slots=None, block_threads=None, stratified=False):
+           kernel_timing=False, traversal=None, block_slots=None, block_threads=None, stratified=False, rounds=None, sched_flags=None):
     """One-call helper: returns (rgb[3,h,w] float32 0..255, xyz[3,h,w] float32, stats dict)."""
     sc = scene if scene is not None else Scene(scene_id)
     cam = sc.camera(w, h)
@@ -356,6 +362,10 @@ def render(scene_id=0, w=400, h=225, spp=8, bounce=10, chunk=(0, 0), strict=Fals
         rm.set_option(OPT_BLOCK_THREADS, block_threads)
     if stratified:
         rm.set_option(OPT_STRATIFIED, 1)
+    if rounds is not None:
+        rm.set_option(OPT_ROUNDS, rounds)
+    if sched_flags is not None:
+        rm.set_option(OPT_SCHED_FLAGS, sched_flags)
     if tiles is not None:
         tw, th, rank, world = tiles
         rm.set_option(OPT_TILE_W, tw); rm.set_option(OPT_TILE_H, th); rm.set_option(OPT_RANK, rank); rm.set_option(OPT_WORLD, world)

@@ -179,21 +179,30 @@ int srt_rm_render_all(srt_render_manager*);
 #define SRT_OPT_TILE_H 4
 #define SRT_OPT_RANK 5         /* ... this process renders the tiles with (tile_x + 5 tile_y) % world == rank */
 #define SRT_OPT_WORLD 6
-#define SRT_OPT_REGEN_LOOP 7   /* (retired tuning knob: accepted and ignored, kept for ABI stability) */
 #define SRT_OPT_KERNEL_TIMING 8 /* 1 = bracket every kernel launch with CUDA events (per-kernel totals in srt_stats) */
-#define SRT_OPT_TAIL_THRESHOLD 9 /* (retired tuning knob: accepted and ignored, kept for ABI stability) */
 #define SRT_OPT_BLOCK_SLOTS 11   /* paths in flight per wavefront block: power of two in [32, 4096], 0 = automatic */
 #define SRT_OPT_BLOCK_THREADS 12 /* threads per wavefront block: 0 = 256 */
 #define SRT_OPT_STRATIFIED 13    /* 1 = stratified pixel sampler (renderer::get_ray_stratified_sample, rendering/rendering.cu:58-64,89-118,
                                     which the reference carries but never calls): sample k takes sub-cell (k % n, k / n) of an n x n
                                     grid, spp must be n*n; 0 (default) = the reference's sampler */
+#define SRT_OPT_ROUNDS 14        /* launches per chunk: the samples of a pixel are rendered in K rounds [0,b1) [b1,b2) .. [b,spp), each 8x
+                                    longer than the one before; the pixel's XORWOW state waits in HBM between rounds like it does between
+                                    chunks (rendering/rendering.cu:209,232), so the film does not depend on K.  From the second round on
+                                    pixels are handed out most-passes-per-sample first, which is what ends all blocks together.
+                                    0 (default) = automatic (1 below 16 spp, 2, 3 from 512 spp), 1 = a single launch */
+#define SRT_OPT_L2_PERSIST 15    /* 1 (default) = keep the state of the paths in flight in a persisting-L2 window (a process-wide
+                                    cudaDeviceSetLimit while a renderer exists), 0 = leave the device's L2 configuration alone */
+#define SRT_OPT_PASS_LOG 16      /* debug: 1 = the first 8 blocks of the LAST k_wavefront launch record a time stamp and their queue lengths
+                                    every pass; read back with srt_rm_get_pass_log */
+#define SRT_OPT_SCHED_FLAGS 17   /* debug / ablation, bit mask: 1 = first round in slot order (no first-guess cost order),
+                                    4 = queue remainders are not pooled into mixed warps */
 #define SRT_OPT_TRAVERSAL 10     /* 0 auto (wide-leaf closest hit when the scene has <= 64 triangles), 1 force the LBVH walk
                                     (scene in shared memory), 3 force the LBVH walk with the scene in global memory */
 int srt_rm_set_option(srt_render_manager*, int option, int value);
 /* pre-tonemap film of the whole image: 3 raster planes of XYZ (mean over spp); downloaded on demand */
 int srt_rm_get_xyz(srt_render_manager*, float* xyz);
 /* device pointer to the XYZ SUM film (3 planes, W*H floats each, zeros outside owned tiles);
- * a caller that owns an NCCL communicator reduces it in place and then calls srt_rm_tonemap_device */
+ * a caller that owns an NCCL communicator may reduce it in place and then call srt_rm_resolve_film */
 float* srt_rm_device_film(srt_render_manager*);
 /* tonemaps the (possibly reduced) device film into the caller's frame buffer and XYZ planes */
 int srt_rm_resolve_film(srt_render_manager*);
@@ -201,14 +210,21 @@ int srt_rm_resolve_film(srt_render_manager*);
  * same image can be rendered again (the reference's render_manager is one-shot) */
 int srt_rm_restart(srt_render_manager*);
 typedef struct {
-    uint64_t samples, rays, kernel_launches, wavefront_iterations;
-    double render_ms;   /* CUDA-event time of all step() kernels */
+    uint64_t samples, rays, kernel_launches;
+    uint64_t wavefront_launches; /* k_wavefront launches so far (rounds x chunks) */
+    uint64_t rounds;             /* launches per chunk (SRT_OPT_ROUNDS after the automatic choice) */
+    double render_ms;   /* CUDA-event time of all step() work on the device */
     double lbvh_ms;     /* last LBVH build of the scene */
-    /* filled when SRT_OPT_KERNEL_TIMING is on: summed CUDA-event durations and launch counts */
-    double generate_ms, shade_ms, tail_ms, other_ms;
-    uint64_t generate_launches, shade_launches, tail_launches;
+    /* filled when SRT_OPT_KERNEL_TIMING is on: summed CUDA-event durations per kernel family ... */
+    double wavefront_ms, megakernel_ms, order_ms, other_ms; /* k_wavefront | k_megakernel | pixel-order sort | RNG seeding */
+    /* ... and the end-of-launch drain of k_wavefront: last block exit minus the moment the first path slot
+     * found no pixel left to fetch (device globaltimer), summed over launches */
+    double drain_ms;
 } srt_stats;
 int srt_rm_get_stats(const srt_render_manager*, srt_stats* out);
+/* SRT_OPT_PASS_LOG read-out: out = 8 blocks x 8192 passes x 4 uint32 {globaltimer ns (low 32 bits), regenerate, lambertian,
+ * metallic | dielectric << 16}; unused entries are zero */
+int srt_rm_get_pass_log(srt_render_manager*, uint32_t* out);
 
 /* measured FP32 FMA issue peak of the current device in TFLOP/s (dependent-free FFMA chains on every
  * SM, CUDA-event timed): the roofline denominator for the instruction-bound render kernels */

@@ -335,6 +335,23 @@ def test_paths_in_flight_do_not_change_the_film(srt):
         assert np.array_equal(base[1].view(np.uint32), other[1].view(np.uint32)), kw
 
 
+@pytest.mark.parametrize("strict", [True, False])
+def test_rounds_do_not_change_the_film(srt, strict):
+    """SRT_OPT_ROUNDS: the samples of a pixel rendered in K launches (XORWOW state parked in HBM between them, pixels handed out
+    most-expensive-first from the second launch on) give the same film bits as one launch -- whole image, and a chunked render of
+    an odd-sized image (edge tiles, RNG carry-over between chunks, rounds inside every chunk), also on a 3-rank tile split"""
+    for kw in (dict(scene_id=0, w=320, h=180, spp=64), dict(scene_id=2, w=203, h=117, spp=16, chunk=(96, 64)), dict(scene_id=1, w=64, h=36, spp=600),
+               dict(scene_id=0, w=320, h=180, spp=24, tiles=(16, 16, 1, 3))):
+        base = srt.render(bounce=10, strict=strict, rounds=1, **kw)
+        assert base[2]["rounds"] == 1
+        for k in (0, 2, 3, 4, 8):
+            other = srt.render(bounce=10, strict=strict, rounds=k, **kw)
+            assert np.array_equal(base[1].view(np.uint32), other[1].view(np.uint32)), (kw, k)
+            assert np.array_equal(base[0], other[0])
+            assert other[2]["samples"] == base[2]["samples"] and other[2]["rays"] == base[2]["rays"]
+        assert other[2]["rounds"] >= 2
+
+
 def test_full_bench_size_bitwise_vs_oracle(srt):
     """The whole bench workload (BASELINE configs[1]: Cornell 1920x1080, 64 spp, depth 10; 435 M rays) in strict FP mode
     against the CPU oracle (which equals the real reference host build on this frame bit for bit, checked in the

@@ -21,9 +21,9 @@ def run(name, **kw):
         if best is None or st["render_ms"] < best["render_ms"]:
             best = st
     st = best
-    print("%-28s %8.2f ms  %7.3f Gsamples/s  %6.3f Grays/s  iters %4d launches %5d  gen %.2f shade %.2f tail %.2f other %.2f" % (
+    print("%-28s %8.2f ms  %7.3f Gsamples/s  %6.3f Grays/s  rounds %d launches %5d  wavefront %.2f mega %.2f order %.2f other %.2f drain %.2f" % (
         name, st["render_ms"], st["samples"] / st["render_ms"] / 1e6, st["rays"] / st["render_ms"] / 1e6,
-        st["wavefront_iterations"], st["kernel_launches"], st["generate_ms"], st["shade_ms"], st["tail_ms"], st["other_ms"]), flush=True)
+        st["rounds"], st["kernel_launches"], st["wavefront_ms"], st["megakernel_ms"], st["order_ms"], st["other_ms"], st["drain_ms"]), flush=True)
 for v in a.variants.split(","):
     if v == "wave": run("wavefront", pipeline=0)
     elif v == "wave_t": run("wavefront+timing", pipeline=0, kernel_timing=True)
@@ -31,6 +31,7 @@ for v in a.variants.split(","):
     elif v == "strict": run("wavefront strict", pipeline=0, strict=True)
     elif v == "bvh": run("wavefront lbvh-walk smem", pipeline=0, traversal=1)
     elif v == "bvhg": run("wavefront lbvh-walk global", pipeline=0, traversal=3)
+    elif v.startswith("rounds"): run("wavefront %s rounds" % v[6:], pipeline=0, rounds=int(v[6:]), kernel_timing=True)
     elif v.startswith("bs"): run("wavefront %s paths per block" % v[2:], pipeline=0, block_slots=int(v[2:]))
     elif v.startswith("tile"):
         tw, th = v[4:].split("x"); run("wavefront tile %sx%s" % (tw, th), pipeline=0, tiles=(int(tw), int(th), 0, 1))
