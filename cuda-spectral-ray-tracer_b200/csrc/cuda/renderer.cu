@@ -43,30 +43,40 @@ int sm_count() {
 constexpr size_t kSmemSceneLimit = 96 * 1024;  // scenes whose nodes+tris+materials fit are staged in shared memory
 }  // namespace
 
-// Process-wide cache of large device buffers.  cudaMalloc/cudaFree of the ~250 MB of per-pixel state
-// cost tens of milliseconds per render manager (more than the render itself at 1080p); a caller that
-// renders frame after frame gets the previous frame's buffers back instead.
+// Process-wide caches of large device buffers and of pinned host staging.  cudaMalloc/cudaFree of the ~250 MB of
+// per-pixel state cost tens of milliseconds per render manager (more than the render itself at 1080p), page-locking
+// the staging buffer costs milliseconds; a caller that renders frame after frame gets the previous frame's blocks back.
+// Blocks are tagged with the CUDA device they live on; srt_trim_caches() returns everything unused to the driver.
 namespace {
-struct PoolBlock { void* ptr; size_t bytes; bool used; };
+struct PoolBlock { void* ptr; size_t bytes; bool used; int device; };
 std::mutex g_pool_mu;
-std::vector<PoolBlock> g_pool;
+std::vector<PoolBlock> g_pool;      // device memory
+std::vector<PoolBlock> g_pinned;    // page-locked host memory (device = -1)
+int current_device() { int d = 0; cudaGetDevice(&d); return d; }
+void release_unused(std::vector<PoolBlock>& pool, bool pinned) {
+    for (size_t i = 0; i < pool.size();) {
+        if (!pool[i].used) {
+            if (pinned) cudaFreeHost(pool[i].ptr); else cudaFree(pool[i].ptr);
+            pool.erase(pool.begin() + i);
+        } else i++;
+    }
+}
 }  // namespace
 bool device_pool_alloc(void** out, size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
+    const int dev = current_device();
     std::lock_guard<std::mutex> lock(g_pool_mu);
     PoolBlock* best = nullptr;
     for (PoolBlock& b : g_pool)
-        if (!b.used && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 && (!best || b.bytes < best->bytes)) best = &b;
+        if (!b.used && b.device == dev && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 && (!best || b.bytes < best->bytes)) best = &b;
     if (best) { best->used = true; *out = best->ptr; return true; }
     void* p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess) {  // out of memory: drop the cache and retry once
         cudaGetLastError();
-        for (size_t i = 0; i < g_pool.size();) {
-            if (!g_pool[i].used) { cudaFree(g_pool[i].ptr); g_pool.erase(g_pool.begin() + i); } else i++;
-        }
+        release_unused(g_pool, false);
         if (!cuda_ok(cudaMalloc(&p, bytes), "cudaMalloc(pool)", __FILE__, __LINE__)) return false;
     }
-    g_pool.push_back({p, bytes, true});
+    g_pool.push_back({p, bytes, true, dev});
     *out = p;
     return true;
 }
@@ -77,20 +87,29 @@ void device_pool_free(void* p) {
         if (b.ptr == p) { b.used = false; return; }
     cudaFree(p);
 }
-
-// One grow-only pinned staging buffer per process: page-locking tens of MB costs milliseconds, far
-// more than the copy it serves, so renderers share it (resolve calls are serialised by the caller).
-static float* pinned_staging(size_t bytes) {
-    static float* buf = nullptr;
-    static size_t cap = 0;
-    if (bytes > cap) {
-        if (buf) cudaFreeHost(buf);
-        buf = nullptr;
-        cap = 0;
-        if (!cuda_ok(cudaMallocHost((void**)&buf, bytes), "cudaMallocHost(staging)", __FILE__, __LINE__)) return nullptr;
-        cap = bytes;
-    }
-    return buf;
+void* pinned_pool_alloc(size_t bytes) {
+    bytes = (bytes + 4095) & ~(size_t)4095;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    PoolBlock* best = nullptr;
+    for (PoolBlock& b : g_pinned)
+        if (!b.used && b.bytes >= bytes && (!best || b.bytes < best->bytes)) best = &b;
+    if (best) { best->used = true; return best->ptr; }
+    void* p = nullptr;
+    if (!cuda_ok(cudaMallocHost(&p, bytes), "cudaMallocHost(staging)", __FILE__, __LINE__)) return nullptr;
+    g_pinned.push_back({p, bytes, true, -1});
+    return p;
+}
+void pinned_pool_free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (PoolBlock& b : g_pinned)
+        if (b.ptr == p) { b.used = false; return; }
+    cudaFreeHost(p);
+}
+void trim_caches() {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    release_unused(g_pool, false);
+    release_unused(g_pinned, true);
 }
 
 static std::atomic<int> g_l2_windows{0};
@@ -115,12 +134,24 @@ struct DeviceRenderer {
     bool l2_window = false;         // this renderer holds a persisting-L2 window (set-aside released with the last one)
     void* d_state = nullptr;        // in-flight path records (R0 R1 P0 P1 L0 L1 carved out of one block)
     size_t state_bytes = 0;
-    unsigned char* d_rgb = nullptr; // resolve staging (device), 3 byte planes of one chunk
-    unsigned char* h_stage = nullptr;  // pinned: 3 byte planes of one chunk, or 3 float planes of the whole film (get_xyz)
+    unsigned char* d_rgb = nullptr; // resolve staging (device): 3 byte planes of the largest region resolved so far
+    size_t rgb_cap = 0;
+    unsigned char* h_stage = nullptr;  // pinned (owned by this renderer): 3 byte planes of a region, or 3 float planes of the whole film (get_xyz)
+    size_t stage_cap = 0;
+    std::mutex stage_mu;            // resolve / get_xyz may come from the consumer thread while another caller reads the film
+    int device = 0;                 // CUDA device everything above lives on; every entry point binds its calling thread to it
+    // multi-GPU film exchange (cfg.comm): slice of the raster this rank tonemaps after the reduce-scatter
+    size_t slice_cnt = 0;
+    unsigned char* d_gather = nullptr;   // rank 0: world x 3 x slice_cnt bytes
+    unsigned long long* d_sum = nullptr; // film checksum accumulator
+    bool exchanged = false;
+    cudaEvent_t ex0 = nullptr, ex1 = nullptr;
+    double exchange_ms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // stats
-    uint64_t launches = 0, iterations = 0, samples = 0, rays = 0;
+    std::atomic<uint64_t> launches{0};
+    uint64_t iterations = 0, samples = 0, rays = 0;
     double render_ms = 0, drain_ms = 0;
     bool slots_inited = false;
     size_t chunk_px = 0;
@@ -163,7 +194,10 @@ void collect_kernel_times(DeviceRenderer* r) {
 void device_renderer_destroy(DeviceRenderer* r) {
     if (!r) return;
     device_pool_free(r->d_cie); device_pool_free(r->d_bg); device_pool_free(r->d_tiles); device_pool_free(r->d_rays); device_pool_free(r->d_rgb);
-    device_pool_free(r->d_pass_log);
+    cudaSetDevice(r->device);
+    device_pool_free(r->d_pass_log); device_pool_free(r->d_gather); device_pool_free(r->d_sum); pinned_pool_free(r->h_stage);
+    if (r->ex0) cudaEventDestroy(r->ex0);
+    if (r->ex1) cudaEventDestroy(r->ex1);
     device_pool_free(r->d_cost); device_pool_free(r->d_drain); pixel_order_destroy(r->order);
     device_pool_free(r->d_state); device_pool_free(r->P.G0); device_pool_free(r->P.G1); device_pool_free(r->P.next_slot); device_pool_free(r->P.acc);
     if (r->l2_window) {  // hand the pinned L2 lines back; the last renderer also returns the set-aside to the normal cache
@@ -178,9 +212,29 @@ void device_renderer_destroy(DeviceRenderer* r) {
     delete r;
 }
 
+// grows the device / pinned staging of the tonemapped bytes to `bytes` (3 planes of a region)
+static bool ensure_staging(DeviceRenderer* r, size_t dev_bytes, size_t host_bytes) {
+    if (dev_bytes > r->rgb_cap) {
+        device_pool_free(r->d_rgb);
+        r->d_rgb = nullptr; r->rgb_cap = 0;
+        if (!device_pool_alloc((void**)&r->d_rgb, dev_bytes)) return false;
+        r->rgb_cap = dev_bytes;
+    }
+    if (host_bytes > r->stage_cap) {
+        pinned_pool_free(r->h_stage);
+        r->h_stage = nullptr; r->stage_cap = 0;
+        r->h_stage = (unsigned char*)pinned_pool_alloc(host_bytes);
+        if (!r->h_stage) return false;
+        r->stage_cap = host_bytes;
+    }
+    return true;
+}
+
 static bool renderer_setup(DeviceRenderer* r) {
     const RenderConfig& c = r->cfg;
     WaveParams& P = r->P;
+    SRT_CUDA(cudaGetDevice(&r->device));
+    if (c.comm && comm_device(c.comm) != r->device) { set_error("the communicator was created on another CUDA device"); return false; }
     P.nodes = device_scene_nodes(r->scene);
     P.tris = device_scene_tris(r->scene);
     P.flat_units = device_scene_flat_units(r->scene);
@@ -231,7 +285,18 @@ static bool renderer_setup(DeviceRenderer* r) {
         P.strat_recip = 1.0f / (float)P.strat_n;
     }
     P.s_begin = 0; P.s_end = P.spp; P.order = nullptr; P.n_order = 0; P.cost = nullptr; P.drain_clock = nullptr;
+    // film planes: W*H floats each; with a communicator the stride is padded to world equal slices (16-byte aligned)
+    // so that the in-place reduce-scatter hands rank r the pixels [r * slice_cnt, (r+1) * slice_cnt) of every plane
     P.plane = (size_t)P.img_w * P.img_h;
+    if (c.comm) {
+        const size_t world = (size_t)comm_world(c.comm);
+        r->slice_cnt = (((P.plane + world - 1) / world) + 3) & ~(size_t)3;
+        P.plane = r->slice_cnt * world;
+        SRT_CUDA(cudaEventCreate(&r->ex0));
+        SRT_CUDA(cudaEventCreate(&r->ex1));
+        if (!device_pool_alloc((void**)&r->d_gather, comm_rank(c.comm) == 0 ? world * 3 * r->slice_cnt : 3 * r->slice_cnt)) return false;
+    }
+    if (!device_pool_alloc((void**)&r->d_sum, sizeof(unsigned long long))) return false;
     const size_t ns = std::max<size_t>(P.nslots, 1);
     P.pass_log = nullptr;
     if (c.pass_log) {
@@ -254,11 +319,9 @@ static bool renderer_setup(DeviceRenderer* r) {
     SRT_CUDA(cudaMemsetAsync(P.acc, 0, 3 * P.plane * sizeof(float), r->stream));
     if (!device_pool_alloc((void**)&r->d_rays, sizeof(unsigned long long))) return false;
     SRT_CUDA(cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), r->stream));
-    const size_t chunk_px = (size_t)c.chunk_w * c.chunk_h;
-    if (!device_pool_alloc((void**)&r->d_rgb, 3 * chunk_px)) return false;
-    r->h_stage = (unsigned char*)pinned_staging(3 * chunk_px);
+    const size_t chunk_px = std::min((size_t)c.chunk_w * c.chunk_h, (size_t)P.img_w * P.img_h);
     r->chunk_px = chunk_px;
-    if (!r->h_stage) return false;
+    if (!ensure_staging(r, 3 * chunk_px, 3 * chunk_px)) return false;
     std::vector<float> cie(3 * SRT_NS);
     for (int k = 0; k < 3; k++) memcpy(cie.data() + k * SRT_NS, cie_table(k), SRT_NS * sizeof(float));
     if (!device_pool_alloc((void**)&r->d_cie, cie.size() * sizeof(float))) return false;
@@ -362,7 +425,9 @@ DeviceRenderer* device_renderer_create(const DeviceScene* scene, const RenderCon
 }
 
 bool device_renderer_render_chunk(DeviceRenderer* r, unsigned off_x, unsigned off_y, unsigned w, unsigned h) {
+    SRT_CUDA(cudaSetDevice(r->device));  // the CUDA device is per host thread: the render_cycle() worker starts on device 0
     WaveParams P = r->P;
+    r->exchanged = false;
     const LaunchTable& T = table(r->cfg.fp_strict);
     cudaStream_t st = r->stream;
     P.off_x = off_x; P.off_y = off_y; P.cw = w; P.ch = h;
@@ -450,37 +515,19 @@ bool device_renderer_render_chunk(DeviceRenderer* r, unsigned off_x, unsigned of
     return true;
 }
 
-bool device_renderer_resolve(DeviceRenderer* r, unsigned off_x, unsigned off_y, unsigned w, unsigned h, float* fr, float* fg, float* fb,
-                             unsigned img_w, unsigned img_h) {
-    const LaunchTable& T = table(r->cfg.fp_strict);
-    const size_t n = (size_t)w * h;
-    if (n > r->chunk_px) {  // whole-image resolve after a chunked / reduced render: go band by band
-        const unsigned rows = std::max(1u, (unsigned)(r->chunk_px / w));
-        for (unsigned y = 0; y < h; y += rows)
-            if (!device_renderer_resolve(r, off_x, off_y + y, w, std::min(rows, h - y), fr, fg, fb, img_w, img_h)) return false;
-        return true;
-    }
-    T.resolve(r->P.acc, r->P.plane, r->P.img_w, off_x, off_y, w, h, r->P.spp, r->d_rgb, r->stream);
-    r->launches++; count_launch();
-    r->cat_launches[3]++;
-    SRT_CUDA_LAST();
-    r->h_stage = (unsigned char*)pinned_staging(3 * n);
-    if (!r->h_stage) return false;
-    SRT_CUDA(cudaMemcpyAsync(r->h_stage, r->d_rgb, 3 * n, cudaMemcpyDeviceToHost, r->stream));
-    SRT_CUDA(cudaStreamSynchronize(r->stream));
-    float* dst[3] = {fr, fg, fb};
-    const unsigned char* stage = r->h_stage;
-    auto widen = [&](unsigned y0, unsigned y1) {  // frame_buffer holds 0..255 as float (frame_buffer.cuh:6-44)
+// frame_buffer holds 0..255 as float (frame_buffer.cuh:6-44): widen `count` bytes per channel into the caller's planes
+static void widen_rows(const unsigned char* stage, size_t stage_plane, float* const dst[3], unsigned off_x, unsigned off_y, unsigned w, unsigned h, unsigned img_w) {
+    auto widen = [&](unsigned y0, unsigned y1) {
         for (int c = 0; c < 3; c++) {
             if (!dst[c]) continue;
             for (unsigned y = y0; y < y1; y++) {
-                const unsigned char* src = stage + c * n + (size_t)y * w;
+                const unsigned char* src = stage + c * stage_plane + (size_t)y * w;
                 float* o = dst[c] + (size_t)(off_y + y) * img_w + off_x;
                 for (unsigned x = 0; x < w; x++) o[x] = (float)src[x];
             }
         }
     };
-    if (n >= (1u << 18)) {  // big chunks: the 4x wider float planes are written by several host threads, one band of rows each
+    if ((size_t)w * h >= (1u << 18)) {  // big regions: the 4x wider float planes are written by several host threads, one band of rows each
         const unsigned nt = std::max(1u, std::min({8u, std::thread::hardware_concurrency(), h}));
         std::vector<std::thread> pool;
         for (unsigned k = 1; k < nt; k++) pool.emplace_back(widen, (unsigned)((uint64_t)h * k / nt), (unsigned)((uint64_t)h * (k + 1) / nt));
@@ -489,29 +536,150 @@ bool device_renderer_resolve(DeviceRenderer* r, unsigned off_x, unsigned off_y, 
     } else {
         widen(0, h);
     }
+}
+
+bool device_renderer_resolve(DeviceRenderer* r, unsigned off_x, unsigned off_y, unsigned w, unsigned h, float* fr, float* fg, float* fb,
+                             unsigned img_w, unsigned img_h) {
+    SRT_CUDA(cudaSetDevice(r->device));
+    const LaunchTable& T = table(r->cfg.fp_strict);
+    const size_t n = (size_t)w * h;
+    if (n == 0) return true;
+    std::lock_guard<std::mutex> lock(r->stage_mu);
+    if (!ensure_staging(r, 3 * n, 3 * n)) return false;  // a whole-image resolve after a chunked / reduced render grows the buffers once
+    T.resolve(r->P.acc, r->P.plane, r->P.img_w, off_x, off_y, w, h, r->P.spp, r->d_rgb, r->stream);
+    r->launches++; count_launch();
+    SRT_CUDA_LAST();
+    SRT_CUDA(cudaMemcpyAsync(r->h_stage, r->d_rgb, 3 * n, cudaMemcpyDeviceToHost, r->stream));
+    SRT_CUDA(cudaStreamSynchronize(r->stream));
+    float* const dst[3] = {fr, fg, fb};
+    widen_rows(r->h_stage, n, dst, off_x, off_y, w, h, img_w);
     return true;
 }
 
-// pre-tonemap film: XYZ sums -> mean, with the same float operation as the kernels ((1/spp) * v)
+// Multi-GPU film exchange (north_star: "per-GPU film buffers combined by an NCCL reduce/gather over NVLink"):
+//   1. in-place reduce-scatter (sum) of the three XYZ planes: rank r then owns pixels [r*cnt, (r+1)*cnt) of the raster
+//      (every pixel was rendered by exactly one rank and is +0 elsewhere, so the sums are the single-GPU bits);
+//   2. every rank tonemaps its slice (1/world of the pixels) to bytes;
+//   3. the byte slices are gathered on rank 0 (send/recv), copied to the host and widened into the caller's planes.
+// Rank 0 therefore touches 1/world of the floats and W*H*3 bytes; nothing but bytes crosses PCIe.
+bool device_renderer_exchange_film(DeviceRenderer* r, float* fr, float* fg, float* fb, unsigned img_w, unsigned img_h) {
+    SRT_CUDA(cudaSetDevice(r->device));
+    Comm* c = r->cfg.comm;
+    if (!c) { set_error("no communicator attached (srt_rm_set_comm)"); return false; }
+    const LaunchTable& T = table(r->cfg.fp_strict);
+    const size_t world = (size_t)comm_world(c), rank = (size_t)comm_rank(c), cnt = r->slice_cnt, npx = (size_t)r->P.img_w * r->P.img_h;
+    const size_t first = rank * cnt;
+    const uint32_t count = first < npx ? (uint32_t)std::min(cnt, npx - first) : 0u;
+    std::lock_guard<std::mutex> lock(r->stage_mu);
+    if (!ensure_staging(r, 3 * cnt, rank == 0 ? world * 3 * cnt : 0)) return false;
+    cudaStream_t st = r->stream;
+    SRT_CUDA(cudaEventRecord(r->ex0, st));
+    if (!comm_film_reduce_scatter(c, r->P.acc, r->P.plane, cnt, st)) return false;
+    T.resolve_slice(r->P.acc, r->P.plane, first, count, (uint32_t)cnt, r->P.spp, r->d_rgb, st);
+    if (count) { r->launches++; count_launch(); }
+    SRT_CUDA_LAST();
+    if (!comm_gather_bytes(c, r->d_rgb, r->d_gather, 3 * cnt, st)) return false;
+    if (rank == 0) SRT_CUDA(cudaMemcpyAsync(r->h_stage, r->d_gather, world * 3 * cnt, cudaMemcpyDeviceToHost, st));
+    SRT_CUDA(cudaEventRecord(r->ex1, st));
+    SRT_CUDA(cudaEventSynchronize(r->ex1));
+    float ms = 0;
+    SRT_CUDA(cudaEventElapsedTime(&ms, r->ex0, r->ex1));
+    r->exchange_ms += ms;
+    r->exchanged = true;
+    if (rank == 0) {  // slices are runs of the raster: widen them as one-row regions
+        float* const planes[3] = {fr, fg, fb};
+        auto widen = [&](size_t k) {
+            const size_t f = k * cnt;
+            if (f >= npx) return;
+            const size_t n = std::min(cnt, npx - f);
+            for (int ch = 0; ch < 3; ch++) {
+                if (!planes[ch]) continue;
+                const unsigned char* src = r->h_stage + (k * 3 + ch) * cnt;
+                float* o = planes[ch] + f;
+                for (size_t i = 0; i < n; i++) o[i] = (float)src[i];
+            }
+        };
+        if (npx >= (1u << 18) && world > 1) {
+            std::vector<std::thread> pool;
+            for (size_t k = 1; k < world; k++) pool.emplace_back(widen, k);
+            widen(0);
+            for (std::thread& th : pool) th.join();
+        } else {
+            for (size_t k = 0; k < world; k++) widen(k);
+        }
+    }
+    return true;
+}
+
+// Order-independent 64-bit checksum of the XYZ-sum film: sum over (plane, pixel) of a mix of the index and the float's
+// bits.  After an exchange every rank sums its own slice and one all-reduce makes the value common to all ranks; it
+// equals the value a single GPU computes over its whole film exactly when the films agree bit for bit.
+__global__ void __launch_bounds__(256) k_film_checksum(const float* __restrict__ acc, size_t plane, size_t npx, size_t first, size_t count,
+                                                       unsigned long long* __restrict__ out) {
+    unsigned long long sum = 0;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < 3 * count; j += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = j / count, i = first + (j - c * count);
+        unsigned long long z = ((unsigned long long)(c * npx + i) << 32) | __float_as_uint(acc[c * plane + i]);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;  // SplitMix64 finaliser
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        sum += z ^ (z >> 31);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(out, sum);
+}
+bool device_renderer_film_checksum(DeviceRenderer* r, uint64_t* out) {
+    SRT_CUDA(cudaSetDevice(r->device));
+    Comm* c = r->cfg.comm;
+    const size_t npx = (size_t)r->P.img_w * r->P.img_h;
+    size_t first = 0, count = npx;
+    if (c) {
+        if (!r->exchanged) { set_error("film checksum with a communicator attached needs srt_rm_exchange_film first"); return false; }
+        first = (size_t)comm_rank(c) * r->slice_cnt;
+        count = first < npx ? std::min(r->slice_cnt, npx - first) : 0;
+    }
+    SRT_CUDA(cudaMemsetAsync(r->d_sum, 0, sizeof(unsigned long long), r->stream));
+    if (count) {
+        k_film_checksum<<<(unsigned)std::min<size_t>((3 * count + 255) / 256, 148 * 8), 256, 0, r->stream>>>(r->P.acc, r->P.plane, npx, first, count, r->d_sum);
+        r->launches++; count_launch();
+        SRT_CUDA_LAST();
+    }
+    if (c && !comm_all_reduce_u64_sum(c, r->d_sum, 1, r->stream)) return false;
+    unsigned long long h = 0;
+    SRT_CUDA(cudaMemcpyAsync(&h, r->d_sum, sizeof h, cudaMemcpyDeviceToHost, r->stream));
+    SRT_CUDA(cudaStreamSynchronize(r->stream));
+    *out = h;
+    return true;
+}
+
+// pre-tonemap film: XYZ sums -> mean, with the same float operation as the kernels ((1/spp) * v).  After an exchange
+// the call is collective: the slices are all-gathered first so that every rank reads the whole reduced film.
 bool device_renderer_download_xyz(DeviceRenderer* r, float* xyz) {
-    const size_t n = 3 * r->P.plane;
-    float* stage = pinned_staging(n * sizeof(float));
-    if (!stage) return false;
-    SRT_CUDA(cudaMemcpyAsync(stage, r->P.acc, n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    SRT_CUDA(cudaSetDevice(r->device));
+    const size_t npx = (size_t)r->P.img_w * r->P.img_h;
+    std::lock_guard<std::mutex> lock(r->stage_mu);
+    if (!ensure_staging(r, 0, 3 * npx * sizeof(float))) return false;
+    if (r->cfg.comm && r->exchanged && !comm_film_all_gather(r->cfg.comm, r->P.acc, r->P.plane, r->slice_cnt, r->stream)) return false;
+    float* stage = (float*)r->h_stage;
+    for (int c = 0; c < 3; c++)
+        SRT_CUDA(cudaMemcpyAsync(stage + c * npx, r->P.acc + c * r->P.plane, npx * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
     SRT_CUDA(cudaStreamSynchronize(r->stream));
     const float inv = 1 / (float)r->P.spp;
-    for (size_t i = 0; i < n; i++) xyz[i] = inv * stage[i];
+    for (size_t i = 0; i < 3 * npx; i++) xyz[i] = inv * stage[i];
     return true;
 }
 
 float* device_renderer_film(DeviceRenderer* r) { return r->P.acc; }
 bool device_renderer_pass_log(DeviceRenderer* r, uint32_t* out) {
+    SRT_CUDA(cudaSetDevice(r->device));
     if (!r->d_pass_log) { set_error("SRT_OPT_PASS_LOG was not set"); return false; }
     SRT_CUDA(cudaMemcpy(out, r->d_pass_log, (size_t)SRT_PASS_LOG_BLOCKS * SRT_PASS_LOG_PASSES * sizeof(uint4), cudaMemcpyDeviceToHost));
     return true;
 }
 
 bool device_renderer_reset(DeviceRenderer* r) {  // back to the state right after creation: empty film, unseeded RNG slots
+    SRT_CUDA(cudaSetDevice(r->device));
+    r->exchanged = false; r->exchange_ms = 0;
     SRT_CUDA(cudaMemsetAsync(r->P.acc, 0, 3 * r->P.plane * sizeof(float), r->stream));
     SRT_CUDA(cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), r->stream));
     SRT_CUDA(cudaStreamSynchronize(r->stream));
@@ -529,6 +697,7 @@ void device_renderer_stats(const DeviceRenderer* r, srt_stats* s) {
     s->wavefront_launches = r->iterations;
     s->rounds = r->round_end.size();
     s->drain_ms = r->drain_ms;
+    s->exchange_ms = r->exchange_ms;
     s->render_ms = r->render_ms;
     s->lbvh_ms = device_scene_lbvh_ms(r->scene);
     s->order_ms = r->cat_ms[0]; s->wavefront_ms = r->cat_ms[1]; s->megakernel_ms = r->cat_ms[2]; s->other_ms = r->cat_ms[3];

@@ -857,24 +857,34 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_megakernel(WaveParams P) {
     if (P.ray_counter && rays) atomicAdd(P.ray_counter, rays);
 }
 
-// film: XYZ sum / spp -> sRGB 0..255 (save_to_fb rendering.cu:140-149, color.cu:15-49), raster order
+// film: XYZ sum / spp -> sRGB 0..255 (save_to_fb rendering.cu:140-149, color.cu:15-49)
+__device__ __forceinline__ void tonemap_pixel(const float* __restrict__ acc, size_t plane, size_t pix, uint32_t spp, unsigned char* __restrict__ out_rgb,
+                                              size_t out_plane, size_t out_i) {
+    const float inv = 1 / (float)spp;  // pixel_color / float(spp) = (1/spp) * v
+    const float X = inv * acc[pix], Y = inv * acc[plane + pix], Z = inv * acc[2 * plane + pix];
+    const float m[9] = {3.2404542f, -1.5371385f, -0.4985314f, -0.9692660f, 1.8760108f, 0.0415560f, 0.0556434f, -0.2040259f, 1.0572252f};
+    const float lin[3] = {(m[0] * X) + (m[1] * Y) + (m[2] * Z), (m[3] * X) + (m[4] * Y) + (m[5] * Z), (m[6] * X) + (m[7] * Y) + (m[8] * Z)};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float v = lin[c];
+        const float g = v < 0.0f ? 0.0f : (v < 0.0031308f ? 12.92f * v : (v < 1.0f ? ((1.055f * powf(v, 0.416666f)) - 0.055f) : 1.0f));
+        out_rgb[c * out_plane + out_i] = (unsigned char)(int)(g * 255.99f);  // 0..255: one byte per channel crosses PCIe, the host widens it
+    }
+}
+// a rectangle of the film, raster order (one chunk, or the whole image)
 __global__ void k_resolve(const float* __restrict__ acc, size_t plane, uint32_t img_w, uint32_t off_x, uint32_t off_y, uint32_t w, uint32_t h,
                           uint32_t spp, unsigned char* __restrict__ out_rgb) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w * h) return;
     const uint32_t cy = i / w, cx = i - cy * w;
-    const size_t pix = (size_t)(off_y + cy) * img_w + (off_x + cx);
-    const float inv = 1 / (float)spp;  // pixel_color / float(spp) = (1/spp) * v
-    const float X = inv * acc[pix], Y = inv * acc[plane + pix], Z = inv * acc[2 * plane + pix];
-    const float m[9] = {3.2404542f, -1.5371385f, -0.4985314f, -0.9692660f, 1.8760108f, 0.0415560f, 0.0556434f, -0.2040259f, 1.0572252f};
-    const float lin[3] = {(m[0] * X) + (m[1] * Y) + (m[2] * Z), (m[3] * X) + (m[4] * Y) + (m[5] * Z), (m[6] * X) + (m[7] * Y) + (m[8] * Z)};
-    const size_t n = (size_t)w * h;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        const float v = lin[c];
-        const float g = v < 0.0f ? 0.0f : (v < 0.0031308f ? 12.92f * v : (v < 1.0f ? ((1.055f * powf(v, 0.416666f)) - 0.055f) : 1.0f));
-        out_rgb[c * n + i] = (unsigned char)(int)(g * 255.99f);  // 0..255: one byte per channel crosses PCIe, the host widens it
-    }
+    tonemap_pixel(acc, plane, (size_t)(off_y + cy) * img_w + (off_x + cx), spp, out_rgb, (size_t)w * h, i);
+}
+// pixels [first, first + count) of the raster: the slice a rank owns after the film reduce-scatter (renderer.cu)
+__global__ void k_resolve_slice(const float* __restrict__ acc, size_t plane, size_t first, uint32_t count, uint32_t out_plane, uint32_t spp,
+                                unsigned char* __restrict__ out_rgb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    tonemap_pixel(acc, plane, first + i, spp, out_rgb, out_plane, i);
 }
 
 // Standalone closest-hit queries (BASELINE.json configs[3]); the scene stays in global memory.
@@ -992,6 +1002,9 @@ LaunchTable make_launch_table() {
     t.megakernel = [](const WaveParams& P, int mode, int grid, size_t smem, cudaStream_t st) { SRT_DISPATCH(k_megakernel, mode, grid, smem, st, P); };
     t.resolve = [](const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,
                    cudaStream_t st) { k_resolve<<<(w * h + 255) / 256, 256, 0, st>>>(acc, plane, img_w, ox, oy, w, h, spp, rgb); };
+    t.resolve_slice = [](const float* acc, size_t plane, size_t first, uint32_t count, uint32_t out_plane, uint32_t spp, unsigned char* rgb, cudaStream_t st) {
+        if (count) k_resolve_slice<<<(count + 255) / 256, 256, 0, st>>>(acc, plane, first, count, out_plane, spp, rgb);
+    };
     t.trace_rays = [](const WaveParams& P, uint32_t n, const float* o, const float* d, const uint32_t* sorted_idx, float* t_out, int32_t* tri_out,
                       unsigned long long* counters, uint32_t* next_ray, int grid, cudaStream_t st) {
         cudaMemsetAsync(next_ray, 0, sizeof(uint32_t), st);

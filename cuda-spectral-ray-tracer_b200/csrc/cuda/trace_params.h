@@ -79,6 +79,7 @@ struct LaunchTable {
     void (*megakernel)(const WaveParams&, int mode, int grid, size_t smem, cudaStream_t);
     void (*resolve)(const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,
                     cudaStream_t);
+    void (*resolve_slice)(const float* acc, size_t plane, size_t first, uint32_t count, uint32_t out_plane, uint32_t spp, unsigned char* rgb, cudaStream_t);
     void (*trace_rays)(const WaveParams&, uint32_t n, const float* o, const float* d, const uint32_t* sorted_idx, float* t_out, int32_t* tri_out,
                        unsigned long long* counters, uint32_t* next_ray, int grid, cudaStream_t);
 };

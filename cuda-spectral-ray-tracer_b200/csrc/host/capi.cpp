@@ -10,6 +10,7 @@ struct srt_params { Params* p; };
 struct srt_camera_builder { CameraBuilder b; };
 struct srt_scene { Scene s; };
 struct srt_render_manager { RenderManager* rm; };
+struct srt_comm { Comm* c; };
 
 static srt_params g_params_handle{nullptr};
 static bool g_ref_compat = true;
@@ -213,6 +214,25 @@ int srt_rm_resolve_film(srt_render_manager* h) { return h->rm->resolve_film(); }
 int srt_rm_restart(srt_render_manager* h) { return h->rm->restart(); }
 int srt_rm_get_pass_log(srt_render_manager* h, uint32_t* out) { return out ? h->rm->get_pass_log(out) : SRT_ERR_ARG; }
 int srt_rm_get_stats(const srt_render_manager* h, srt_stats* out) { return out ? h->rm->stats(out) : SRT_ERR_ARG; }
+
+int srt_comm_get_unique_id(unsigned char* id) { return id && comm_unique_id(id) ? SRT_OK : SRT_ERR_CUDA; }
+srt_comm* srt_comm_create(const unsigned char* id, int rank, int world) {
+    if (!id) { set_error("null unique id"); return nullptr; }
+    Comm* c = comm_create(id, rank, world);
+    if (!c) return nullptr;
+    auto* h = new srt_comm();
+    h->c = c;
+    return h;
+}
+void srt_comm_destroy(srt_comm* h) { if (h) { comm_destroy(h->c); delete h; } }
+int srt_comm_rank(const srt_comm* h) { return comm_rank(h->c); }
+int srt_comm_world(const srt_comm* h) { return comm_world(h->c); }
+int srt_comm_max_double(srt_comm* h, double* v) { return h && v && comm_max_double(h->c, v) ? SRT_OK : SRT_ERR_CUDA; }
+int srt_nccl_version(void) { return comm_nccl_version(); }
+int srt_rm_set_comm(srt_render_manager* h, srt_comm* c) { return h->rm->set_comm(c ? c->c : nullptr); }
+int srt_rm_exchange_film(srt_render_manager* h) { return h->rm->exchange_film(); }
+int srt_rm_film_checksum(srt_render_manager* h, uint64_t* out) { return out ? h->rm->film_checksum(out) : SRT_ERR_ARG; }
+void srt_trim_caches(void) { trim_caches(); }
 
 double srt_measure_fp32_tflops(void) { return measure_fp32_tflops(); }
 double srt_measure_copy_gbs(uint32_t mbytes) { return measure_copy_gbs(mbytes); }

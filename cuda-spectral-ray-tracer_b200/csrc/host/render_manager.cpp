@@ -61,6 +61,23 @@ int RenderManager::set_option(int opt, int value) {
     return SRT_OK;
 }
 
+int RenderManager::set_comm(Comm* comm) {
+    if (device_inited_) { set_error("the communicator must be attached before init_device_params"); return SRT_ERR_STATE; }
+    cfg_.comm = comm;
+    cfg_.rank = comm ? comm_rank(comm) : 0;
+    cfg_.world = comm ? comm_world(comm) : 1;
+    return SRT_OK;
+}
+int RenderManager::exchange_film() {
+    end_render();
+    if (!dev_) { set_error("render manager: not initialised"); return SRT_ERR_STATE; }
+    return device_renderer_exchange_film(dev_, fb_r_, fb_g_, fb_b_, cam_.width, cam_.height) ? SRT_OK : SRT_ERR_CUDA;
+}
+int RenderManager::film_checksum(uint64_t* out) {
+    if (!dev_) { set_error("render manager: not initialised"); return SRT_ERR_STATE; }
+    return device_renderer_film_checksum(dev_, out) ? SRT_OK : SRT_ERR_CUDA;
+}
+
 int RenderManager::init_device_params(unsigned cw, unsigned ch) {  // render_manager.cu:68-119
     if (!renderer_inited_) {
         std::cerr << "Init renderer before assigning device parameters" << std::endl;
@@ -139,7 +156,7 @@ int RenderManager::update_fb() {  // render_manager.cuh:68-142
     {
         std::unique_lock<std::mutex> lock(mu_);
         cv_.wait(lock, [&] { return slot->full || worker_rc_ < 0; });  // full.acquire()
-        if (!slot->full) return worker_rc_;
+        if (!slot->full) { set_error(worker_error_); return worker_rc_; }
     }
     // the film already is in raster order: the reference's block-linear un-swizzle (:88-133) has no counterpart
     const bool ok = device_renderer_resolve(dev_, slot->off_x, slot->off_y, slot->w, slot->h, fb_r_, fb_g_, fb_b_, cam_.width, cam_.height);
@@ -162,7 +179,7 @@ int RenderManager::render_cycle() {  // render_manager.cuh:160-167
         int rc;
         while ((rc = step()) > 0) {}
         if (rc < 0) {
-            { std::lock_guard<std::mutex> lock(mu_); worker_rc_ = rc; }
+            { std::lock_guard<std::mutex> lock(mu_); worker_rc_ = rc; worker_error_ = last_error(); }
             cv_.notify_all();
         }
     });

@@ -13,6 +13,8 @@
 #include "../common/srt_types.h"
 #include "../../../include/srt.h"
 
+typedef struct CUstream_st* cudaStream_t;  // as in driver_types.h: host files need not include the CUDA headers
+
 namespace srt {
 
 void set_error(const std::string& msg);
@@ -123,6 +125,21 @@ bool build_flat_leaf(const std::vector<HostTri>& tris, const std::vector<HostMat
                      double origin_l1_bound, FlatLeaf& out);
 
 // ---------------------------------------------------------------- device objects (defined in cuda/*.cu)
+struct Comm;            // NCCL communicator owned by libsrt (host/nccl_comm.cpp)
+bool comm_unique_id(unsigned char id[SRT_NCCL_UNIQUE_ID_BYTES]);
+Comm* comm_create(const unsigned char id[SRT_NCCL_UNIQUE_ID_BYTES], int rank, int world);
+void comm_destroy(Comm*);
+int comm_rank(const Comm*);
+int comm_world(const Comm*);
+int comm_device(const Comm*);
+int comm_nccl_version();
+bool comm_film_reduce_scatter(Comm*, float* acc, size_t plane_stride, size_t cnt, cudaStream_t);
+bool comm_film_all_gather(Comm*, float* acc, size_t plane_stride, size_t cnt, cudaStream_t);
+bool comm_gather_bytes(Comm*, const unsigned char* send, unsigned char* recv_all, size_t bytes, cudaStream_t);
+bool comm_all_reduce_u64_sum(Comm*, unsigned long long* dev, size_t n, cudaStream_t);
+bool comm_max_double(Comm*, double* v);
+void trim_caches();
+
 struct DeviceScene;     // triangles, materials, LBVH
 struct DeviceRenderer;  // per-pixel state, queues, film
 
@@ -154,6 +171,7 @@ struct RenderConfig {
     int l2_persist = 1;      // persisting-L2 window over the in-flight path state (SRT_OPT_L2_PERSIST)
     int traversal = 0;  // 0 auto (wide leaf when <= 64 triangles), 1 force LBVH walk in shared memory, 3 force LBVH walk in global memory
     int tile_w = 0, tile_h = 0, rank = 0, world = 1;  // tile 0x0 = pick automatically
+    Comm* comm = nullptr;    // multi-GPU film exchange (borrowed); rank / world then come from it
     float bg_spectrum[SRT_NS];
     int bg_is_zero = 1;
 };
@@ -165,6 +183,8 @@ bool device_renderer_render_chunk(DeviceRenderer*, unsigned off_x, unsigned off_
 bool device_renderer_resolve(DeviceRenderer*, unsigned off_x, unsigned off_y, unsigned w, unsigned h, float* r, float* g,
                              float* b, unsigned img_w, unsigned img_h);
 bool device_renderer_download_xyz(DeviceRenderer*, float* xyz);
+bool device_renderer_exchange_film(DeviceRenderer*, float* r, float* g, float* b, unsigned img_w, unsigned img_h);
+bool device_renderer_film_checksum(DeviceRenderer*, uint64_t* out);
 float* device_renderer_film(DeviceRenderer*);
 bool device_renderer_reset(DeviceRenderer*);
 bool device_renderer_pass_log(DeviceRenderer*, uint32_t* out);
@@ -198,6 +218,9 @@ public:
     int render_cycle();
     int end_render();
     int set_option(int opt, int value);
+    int set_comm(Comm* comm);
+    int exchange_film();
+    int film_checksum(uint64_t* out);
     int get_xyz(float* xyz);
     int get_pass_log(uint32_t* out) { return dev_ && device_renderer_pass_log(dev_, out) ? SRT_OK : SRT_ERR_STATE; }
     float* device_film();
@@ -227,6 +250,7 @@ private:
     std::thread worker_;
     bool worker_started_ = false;
     int worker_rc_ = 0;
+    std::string worker_error_;  // the worker's srt_last_error() text (the error string is per thread)
 };
 
 bool write_ppm(const char* path, const float* r, const float* g, const float* b, uint32_t w, uint32_t h);

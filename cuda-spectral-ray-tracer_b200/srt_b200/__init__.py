@@ -41,7 +41,7 @@ class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("wavefront_launches", C.c_uint64), ("rounds", C.c_uint64), ("render_ms", C.c_double), ("lbvh_ms", C.c_double),
                 ("wavefront_ms", C.c_double), ("megakernel_ms", C.c_double), ("order_ms", C.c_double), ("other_ms", C.c_double),
-                ("drain_ms", C.c_double)]
+                ("drain_ms", C.c_double), ("exchange_ms", C.c_double)]
 
 
 OPT_FP_MODE, OPT_PIPELINE, OPT_TILE_W, OPT_TILE_H, OPT_RANK, OPT_WORLD, OPT_KERNEL_TIMING, OPT_TRAVERSAL, OPT_BLOCK_SLOTS, OPT_BLOCK_THREADS, OPT_STRATIFIED, OPT_ROUNDS, OPT_L2_PERSIST, OPT_PASS_LOG, OPT_SCHED_FLAGS = 1, 2, 3, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16, 17
@@ -103,6 +103,16 @@ _SIGS = [
     ("srt_rm_restart", C.c_int, [_P]),
     ("srt_rm_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("srt_rm_get_pass_log", C.c_int, [_P, _P]),
+    ("srt_comm_get_unique_id", C.c_int, [_P]),
+    ("srt_comm_create", _P, [_P, C.c_int, C.c_int]),
+    ("srt_comm_destroy", None, [_P]),
+    ("srt_comm_rank", C.c_int, [_P]), ("srt_comm_world", C.c_int, [_P]),
+    ("srt_comm_max_double", C.c_int, [_P, C.POINTER(C.c_double)]),
+    ("srt_nccl_version", C.c_int, []),
+    ("srt_rm_set_comm", C.c_int, [_P, _P]),
+    ("srt_rm_exchange_film", C.c_int, [_P]),
+    ("srt_rm_film_checksum", C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    ("srt_trim_caches", None, []),
     ("srt_measure_fp32_tflops", C.c_double, []),
     ("srt_measure_copy_gbs", C.c_double, [C.c_uint32]),
     ("srt_write_ppm", C.c_int, [C.c_char_p, _P, _P, _P, C.c_uint32, C.c_uint32]),
@@ -276,6 +286,40 @@ class Scene:
         return t, tri, ms.value
 
 
+class Comm:
+    """NCCL communicator owned by libsrt (one process per GPU).  Rank 0 calls Comm.unique_id() and hands the 128 bytes
+    to the other ranks out of band; then every rank calls Comm(id, rank, world) after srt_set_device."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        _check(lib().srt_comm_get_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, uid, rank, world):
+        buf = (C.c_ubyte * 128)(*uid)
+        self.h = lib().srt_comm_create(buf, rank, world)
+        if not self.h:
+            raise SrtError(lib().srt_last_error().decode())
+        self.rank, self.world = rank, world
+
+    def __del__(self):
+        self.close()
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().srt_comm_destroy(self.h)
+            self.h = None
+
+    def max(self, v):
+        d = C.c_double(v)
+        _check(lib().srt_comm_max_double(self.h, C.byref(d)))
+        return d.value
+
+    def barrier(self):
+        self.max(0.0)
+
+
 class FrameBuffer:
     """frame_buffer (reference rendering/frame_buffer.cuh): planar float32 R, G, B, raster order, 0..255."""
 
@@ -325,6 +369,18 @@ class RenderManager:
     def end_render(self): _check(lib().srt_rm_end_render(self.h))
     def render_all(self): _check(lib().srt_rm_render_all(self.h))
     def device_film(self): return lib().srt_rm_device_film(self.h)
+
+    def set_comm(self, comm):
+        self.comm = comm  # borrowed, keep alive
+        _check(lib().srt_rm_set_comm(self.h, comm.h if comm is not None else None))
+
+    def exchange_film(self): _check(lib().srt_rm_exchange_film(self.h))
+
+    def film_checksum(self):
+        v = C.c_uint64(0)
+        _check(lib().srt_rm_film_checksum(self.h, C.byref(v)))
+        return int(v.value)
+
     def resolve_film(self): _check(lib().srt_rm_resolve_film(self.h))
     def restart(self): _check(lib().srt_rm_restart(self.h))
 

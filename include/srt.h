@@ -199,7 +199,8 @@ int srt_rm_render_all(srt_render_manager*);
 #define SRT_OPT_TRAVERSAL 10     /* 0 auto (wide-leaf closest hit when the scene has <= 64 triangles), 1 force the LBVH walk
                                     (scene in shared memory), 3 force the LBVH walk with the scene in global memory */
 int srt_rm_set_option(srt_render_manager*, int option, int value);
-/* pre-tonemap film of the whole image: 3 raster planes of XYZ (mean over spp); downloaded on demand */
+/* pre-tonemap film of the whole image: 3 raster planes of XYZ (mean over spp); downloaded on demand.
+ * After srt_rm_exchange_film the call is collective (the reduced slices are all-gathered first). */
 int srt_rm_get_xyz(srt_render_manager*, float* xyz);
 /* device pointer to the XYZ SUM film (3 planes, W*H floats each, zeros outside owned tiles);
  * a caller that owns an NCCL communicator may reduce it in place and then call srt_rm_resolve_film */
@@ -220,11 +221,42 @@ typedef struct {
     /* ... and the end-of-launch drain of k_wavefront: last block exit minus the moment the first path slot
      * found no pixel left to fetch (device globaltimer), summed over launches */
     double drain_ms;
+    double exchange_ms; /* CUDA-event time of srt_rm_exchange_film calls (reduce-scatter + slice tonemap + gather + D2H) */
 } srt_stats;
 int srt_rm_get_stats(const srt_render_manager*, srt_stats* out);
 /* SRT_OPT_PASS_LOG read-out: out = 8 blocks x 8192 passes x 4 uint32 {globaltimer ns (low 32 bits), regenerate, lambertian,
  * metallic | dielectric << 16}; unused entries are zero */
 int srt_rm_get_pass_log(srt_render_manager*, uint32_t* out);
+
+/* ------------------------------------------------------------------ multi-GPU film exchange
+ * No reference counterpart (the reference is single-GPU); BASELINE.json north_star: "rendering shards by image
+ * tiles across the GPUs of one box, with per-GPU film buffers combined by an NCCL reduce/gather over NVLink".  One process per
+ * GPU; libsrt owns the NCCL communicator (libnccl.so.2 is opened on first use).  Rank 0 creates the id and hands its 128 bytes to
+ * the other ranks by any out-of-band channel (file, socket, MPI, torch.distributed ...). */
+#define SRT_NCCL_UNIQUE_ID_BYTES 128
+typedef struct srt_comm srt_comm;
+int srt_comm_get_unique_id(unsigned char id[SRT_NCCL_UNIQUE_ID_BYTES]);
+/* ncclCommInitRank on the current device (srt_set_device first); collective over all `world` ranks */
+srt_comm* srt_comm_create(const unsigned char id[SRT_NCCL_UNIQUE_ID_BYTES], int rank, int world);
+void srt_comm_destroy(srt_comm*);
+int srt_comm_rank(const srt_comm*);
+int srt_comm_world(const srt_comm*);
+/* *v = max over ranks of *v (device-timed milliseconds in bench.py); collective, doubles as a barrier */
+int srt_comm_max_double(srt_comm*, double* v);
+int srt_nccl_version(void); /* e.g. 22703; 0 when libnccl.so.2 cannot be loaded */
+/* attach before srt_rm_init_device_params: tile ownership (SRT_OPT_RANK / SRT_OPT_WORLD) follows the communicator and
+ * the film planes are laid out for the in-place reduce-scatter */
+int srt_rm_set_comm(srt_render_manager*, srt_comm*);
+/* collective, after the last srt_rm_step: reduce-scatter (sum) of the XYZ films, every rank tonemaps its 1/world of the
+ * pixels, the byte planes are gathered on rank 0 and land in rank 0's frame buffer.  Replaces srt_rm_update_fb /
+ * srt_rm_resolve_film in a multi-GPU render. */
+int srt_rm_exchange_film(srt_render_manager*);
+/* order-independent 64-bit checksum of the XYZ-sum film bits.  Without a communicator: of this manager's film.  With one
+ * (after srt_rm_exchange_film, collective): of the reduced film, the same value on every rank -- and equal to the
+ * single-GPU value exactly when the reduced film equals the single-GPU film bit for bit. */
+int srt_rm_film_checksum(srt_render_manager*, uint64_t* out);
+/* returns every cached, currently unused device / pinned block to the driver (the library keeps freed buffers for reuse) */
+void srt_trim_caches(void);
 
 /* measured FP32 FMA issue peak of the current device in TFLOP/s (dependent-free FFMA chains on every
  * SM, CUDA-event timed): the roofline denominator for the instruction-bound render kernels */

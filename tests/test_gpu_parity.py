@@ -352,6 +352,92 @@ def test_rounds_do_not_change_the_film(srt, strict):
         assert other[2]["rounds"] >= 2
 
 
+def _run_ranks(world, tmp_path, scene, w, h, spp, strict):
+    import subprocess
+    import sys
+
+    procs = [subprocess.Popen([sys.executable, str(ROOT / "tests" / "multigpu_worker.py"), str(r), str(world), str(tmp_path), str(scene), str(w), str(h), str(spp),
+                               str(strict)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    return [np.load(tmp_path / ("rank%d.npz" % r)) for r in range(world)]
+
+
+def test_film_exchange_single_rank_communicator(srt, tmp_path):
+    """srt_rm_exchange_film through a real NCCL communicator of one rank: reduce-scatter, slice tonemap and gather must reproduce
+    what update_fb / get_xyz deliver without a communicator, and the film checksum must agree"""
+    scene, w, h, spp = 2, 203, 117, 8  # odd size: the padded plane stride and the short last slice are on the path
+    rgb, xyz, _ = srt.render(scene_id=scene, w=w, h=h, spp=spp, bounce=10, strict=True)
+    sc = srt.Scene(scene)
+    fb = srt.FrameBuffer(w, h)
+    rm = srt.RenderManager(sc, sc.camera(w, h), fb)
+    rm.init_renderer(10, spp)
+    rm.set_option(srt.OPT_FP_MODE, 1)
+    rm.init_device_params(0, 0)
+    rm.render_all()
+    crc_plain = rm.film_checksum()
+    res = _run_ranks(1, tmp_path, scene, w, h, spp, 1)[0]
+    assert int(res["crc"]) == crc_plain
+    assert np.array_equal(res["rgb"], rgb)
+    assert np.array_equal(res["xyz"].view(np.uint32), xyz.view(np.uint32))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_film_exchange_multi_gpu_equals_single_gpu(srt, tmp_path, world):
+    """N ranks on N GPUs, libsrt's own NCCL communicator: the reduced film (checksum on every rank, XYZ bits, rank 0's sRGB frame
+    buffer) equals the single-GPU film bit for bit.  Needs N devices: run with `gpurun --gpus N`."""
+    if srt.lib().srt_device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    scene, w, h, spp = 0, 400, 225, 16
+    for strict in (1, 0):
+        rgb, xyz, _ = srt.render(scene_id=scene, w=w, h=h, spp=spp, bounce=10, strict=bool(strict))
+        sc = srt.Scene(scene)
+        fb = srt.FrameBuffer(w, h)
+        rm = srt.RenderManager(sc, sc.camera(w, h), fb)
+        rm.init_renderer(10, spp)
+        rm.set_option(srt.OPT_FP_MODE, strict)
+        rm.init_device_params(0, 0)
+        rm.render_all()
+        crc1 = rm.film_checksum()
+        d = tmp_path / ("s%d" % strict)
+        d.mkdir()
+        res = _run_ranks(world, d, scene, w, h, spp, strict)
+        assert [int(r["crc"]) for r in res] == [crc1] * world
+        assert sum(int(r["samples"]) for r in res) == w * h * spp
+        assert np.array_equal(res[0]["xyz"].view(np.uint32), xyz.view(np.uint32))
+        assert np.array_equal(res[0]["rgb"], rgb)
+
+
+def test_render_cycle_on_second_device(srt):
+    """the worker thread of render_cycle() must render on the device the manager was created on (the CUDA device is per thread)"""
+    if srt.lib().srt_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    base = srt.render(scene_id=1, w=96, h=54, spp=4, bounce=10, strict=True)
+    assert srt.lib().srt_set_device(1) == 0
+    try:
+        other = srt.render(scene_id=1, w=96, h=54, spp=4, bounce=10, strict=True)
+    finally:
+        srt.lib().srt_set_device(0)
+    assert np.array_equal(base[1].view(np.uint32), other[1].view(np.uint32))
+
+
+def test_whole_image_resolve_after_small_chunks(srt):
+    """srt_rm_resolve_film after a render whose chunks are smaller than one image row (16x16 chunks of a 400-wide image)"""
+    w, h, spp = 400, 48, 2
+    sc = srt.Scene(1)
+    fb = srt.FrameBuffer(w, h)
+    rm = srt.RenderManager(sc, sc.camera(w, h), fb)
+    rm.init_renderer(10, spp)
+    rm.set_option(srt.OPT_FP_MODE, 1)
+    rm.init_device_params(16, 16)
+    rm.render_all()
+    chunked = fb.rgb().copy()
+    fb.r[:] = 0; fb.g[:] = 0; fb.b[:] = 0
+    rm.resolve_film()
+    assert np.array_equal(fb.rgb(), chunked)
+
+
 def test_full_bench_size_bitwise_vs_oracle(srt):
     """The whole bench workload (BASELINE configs[1]: Cornell 1920x1080, 64 spp, depth 10; 435 M rays) in strict FP mode
     against the CPU oracle (which equals the real reference host build on this frame bit for bit, checked in the
