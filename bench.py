@@ -6,22 +6,31 @@
 
 Metric (BASELINE.json): spectral path samples/s.  One "step" = one full render of the workload.
 Workload at every N: BASELINE.json configs[1] -- reference Cornell scene (id 0), 1920x1080, 64 spp,
-depth 10 -- split over the ranks by interleaved image tiles (strong scaling), per-rank XYZ films
-summed with one NCCL reduce to rank 0 which tonemaps.  L2 is flushed before every timed step.
+depth 10 -- split over the ranks by interleaved image tiles (strong scaling).  One process per GPU;
+libsrt owns the NCCL communicator: the per-rank XYZ films are combined by srt_rm_exchange_film
+(reduce-scatter, per-rank slice tonemap, byte gather to rank 0).  torch.distributed (gloo) is used
+for ONE thing only: handing rank 0's NCCL unique id to the other ranks.  L2 is flushed before every
+timed step.
 
-  value      samples / device time, scene + state resident in HBM (CUDA events inside libsrt around
-             the render kernels; at N>1 plus the NCCL film reduce; max over ranks)
+  value      samples / device time, scene + state resident in HBM: per step the max over ranks of
+             (CUDA-event time of the render launches + CUDA-event time of the film reduce-scatter, after
+             which the summed film sits in HBM, 1/N of it on every rank), mean over the K steps.  The
+             tonemap + byte gather + device-to-host copy that follow are reported as film_out_ms and are
+             inside e2e (at N=1 value likewise ends with the film in HBM)
   e2e        the same metric through the public C-ABI with HOST buffers: every step uploads the scene
-             (host triangle build + H2D + LBVH build), renders, tonemaps and copies the film back into
-             caller-owned host planes; wall clock around the calls, barrier on both sides
+             (host triangle build + H2D + LBVH build), renders, exchanges / tonemaps and copies the film
+             back into caller-owned host planes; wall clock around the calls, barrier on both sides;
+             e2e_breakdown splits rank 0's step
   roofline   k_wavefront (the dominant kernel): algorithmic FLOPs (oracle op counters x the constants of
              SURVEY.md 8d) / its CUDA-event duration against the FP32 issue peak measured in this run
+  film_crc   checksum of the reduced XYZ film bits in strict FP mode (srt_rm_film_checksum): the same value
+             at every N exactly when the multi-GPU film equals the single-GPU film bit for bit
   cpu_baseline  the reference's own host-compiled code (oracle/_ref) or the C port (oracle/), timed on the
              box's host cores on a bounded sample of the same workload
-  c5, soup   extra, same N GPUs: BASELINE configs[4] (Cornell 3840x2160, 1024 spp) and whole renders of the
-             1M-triangle soup of configs[3] (1920x1080, 8 spp); 1 warm-up + 2 timed steps each
-  reference_cuda / strict_fp / lbvh   (N=1) the reference's CUDA renderer on this GPU, our -fmad=false kernels,
-             the 1M-triangle LBVH build and soup ray queries with their rooflines
+  c3, c5, soup   extra legs, same N GPUs: BASELINE configs[2] (Prism 1920x1080, 256 spp), configs[4]
+             (Cornell 3840x2160, 1024 spp) and whole renders of the 1M-triangle soup of configs[3]
+  reference_cuda / strict_fp / lbvh   (N=1) the reference's CUDA renderer on this GPU, our -fmad=false
+             kernels, LBVH builds of the 1M and 10M soups and soup ray queries with their rooflines
 """
 import argparse
 import json
@@ -96,7 +105,7 @@ class ClockSampler(threading.Thread):
 
 def cpu_reference_render(w, h, scene, spp, depth, threads=0):
     """One bounded CPU render with the reference's own code when oracle/_ref is there, else the C port.
-    Returns (seconds, kind, counters-or-None)."""
+    Returns (seconds, kind)."""
     import refhost
     import oracle
 
@@ -126,6 +135,11 @@ def cpu_reference_render(w, h, scene, spp, depth, threads=0):
     return time.perf_counter() - t0, "port"
 
 
+def workload_config(name, wl):
+    scene, w, h, spp, depth = wl
+    return {"workload": name, "scene": scene, "width": w, "height": h, "spp": spp, "depth": depth}
+
+
 def run_reference_arm(a, wl_name, wl):
     scene, w, h, spp, depth = wl
     rank = int(os.environ.get("RANK", "0"))
@@ -145,7 +159,7 @@ def run_reference_arm(a, wl_name, wl):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": wl_name, "scene": scene, "width": w, "height": h, "spp": spp, "depth": depth},
+        "config": workload_config(wl_name, wl),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -172,6 +186,26 @@ def reference_cuda_baseline(wl):
     return None
 
 
+def profile_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu captures (profiles/r2_traffic.json, key path a/b), or None"""
+    for f in ("r2_traffic.json", "r1_traffic.json"):
+        p = ROOT / "profiles" / f
+        if p.exists():
+            try:
+                v = json.loads(p.read_text())
+                for k in name.split("/"):
+                    v = v[k]
+                return v
+            except Exception:
+                continue
+    return None
+
+
+def l2_peak_gbs():
+    v = profile_traffic("l2_peak_gbs")
+    return float(v) if v else 20000.0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,9 +217,10 @@ def main():
     ap.add_argument("--strict", action="store_true", help="strict FP mode (-fmad=false kernels)")
     ap.add_argument("--tile-w", type=int, default=0, help="0 = library picks by pixels per rank")
     ap.add_argument("--tile-h", type=int, default=0)
+    ap.add_argument("--rounds", type=int, default=0, help="SRT_OPT_ROUNDS, 0 = automatic")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-c5", action="store_true", help="skip the extra BASELINE configs[4] measurement (4K, 1024 spp)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (c3, c5, soup renders, 10M soup)")
     a = ap.parse_args()
     # torchrun exports OMP_NUM_THREADS=1; the CPU reference legs must use every host core (the OpenMP
     # runtime reads the variable when the oracle library is loaded, which happens later)
@@ -199,133 +234,133 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # control plane only: rank 0's NCCL unique id travels to the other ranks over gloo.  torch is imported before
+        # libsrt.so so that the process carries ONE libnccl.so.2 (libsrt opens it by soname on first use).
+        import torch.distributed as dist
+
+        dist.init_process_group("gloo")
     import srt_b200 as S
 
     if S.lib().srt_device_count() == 0:
         raise SystemExit("bench.py: no CUDA device -- libsrt has no CPU fallback")
     S.lib().srt_set_device(local_rank)
-    dist = None
-    torch = None
+    comm = None
     if world > 1:
-        import torch
-        import torch.distributed as dist
+        box = [S.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = S.Comm(box[0], rank, world)  # ncclCommInitRank inside libsrt
+        dist.destroy_process_group()
 
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    launches0 = S.kernel_launch_count()
+    def barrier():
+        if comm:
+            comm.barrier()
+
+    def gmax(v):
+        return comm.max(float(v)) if comm else float(v)
+
+    def gmin(v):
+        return -comm.max(-float(v)) if comm else float(v)
+
+    def make_manager(scene_obj, w_, h_, spp_, d_, strict=False, timing=False):
+        fb_ = S.FrameBuffer(w_, h_)
+        rm_ = S.RenderManager(scene_obj, scene_obj.camera(w_, h_), fb_)
+        rm_.init_renderer(d_, spp_)
+        rm_.set_option(S.OPT_FP_MODE, 1 if strict else 0)
+        if timing:
+            rm_.set_option(S.OPT_KERNEL_TIMING, 1)
+        rm_.set_option(S.OPT_TILE_W, a.tile_w); rm_.set_option(S.OPT_TILE_H, a.tile_h)
+        rm_.set_option(S.OPT_ROUNDS, a.rounds)
+        if comm:
+            rm_.set_comm(comm)
+        rm_.init_device_params(0, 0)
+        return rm_, fb_
+
+    def resident_step(rm_):
+        """one step with scene and state resident: (device ms of this rank = render launches + film exchange, stats)"""
+        S.lib().srt_measure_copy_gbs(256)  # untimed 256 MB device copy (2x + 2x the 126 MB L2): evicts the previous step's film / RNG / path state
+        rm_.restart()
+        barrier()  # untimed: every rank starts its step together, so the exchange time is the collective, not start-up skew
+        while rm_.step():
+            pass
+        if comm:
+            rm_.exchange_film()
+        st_ = rm_.stats()
+        return st_["render_ms"] + st_["exchange_ms"], st_
+
+    def resident_leg(scene_obj, w_, h_, spp_, d_, warm=1, steps=2):
+        """device ms per step (mean over steps of the per-step max over ranks) of one more workload on the same N GPUs"""
+        rm_, fb_ = make_manager(scene_obj, w_, h_, spp_, d_)
+        ms_ = []
+        st_ = None
+        for i in range(warm + steps):
+            ms, st_ = resident_step(rm_)
+            ms = gmax(ms)
+            if i >= warm:
+                ms_.append(ms)
+        rays_per_sample = st_["rays"] / max(1, st_["samples"])
+        del rm_, fb_
+        return float(np.mean(ms_)), rays_per_sample
 
     # ---- resident-state arm: scene + render manager built once, every step re-renders the image
     sc = S.Scene(scene_id)
-    cam = sc.camera(w, h)
-    fb = S.FrameBuffer(w, h)
-    rm = S.RenderManager(sc, cam, fb)
-    rm.init_renderer(depth, spp)
-    rm.set_option(S.OPT_FP_MODE, 1 if a.strict else 0)
-    rm.set_option(S.OPT_KERNEL_TIMING, 1)
-    rm.set_option(S.OPT_TILE_W, a.tile_w); rm.set_option(S.OPT_TILE_H, a.tile_h)
-    if world > 1:
-        rm.set_option(S.OPT_RANK, rank); rm.set_option(S.OPT_WORLD, world)
-    rm.init_device_params(0, 0)
-    film = None
-    if world > 1:
-        class _Film:  # zero-copy view of libsrt's device film for torch.distributed
-            def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-        film = torch.as_tensor(_Film(rm.device_film(), 3 * w * h), device="cuda")
-
-    def one_step():
-        """returns device milliseconds of this rank (render kernels [+ film reduce])"""
-        S.lib().srt_measure_copy_gbs(256)  # untimed 256 MB device copy (2x + 2x the 126 MB L2): evicts the previous step's film / RNG / path state
-        rm.restart()
-        while rm.step():
-            pass
-        st = rm.stats()
-        ms = st["render_ms"]
-        if world > 1:
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
-            e1.record()
-            e1.synchronize()
-            ms += e0.elapsed_time(e1)
-        return ms, st
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
+    rm, fb = make_manager(sc, w, h, spp, depth, strict=a.strict, timing=True)
     for _ in range(a.warmup):
-        one_step()
+        resident_step(rm)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    dev_ms, kern_ms = [], []
+    step_ms, kern_ms, drain_ms, exch_ms, order_ms, out_ms = [], [], [], [], [], []
+    kmin, kmax = [], []
     st = None
     launches_timed0 = S.kernel_launch_count()
     for _ in range(a.steps):
-        ms, st = one_step()
-        dev_ms.append(ms)
-        kern_ms.append(st["wavefront_ms"] if st["wavefront_ms"] > 0 else st["render_ms"])
+        ms, st = resident_step(rm)
+        step_ms.append(gmax(ms))  # per-step max over ranks
+        k = st["wavefront_ms"] if st["wavefront_ms"] > 0 else st["render_ms"]
+        kern_ms.append(k); drain_ms.append(st["drain_ms"]); exch_ms.append(st["exchange_ms"]); order_ms.append(st["order_ms"]); out_ms.append(st["film_out_ms"])
+        kmin.append(gmin(st["render_ms"])); kmax.append(gmax(st["render_ms"]))
     launches = S.kernel_launch_count() - launches_timed0
     barrier()
     clocks = sampler.summary() if sampler else None
-    step_ms = float(np.mean(dev_ms))
-    if world > 1:
-        tmax = torch.tensor([step_ms], device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        step_ms = float(tmax.item())
-    if rank == 0:
+    ms_per_step = float(np.mean(step_ms))
+    if not comm and rank == 0:
         rm.resolve_film()
     total_samples = w * h * spp
-    value = total_samples / (step_ms * 1e-3)
+    value = total_samples / (ms_per_step * 1e-3)
+    rounds_used = st["rounds"]
 
-    # ---- BASELINE configs[4] next to the headline: Cornell 3840x2160, 1024 spp on the same N GPUs (device time incl.
-    # the film reduce, max over ranks).  Its per-pixel chains are 16x longer than C2's, so it shows how the tile split
-    # scales when the end-of-kernel drain is amortised; 1 warm-up + 2 timed steps keep it to seconds.
-    def resident_leg(scene_obj, w_, h_, spp_, d_, warm=1, steps=2):
-        """device ms per step (render [+ film reduce], max over ranks) of one more workload on the same N GPUs"""
-        fb_ = S.FrameBuffer(w_, h_)
-        rm_ = S.RenderManager(scene_obj, scene_obj.camera(w_, h_), fb_)
-        rm_.init_renderer(d_, spp_)
-        rm_.set_option(S.OPT_TILE_W, a.tile_w); rm_.set_option(S.OPT_TILE_H, a.tile_h)
-        if world > 1:
-            rm_.set_option(S.OPT_RANK, rank); rm_.set_option(S.OPT_WORLD, world)
-        rm_.init_device_params(0, 0)
-        film_ = torch.as_tensor(_Film(rm_.device_film(), 3 * w_ * h_), device="cuda") if world > 1 else None
-        ms_ = []
-        for i in range(warm + steps):
-            S.lib().srt_measure_copy_gbs(256)
-            rm_.restart()
-            while rm_.step():
-                pass
-            ms = rm_.stats()["render_ms"]
-            if world > 1:
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record()
-                dist.reduce(film_, dst=0, op=dist.ReduceOp.SUM)
-                e1.record()
-                e1.synchronize()
-                ms += e0.elapsed_time(e1)
-            if i >= warm:
-                ms_.append(ms)
-        m = float(np.mean(ms_))
-        rays_per_sample = rm_.stats()["rays"] / max(1, rm_.stats()["samples"])
-        if world > 1:
-            tmax = torch.tensor([m], device="cuda")
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            m = float(tmax.item())
-        del rm_, film_, fb_
-        return m, rays_per_sample
+    # ---- film checksum in strict FP mode (the mode whose film is bit-identical to the reference's host build): same value at every N
+    rm_c, fb_c = make_manager(sc, w, h, spp, depth, strict=True)
+    t_strict = []
+    n_strict = 1 if world > 1 else 2 + min(a.steps, 3)
+    for i in range(n_strict):
+        rm_c.restart()
+        while rm_c.step():
+            pass
+        if i >= 2 or world > 1:
+            t_strict.append(rm_c.stats()["render_ms"])
+    if comm:
+        rm_c.exchange_film()
+    film_crc = "%016x" % rm_c.film_checksum()
+    strict_info = None
+    if world == 1 and not a.strict:
+        strict_info = {"value": total_samples / (float(np.mean(t_strict)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(t_strict)),
+                       "what": "same workload, kernels built with -fmad=false: film bit-identical to the reference's host build (tests/test_gpu_parity.py)"}
+    del rm_c, fb_c
 
-    c5_info = None
-    soup_info = None
-    if wl_name == "c2" and not a.no_c5 and not a.strict:
+    # ---- extra legs on the same N GPUs
+    c3_info = c5_info = soup_info = None
+    if wl_name == "c2" and not a.no_extra and not a.strict:
+        s3, w3, h3, spp3, d3 = WORKLOADS["c3"]
+        m3, rps3 = resident_leg(S.Scene(s3), w3, h3, spp3, d3)
+        c3_info = dict(workload_config("c3", WORKLOADS["c3"]), value=w3 * h3 * spp3 / (m3 * 1e-3), unit=UNIT, ms_per_step=m3, steps=2, warmup=1, rays_per_sample=rps3,
+                       what="BASELINE configs[2] (Prism dispersion scene) on the same GPUs, device time incl. the film exchange, per-step max over ranks")
         s5, w5, h5, spp5, d5 = WORKLOADS["c5"]
         m5, _ = resident_leg(S.Scene(s5), w5, h5, spp5, d5)
-        c5_info = {"workload": "c5", "width": w5, "height": h5, "spp": spp5, "depth": d5, "value": w5 * h5 * spp5 / (m5 * 1e-3), "unit": UNIT,
-                   "ms_per_step": m5, "steps": 2, "warmup": 1, "what": "BASELINE configs[4] on the same GPUs, device time incl. the film reduce, max over ranks"}
+        c5_info = dict(workload_config("c5", WORKLOADS["c5"]), value=w5 * h5 * spp5 / (m5 * 1e-3), unit=UNIT, ms_per_step=m5, steps=2, warmup=1,
+                       what="BASELINE configs[4] on the same GPUs, device time incl. the film exchange, per-step max over ranks")
         # BASELINE configs[3] as a render: the seeded 1M-triangle soup (LBVH walk from global memory), 1920x1080, 8 spp
         soup_sc = S.Scene(soup=1 << 20, seed=1984)
         ms_s, rps = resident_leg(soup_sc, 1920, 1080, 8, 10)
@@ -334,93 +369,78 @@ def main():
                      "ms_per_step": ms_s, "steps": 2, "warmup": 1, "what": "whole renders of the 1M-triangle soup on the same GPUs (every rank holds the full LBVH)"}
         del soup_sc
 
-    # ---- the same resident-state measurement in strict FP mode (-fmad=false kernels: the mode whose film is
-    # bit-identical to the reference's host-compiled image); reported next to the headline, single GPU only
-    strict_info = None
-    if world == 1 and not a.strict:
-        fb_s = S.FrameBuffer(w, h)
-        rm_s = S.RenderManager(sc, cam, fb_s)
-        rm_s.init_renderer(depth, spp)
-        rm_s.set_option(S.OPT_FP_MODE, 1)
-        rm_s.set_option(S.OPT_TILE_W, a.tile_w); rm_s.set_option(S.OPT_TILE_H, a.tile_h)
-        rm_s.init_device_params(0, 0)
-        ms_s = []
-        for i in range(2 + min(a.steps, 3)):
-            rm_s.restart()
-            while rm_s.step():
-                pass
-            if i >= 2:
-                ms_s.append(rm_s.stats()["render_ms"])
-        strict_info = {"value": total_samples / (float(np.mean(ms_s)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ms_s)),
-                       "what": "same workload, kernels built with -fmad=false: film bit-identical to the reference's host build (tests/test_gpu_parity.py)"}
-        del rm_s
-
     # ---- end-to-end arm: host buffers in, host film out, every step
-    def e2e_step():
+    bd = {"scene_lbvh_ms": [], "init_ms": [], "render_ms": [], "film_out_ms": []}
+
+    fb2 = S.FrameBuffer(w, h)  # caller-owned host planes, reused from frame to frame like any application's frame buffer
+
+    def e2e_step(record):
+        t0 = time.perf_counter()
         sc2 = S.Scene(scene_id)  # host triangle/material build + H2D + device LBVH
-        fb2 = S.FrameBuffer(w, h)
+        t1 = time.perf_counter()
         rm2 = S.RenderManager(sc2, sc2.camera(w, h), fb2)
         rm2.init_renderer(depth, spp)
         rm2.set_option(S.OPT_FP_MODE, 1 if a.strict else 0)
         rm2.set_option(S.OPT_TILE_W, a.tile_w); rm2.set_option(S.OPT_TILE_H, a.tile_h)
-        if world > 1:
-            rm2.set_option(S.OPT_RANK, rank); rm2.set_option(S.OPT_WORLD, world)
+        rm2.set_option(S.OPT_ROUNDS, a.rounds)
+        if comm:
+            rm2.set_comm(comm)
         rm2.init_device_params(0, 0)
-        if world > 1:
-            while rm2.step():
-                pass
-            f2 = torch.as_tensor(_Film(rm2.device_film(), 3 * w * h), device="cuda")
-            dist.reduce(f2, dst=0, op=dist.ReduceOp.SUM)
-            torch.cuda.synchronize()
-            if rank == 0:
-                rm2.resolve_film()
+        t2 = time.perf_counter()
+        while rm2.step():
+            pass
+        t3 = time.perf_counter()
+        if comm:
+            rm2.exchange_film()  # reduce-scatter + slice tonemap + gather + D2H + widen into fb2 on rank 0
         else:
-            rm2.render_all()  # worker thread renders, caller thread resolves + copies D2H into fb2
-        return float(fb2.r.sum())
+            rm2.resolve_film()   # tonemap + D2H + widen into fb2
+        t4 = time.perf_counter()
+        if record:
+            bd["scene_lbvh_ms"].append((t1 - t0) * 1e3); bd["init_ms"].append((t2 - t1) * 1e3)
+            bd["render_ms"].append((t3 - t2) * 1e3); bd["film_out_ms"].append((t4 - t3) * 1e3)
+        return float(fb2.r[0])
 
-    e2e_warm = min(a.warmup, 2)
-    for _ in range(e2e_warm):
-        e2e_step()
+    for _ in range(min(a.warmup, 2)):
+        e2e_step(False)
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        e2e_step()
+        e2e_step(True)
     barrier()
-    e2e_s = (time.perf_counter() - t0) / a.steps
-    if world > 1:
-        tmax = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        e2e_s = float(tmax.item())
+    e2e_s = gmax((time.perf_counter() - t0) / a.steps)
     h2d = sc.ntris * (9 * 4 + 48) + sc.nmats * 416 + 4 * 95 * 4
     d2h = 3 * w * h  # the film crosses PCIe as one byte per channel (values are 0..255); the host widens it to float planes
 
+    nccl_version = S.lib().srt_nccl_version() if comm else 0
+    if comm:  # every rank leaves the communicator at the same point; what follows is rank 0's single-GPU and CPU work
+        comm.barrier()
+        del rm
+        rm = None
+        comm.close()
+        comm = None
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel
     import oracle
     fp32_peak = S.lib().srt_measure_fp32_tflops()
+    sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    fp32_nominal = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     cw, chh, cspp = 480, 270, 4  # bounded, deterministic counter sample of the same scene/camera
     _, _, cnt = oracle.render(oracle.Scene(scene_id), oracle.camera(cw, chh), cspp, depth, counters=True)
     fl_sample = algorithmic_flops_per_sample(cnt, spp)
     k_ms = float(np.mean(kern_ms))
     samples_rank = st["samples"]
     achieved = fl_sample * samples_rank / (k_ms * 1e-3) / 1e12
-    traffic = None
-    tfile = ROOT / "profiles" / "r1_traffic.json"
-    if tfile.exists():
-        try:
-            traffic = json.loads(tfile.read_text()).get(wl_name, {}).get("k_wavefront_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
     roofline = {"bound": "fp32", "kernel": "k_wavefront", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
-                "traffic": traffic, "peak_source": "measured in this run (srt_measure_fp32_tflops: FFMA chains on all SMs); MEASURED_PEAKS.json has no FP32 figure",
-                "algorithmic_flops_per_sample": fl_sample, "kernel_ms": k_ms, "rays_per_sample": st["rays"] / max(1, st["samples"])}
+                "traffic": profile_traffic(wl_name + "/k_wavefront_dram_bytes_per_step"),
+                "peak_source": "measured in this run (srt_measure_fp32_tflops: FFMA chains on all SMs); MEASURED_PEAKS.json has no FP32 figure",
+                "peak_nominal": fp32_nominal, "peak_nominal_source": "148 SMs x 128 FP32 lanes x 2 FLOP x %.0f MHz" % sm_mhz,
+                "algorithmic_flops_per_sample": fl_sample, "kernel_ms": k_ms, "launches_per_step": rounds_used,
+                "rays_per_sample": st["rays"] / max(1, st["samples"])}
 
-    # ---- LBVH build (second half of the BASELINE metric): 1M-triangle soup, device resident
-    del rm  # the renderer's persisting-L2 set-aside goes back to the normal cache before other kernels are timed
+    # ---- LBVH build (second half of the BASELINE metric): 1M- and 10M-triangle soups, device resident
+    rm = None  # the renderer's persisting-L2 set-aside goes back to the normal cache before other kernels are timed
     lb = None
     if world == 1:
         try:
@@ -428,12 +448,45 @@ def main():
             hbm = float(peaks["hbm_gbs"]); hbm_src = "MEASURED_PEAKS.json"
         except Exception:
             hbm = 6650.0; hbm_src = "fallback (B200_PROFILING.md)"
-        soup = S.Scene(soup=1 << 20, seed=1984)
-        soup.rebuild_lbvh(3)
-        ms = [soup.rebuild_lbvh(1)["total"] for _ in range(10)]
-        t = float(np.median(ms))
-        ach = 256.0 * (1 << 20) / (t * 1e-3) / 1e9
-        phases = soup.rebuild_lbvh(1)
+        l2_peak = l2_peak_gbs()
+
+        def lbvh_leg(n_tris, tag):
+            soup = S.Scene(soup=n_tris, seed=1984)
+            soup.rebuild_lbvh(3)
+            ms = [soup.rebuild_lbvh(1)["total"] for _ in range(10)]
+            t = float(np.median(ms))
+            ach = 256.0 * n_tris / (t * 1e-3) / 1e9
+            out = {"n_tris": n_tris, "build_ms": t, "phases_ms": soup.rebuild_lbvh(1),
+                   "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": profile_traffic("lbvh_%s/build_dram_bytes" % tag),
+                                "peak_source": hbm_src, "algorithmic_bytes_per_tri": 256}}
+            # BASELINE.json configs[3]: closest-hit rays/s through the device LBVH of the same soup
+            # (primary = the reference camera at 1920x1080, secondary = one random bounce off the primary hits)
+            cam_a = soup.camera(1920, 1080).as_array()
+            ys, xs = np.mgrid[0:1080, 0:1920]
+            d = (cam_a[8:11][None, :] + xs.reshape(-1, 1) * cam_a[2:5][None, :] + ys.reshape(-1, 1) * cam_a[5:8][None, :] - cam_a[12:15][None, :]).astype(np.float32)
+            o = np.tile(cam_a[12:15], (d.shape[0], 1)).astype(np.float32)
+            tt, tri, ms1, v1 = soup.trace_rays(o, d, counted=True)
+            hit = tri >= 0
+            rs = np.random.RandomState(1)
+            d2 = rs.randn(int(hit.sum()), 3).astype(np.float32)
+            o2 = (o[hit] + tt[hit, None] * d[hit] + 1e-3 * d2).astype(np.float32)
+            _, _, ms2, v2 = soup.trace_rays(o2, d2, counted=True)
+
+            def walk_roofline(visits, ms, key):  # 32 B per node visit + 48 B per triangle test
+                ach = (32.0 * visits[0] + 48.0 * visits[1]) / (ms * 1e-3) / 1e9
+                return {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": profile_traffic("lbvh_%s/%s" % (tag, key)), "peak_source": hbm_src,
+                        "frac_of_l2": ach / l2_peak, "l2_peak": l2_peak,
+                        "note": "algorithmic bytes; a scene whose nodes + triangles fit the 126 MB L2 is served from L2: compare `traffic` (DRAM bytes, ncu) and frac_of_l2"}
+            out["scene_bytes"] = n_tris * (64 + 48)
+            out["trace"] = {"primary_rays_per_s": d.shape[0] / (ms1 * 1e-3), "secondary_rays_per_s": d2.shape[0] / (ms2 * 1e-3), "primary_hit_fraction": float(hit.mean()),
+                            "primary_nodes_per_ray": v1[0] / d.shape[0], "primary_tris_per_ray": v1[1] / d.shape[0],
+                            "secondary_nodes_per_ray": v2[0] / max(1, d2.shape[0]), "secondary_tris_per_ray": v2[1] / max(1, d2.shape[0]),
+                            "primary_roofline": walk_roofline(v1, ms1, "primary_dram_bytes"), "secondary_roofline": walk_roofline(v2, ms2, "secondary_dram_bytes")}
+            del soup
+            S.lib().srt_trim_caches()
+            return out
+
+        lb = lbvh_leg(1 << 20, "1m")
         cub = None
         exe = ROOT / "baseline" / "_ref" / "cub_sort_bench"
         if exe.exists():  # library sort of the same pairs, timing context only
@@ -442,28 +495,9 @@ def main():
                 cub = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
             except Exception as e:  # pragma: no cover
                 cub = {"error": str(e)}
-        lb = {"n_tris": 1 << 20, "build_ms": t, "phases_ms": phases, "sort_baseline_cub": cub, "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
-                                                              "peak_source": hbm_src, "algorithmic_bytes_per_tri": 256}}
-        # BASELINE.json configs[3]: closest-hit rays/s through the device LBVH of the same soup
-        # (primary = the reference camera at 1920x1080, secondary = one random bounce off the primary hits)
-        cam_a = soup.camera(1920, 1080).as_array()
-        ys, xs = np.mgrid[0:1080, 0:1920]
-        d = (cam_a[8:11][None, :] + xs.reshape(-1, 1) * cam_a[2:5][None, :] + ys.reshape(-1, 1) * cam_a[5:8][None, :] - cam_a[12:15][None, :]).astype(np.float32)
-        o = np.tile(cam_a[12:15], (d.shape[0], 1)).astype(np.float32)
-        tt, tri, ms1, v1 = soup.trace_rays(o, d, counted=True)
-        hit = tri >= 0
-        rs = np.random.RandomState(1)
-        d2 = rs.randn(int(hit.sum()), 3).astype(np.float32)
-        o2 = (o[hit] + tt[hit, None] * d[hit] + 1e-3 * d2).astype(np.float32)
-        _, _, ms2, v2 = soup.trace_rays(o2, d2, counted=True)
-        def walk_roofline(visits, ms):  # 32 B per node visit + 48 B per triangle test
-            ach = (32.0 * visits[0] + 48.0 * visits[1]) / (ms * 1e-3) / 1e9
-            return {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": hbm_src}
-        lb["trace"] = {"primary_rays_per_s": d.shape[0] / (ms1 * 1e-3), "secondary_rays_per_s": d2.shape[0] / (ms2 * 1e-3), "primary_hit_fraction": float(hit.mean()),
-                       "primary_nodes_per_ray": v1[0] / d.shape[0], "primary_tris_per_ray": v1[1] / d.shape[0],
-                       "secondary_nodes_per_ray": v2[0] / max(1, d2.shape[0]), "secondary_tris_per_ray": v2[1] / max(1, d2.shape[0]),
-                       "primary_roofline": walk_roofline(v1, ms1), "secondary_roofline": walk_roofline(v2, ms2)}
-        del soup
+        lb["sort_baseline_cub"] = cub
+        if not a.no_extra:
+            lb["soup_10m"] = lbvh_leg(10 << 20, "10m")
 
     cpu_base = None
     if not a.no_cpu_baseline and world == 1:
@@ -471,26 +505,39 @@ def main():
         cpu_base = {"value": w * h * a.ref_spp / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
                     "sample": "%dx%d at %d spp of %d, depth %d, one render" % (w, h, a.ref_spp, spp, depth)}
     ref_cuda = None if (a.no_ref_cuda or world > 1) else reference_cuda_baseline(wl)
+    if c3_info and world == 1 and not a.no_ref_cuda:
+        rc3 = reference_cuda_baseline(WORKLOADS["c3"])
+        if rc3 and "value" in rc3:
+            c3_info["reference_cuda"] = rc3
+            c3_info["vs_reference_cuda"] = c3_info["value"] / rc3["value"]
+
+    def mean(v):
+        return float(np.mean(v)) if v else None
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": step_ms,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl_name, "scene": scene_id, "width": w, "height": h, "spp": spp, "depth": depth,
-                   "fp_mode": "strict(-fmad=false)" if a.strict else "fast(fma, as the reference's nvcc build)",
-                   "parallelism": "image tiles (auto size) interleaved over %d ranks + nccl film reduce" % world if world > 1 else "single gpu",
-                   "l2": "flushed before every step (untimed 256 MB device-to-device copy); film, RNG and path state are re-initialised every step"},
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
+        "config": workload_config(wl_name, wl),
+        "notes": {"fp_mode": "strict(-fmad=false)" if a.strict else "fast(fma, as the reference's nvcc build)",
+                  "parallelism": ("image tiles (auto size) interleaved over %d ranks; libsrt-owned NCCL %d communicator: film reduce-scatter + per-rank slice tonemap + byte gather"
+                                  % (world, nccl_version)) if world > 1 else "single gpu",
+                  "l2": "flushed before every step (untimed 256 MB device-to-device copy); film, RNG and path state are re-initialised every step",
+                  "timing": "per step: max over ranks of (CUDA events around the render launches + CUDA events around the film exchange); mean over steps"},
         "clocks": clocks,
         "e2e": {"value": total_samples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
+        "e2e_breakdown": {"what": "rank 0, wall clock, mean over the timed steps", "scene_build_upload_lbvh_ms": mean(bd["scene_lbvh_ms"]), "manager_init_ms": mean(bd["init_ms"]),
+                          "render_ms": mean(bd["render_ms"]), "film_exchange_tonemap_d2h_widen_ms": mean(bd["film_out_ms"])},
         "gpu_launches": int(launches),
+        "film_crc": film_crc,
+        "per_step": {"rank0_wavefront_ms": mean(kern_ms), "rank0_drain_ms": mean(drain_ms), "rank0_order_ms": mean(order_ms), "rank0_exchange_ms": mean(exch_ms), "rank0_film_out_ms": mean(out_ms),
+                     "render_ms_min_over_ranks": mean(kmin), "render_ms_max_over_ranks": mean(kmax), "wavefront_launches_per_step": rounds_used},
         "roofline": roofline,
-        "cpu_baseline": cpu_base, "c5": c5_info, "soup": soup_info,
+        "cpu_baseline": cpu_base, "c3": c3_info, "c5": c5_info, "soup": soup_info,
         "reference_cuda": ref_cuda,
         "strict_fp": strict_info,
         "lbvh": lb,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 

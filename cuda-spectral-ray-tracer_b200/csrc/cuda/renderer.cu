@@ -145,8 +145,8 @@ struct DeviceRenderer {
     unsigned char* d_gather = nullptr;   // rank 0: world x 3 x slice_cnt bytes
     unsigned long long* d_sum = nullptr; // film checksum accumulator
     bool exchanged = false;
-    cudaEvent_t ex0 = nullptr, ex1 = nullptr;
-    double exchange_ms = 0;
+    cudaEvent_t ex0 = nullptr, ex1 = nullptr, ex2 = nullptr;
+    double exchange_ms = 0, film_out_ms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // stats
@@ -198,6 +198,7 @@ void device_renderer_destroy(DeviceRenderer* r) {
     device_pool_free(r->d_pass_log); device_pool_free(r->d_gather); device_pool_free(r->d_sum); pinned_pool_free(r->h_stage);
     if (r->ex0) cudaEventDestroy(r->ex0);
     if (r->ex1) cudaEventDestroy(r->ex1);
+    if (r->ex2) cudaEventDestroy(r->ex2);
     device_pool_free(r->d_cost); device_pool_free(r->d_drain); pixel_order_destroy(r->order);
     device_pool_free(r->d_state); device_pool_free(r->P.G0); device_pool_free(r->P.G1); device_pool_free(r->P.next_slot); device_pool_free(r->P.acc);
     if (r->l2_window) {  // hand the pinned L2 lines back; the last renderer also returns the set-aside to the normal cache
@@ -233,6 +234,7 @@ static bool ensure_staging(DeviceRenderer* r, size_t dev_bytes, size_t host_byte
 static bool renderer_setup(DeviceRenderer* r) {
     const RenderConfig& c = r->cfg;
     WaveParams& P = r->P;
+    PhaseTrace tr("renderer_setup");
     SRT_CUDA(cudaGetDevice(&r->device));
     if (c.comm && comm_device(c.comm) != r->device) { set_error("the communicator was created on another CUDA device"); return false; }
     P.nodes = device_scene_nodes(r->scene);
@@ -294,6 +296,7 @@ static bool renderer_setup(DeviceRenderer* r) {
         P.plane = r->slice_cnt * world;
         SRT_CUDA(cudaEventCreate(&r->ex0));
         SRT_CUDA(cudaEventCreate(&r->ex1));
+        SRT_CUDA(cudaEventCreate(&r->ex2));
         if (!device_pool_alloc((void**)&r->d_gather, comm_rank(c.comm) == 0 ? world * 3 * r->slice_cnt : 3 * r->slice_cnt)) return false;
     }
     if (!device_pool_alloc((void**)&r->d_sum, sizeof(unsigned long long))) return false;
@@ -309,6 +312,7 @@ static bool renderer_setup(DeviceRenderer* r) {
     if (!device_pool_alloc((void**)&r->d_tiles, std::max<size_t>(1, r->h_tiles.size()) * sizeof(uint32_t))) return false;
     if (!r->h_tiles.empty()) SRT_CUDA(cudaMemcpy(r->d_tiles, r->h_tiles.data(), r->h_tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     P.tiles = r->d_tiles;
+    tr.mark("tiles");
     SRT_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     SRT_CUDA(cudaEventCreate(&r->ev0));
     SRT_CUDA(cudaEventCreate(&r->ev1));
@@ -331,6 +335,7 @@ static bool renderer_setup(DeviceRenderer* r) {
     P.cie = r->d_cie;
     P.bg = r->d_bg;
     P.ray_counter = r->d_rays;
+    tr.mark("buffers + constants");
     const LaunchTable& T = table(c.fp_strict);
     // wide leaf only when the scene collapsed into <= 32 units AND this camera's origins respect the
     // origin bound the units' error budgets were computed for
@@ -361,6 +366,7 @@ static bool renderer_setup(DeviceRenderer* r) {
         SRT_CUDA(T.configure(r->smem + P.queue_bytes));
         resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.block_threads, r->smem + P.queue_bytes));
     }
+    tr.mark("launch configuration");
     r->wave_grid = (int)std::min<uint64_t>(resident, ((uint64_t)P.nslots + P.block_slots - 1) / P.block_slots);
     // rounds of samples: K launches per chunk that render samples [0,b1) [b1,b2) ... [b_{K-1},spp), each 8x longer than
     // the one before.  The first round hands the pixels out by a first guess of their cost (k_prior_cost), the later
@@ -393,6 +399,7 @@ static bool renderer_setup(DeviceRenderer* r) {
     unsigned char* sb = (unsigned char*)r->d_state;
     P.R0 = (float4*)sb; P.R1 = (float4*)(sb + nrec * 16); P.P0 = (float4*)(sb + nrec * 32); P.P1 = (float4*)(sb + nrec * 48);
     P.L0 = (uint4*)(sb + nrec * 64); P.L1 = (uint2*)(sb + nrec * 80);
+    tr.mark("order + path state");
     {
         int dev = 0, max_persist = 0, max_window = 0;
         cudaGetDevice(&dev);
@@ -412,7 +419,9 @@ static bool renderer_setup(DeviceRenderer* r) {
             else { r->l2_window = true; ++g_l2_windows; }
         }
     }
+    tr.mark("L2 window");
     SRT_CUDA(cudaStreamSynchronize(r->stream));
+    tr.mark("sync");
     return true;
 }
 
@@ -573,19 +582,27 @@ bool device_renderer_exchange_film(DeviceRenderer* r, float* fr, float* fg, floa
     std::lock_guard<std::mutex> lock(r->stage_mu);
     if (!ensure_staging(r, 3 * cnt, rank == 0 ? world * 3 * cnt : 0)) return false;
     cudaStream_t st = r->stream;
+    PhaseTrace tr("exchange_film");
     SRT_CUDA(cudaEventRecord(r->ex0, st));
     if (!comm_film_reduce_scatter(c, r->P.acc, r->P.plane, cnt, st)) return false;
+    SRT_CUDA(cudaEventRecord(r->ex1, st));
+    if (tr.on) { cudaStreamSynchronize(st); tr.mark("reduce-scatter"); }
     T.resolve_slice(r->P.acc, r->P.plane, first, count, (uint32_t)cnt, r->P.spp, r->d_rgb, st);
     if (count) { r->launches++; count_launch(); }
     SRT_CUDA_LAST();
+    if (tr.on) { cudaStreamSynchronize(st); tr.mark("slice tonemap"); }
     if (!comm_gather_bytes(c, r->d_rgb, r->d_gather, 3 * cnt, st)) return false;
+    if (tr.on) { cudaStreamSynchronize(st); tr.mark("gather"); }
     if (rank == 0) SRT_CUDA(cudaMemcpyAsync(r->h_stage, r->d_gather, world * 3 * cnt, cudaMemcpyDeviceToHost, st));
-    SRT_CUDA(cudaEventRecord(r->ex1, st));
-    SRT_CUDA(cudaEventSynchronize(r->ex1));
+    SRT_CUDA(cudaEventRecord(r->ex2, st));
+    SRT_CUDA(cudaEventSynchronize(r->ex2));
     float ms = 0;
     SRT_CUDA(cudaEventElapsedTime(&ms, r->ex0, r->ex1));
     r->exchange_ms += ms;
+    SRT_CUDA(cudaEventElapsedTime(&ms, r->ex1, r->ex2));
+    r->film_out_ms += ms;
     r->exchanged = true;
+    tr.mark("d2h");
     if (rank == 0) {  // slices are runs of the raster: widen them as one-row regions
         float* const planes[3] = {fr, fg, fb};
         auto widen = [&](size_t k) {
@@ -679,7 +696,7 @@ bool device_renderer_pass_log(DeviceRenderer* r, uint32_t* out) {
 
 bool device_renderer_reset(DeviceRenderer* r) {  // back to the state right after creation: empty film, unseeded RNG slots
     SRT_CUDA(cudaSetDevice(r->device));
-    r->exchanged = false; r->exchange_ms = 0;
+    r->exchanged = false; r->exchange_ms = 0; r->film_out_ms = 0;
     SRT_CUDA(cudaMemsetAsync(r->P.acc, 0, 3 * r->P.plane * sizeof(float), r->stream));
     SRT_CUDA(cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), r->stream));
     SRT_CUDA(cudaStreamSynchronize(r->stream));
@@ -698,6 +715,7 @@ void device_renderer_stats(const DeviceRenderer* r, srt_stats* s) {
     s->rounds = r->round_end.size();
     s->drain_ms = r->drain_ms;
     s->exchange_ms = r->exchange_ms;
+    s->film_out_ms = r->film_out_ms;
     s->render_ms = r->render_ms;
     s->lbvh_ms = device_scene_lbvh_ms(r->scene);
     s->order_ms = r->cat_ms[0]; s->wavefront_ms = r->cat_ms[1]; s->megakernel_ms = r->cat_ms[2]; s->other_ms = r->cat_ms[3];

@@ -41,7 +41,7 @@ class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("wavefront_launches", C.c_uint64), ("rounds", C.c_uint64), ("render_ms", C.c_double), ("lbvh_ms", C.c_double),
                 ("wavefront_ms", C.c_double), ("megakernel_ms", C.c_double), ("order_ms", C.c_double), ("other_ms", C.c_double),
-                ("drain_ms", C.c_double), ("exchange_ms", C.c_double)]
+                ("drain_ms", C.c_double), ("exchange_ms", C.c_double), ("film_out_ms", C.c_double)]
 
 
 OPT_FP_MODE, OPT_PIPELINE, OPT_TILE_W, OPT_TILE_H, OPT_RANK, OPT_WORLD, OPT_KERNEL_TIMING, OPT_TRAVERSAL, OPT_BLOCK_SLOTS, OPT_BLOCK_THREADS, OPT_STRATIFIED, OPT_ROUNDS, OPT_L2_PERSIST, OPT_PASS_LOG, OPT_SCHED_FLAGS = 1, 2, 3, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16, 17
@@ -175,7 +175,7 @@ class CameraBuilder:
         self.h = lib().srt_camera_builder_create()
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib().srt_camera_builder_destroy(self.h)
             self.h = None
 
@@ -236,7 +236,7 @@ class Scene:
         self.nmats = L.srt_scene_num_materials(self.h)
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:  # `lib` is gone when the interpreter shuts down
             lib().srt_scene_destroy(self.h)
             self.h = None
 
@@ -307,7 +307,7 @@ class Comm:
         self.close()
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib().srt_comm_destroy(self.h)
             self.h = None
 
@@ -341,7 +341,7 @@ class RenderManager:
             raise SrtError(lib().srt_last_error().decode())
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib().srt_render_manager_destroy(self.h)
             self.h = None
 

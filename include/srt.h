@@ -221,7 +221,8 @@ typedef struct {
     /* ... and the end-of-launch drain of k_wavefront: last block exit minus the moment the first path slot
      * found no pixel left to fetch (device globaltimer), summed over launches */
     double drain_ms;
-    double exchange_ms; /* CUDA-event time of srt_rm_exchange_film calls (reduce-scatter + slice tonemap + gather + D2H) */
+    double exchange_ms; /* srt_rm_exchange_film, CUDA events: the collective (reduce-scatter of the XYZ planes, incl. waiting for the slowest rank) */
+    double film_out_ms; /* srt_rm_exchange_film, CUDA events: slice tonemap + byte gather to rank 0 + device-to-host copy */
 } srt_stats;
 int srt_rm_get_stats(const srt_render_manager*, srt_stats* out);
 /* SRT_OPT_PASS_LOG read-out: out = 8 blocks x 8192 passes x 4 uint32 {globaltimer ns (low 32 bits), regenerate, lambertian,
