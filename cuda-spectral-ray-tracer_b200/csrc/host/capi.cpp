@@ -61,6 +61,10 @@ int srt_camera_builder_get_camera_res(const srt_camera_builder* b, uint32_t w, u
 }
 
 void srt_set_ref_compat(int on) { g_ref_compat = on != 0; }
+int srt_glass_coefficients(int which, float b[3], float c[3]) {
+    if (!b || !c || !glass_coefficients(which, b, c)) { set_error("srt_glass_coefficients: unknown glass"); return SRT_ERR_ARG; }
+    return SRT_OK;
+}
 
 static srt_scene* finish_scene(srt_scene* h) {
     Scene& s = h->s;

@@ -15,6 +15,8 @@ inline float radians(float deg) { return deg * kPi / 180.0f; }
 // refraction/sellmeier.cuh:6-13
 const float kBK7_b[3] = {1.03961212f, 0.231792344f, 1.01046945f};
 const float kBK7_c[3] = {6.00069867e-3f, 2.00179144e-2f, 1.03560653e2f};
+const float kSilica_b[3] = {0.6961663f, 0.4079426f, 0.8974794f};  // no reference scene uses fused silica; kept for srt_glass_coefficients
+const float kSilica_c[3] = {0.0684043f, 0.1162414f, 9.896161f};
 const float kFlint_b[3] = {1.34533359f, 0.209073176f, 0.937357162f};
 const float kFlint_c[3] = {0.00997743871f, 0.0470450767f, 111.886764f};
 
@@ -39,6 +41,20 @@ HostMaterial dielectric(const float b[3], const float c[3], bool ref_compat) {
     for (int i = 0; i < 3; i++) { d.sellmeier_b[i] = b[i]; d.sellmeier_c[i] = c[i]; }
     return HostMaterial::from_desc(d, ref_compat);
 }
+
+}  // namespace
+bool glass_coefficients(int which, float b[3], float c[3]) {  // refraction/sellmeier.cuh:6-13
+    const float *sb, *sc;
+    switch (which) {
+        case SRT_GLASS_BK7: sb = kBK7_b; sc = kBK7_c; break;
+        case SRT_GLASS_FUSED_SILICA: sb = kSilica_b; sc = kSilica_c; break;
+        case SRT_GLASS_FLINT: sb = kFlint_b; sc = kFlint_c; break;
+        default: return false;
+    }
+    for (int i = 0; i < 3; i++) { b[i] = sb[i]; c[i] = sc[i]; }
+    return true;
+}
+namespace {
 
 // five walls + ceiling light, written to fixed triangle slots 0..11 (scene.cu:83-102)
 void room(TriangleSoup& g, const uint32_t wall[5], uint32_t light) {

@@ -101,6 +101,7 @@ struct SceneDescription {
 };
 SceneDescription make_reference_scene(unsigned scene_id, bool ref_compat);
 SceneDescription make_soup_scene(uint32_t n, uint64_t seed);
+bool glass_coefficients(int which, float b[3], float c[3]);
 bool load_obj(const char* path, std::vector<float>& verts9);
 bool load_ply(const char* path, std::vector<float>& verts9);
 

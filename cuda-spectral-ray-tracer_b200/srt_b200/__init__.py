@@ -83,6 +83,7 @@ _SIGS = [
     ("srt_scene_camera_res", C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(Camera)]),
     ("srt_scene_num_tris", C.c_uint32, [_P]), ("srt_scene_num_materials", C.c_uint32, [_P]),
     ("srt_set_ref_compat", None, [C.c_int]),
+    ("srt_glass_coefficients", C.c_int, [C.c_int, _P, _P]),
     ("srt_scene_get_tris", C.c_int, [_P, _P, _P]), ("srt_scene_get_materials", C.c_int, [_P, _P, _P]),
     ("srt_scene_get_lbvh", C.c_int, [_P] * 8),
     ("srt_scene_rebuild_lbvh", C.c_int, [_P, C.c_int, _P]),

@@ -121,6 +121,11 @@ uint32_t srt_scene_num_materials(const srt_scene*);
 /* 1 = dielectrics reproduce material.cuh:67 (C := B), the default; 0 = physical Sellmeier.
  * Must be set before srt_scene_create*. */
 void srt_set_ref_compat(int on);
+/* the Sellmeier coefficient tables the reference carries (refraction/sellmeier.cuh:6-13) for srt_material_desc */
+#define SRT_GLASS_BK7 0
+#define SRT_GLASS_FUSED_SILICA 1
+#define SRT_GLASS_FLINT 2
+int srt_glass_coefficients(int which, float b[3], float c[3]);
 /* parity dumps.  tris_f: n*22 floats (v0 v1 v2 normal D bbox[xmin xmax ymin ymax zmin zmax] pad3),
  * tris_i: n*3 ints (clockwise, aa_plane, material).  mats_f: m*108 floats (col3 fuzz power B3 C3
  * spectrum95 pad2), mats_i: m ints (type). */

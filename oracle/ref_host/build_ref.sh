@@ -6,13 +6,23 @@
 # are shimmed (shim/cuda_shim.h).  Patched scratch copies live in a temp dir outside the repo
 # and are removed afterwards; only the .so is kept (git-ignored, travels with gpurun).
 #
-#   oracle/ref_host/build_ref.sh [--draw-order ltr|rtl]
+#   oracle/ref_host/build_ref.sh [--draw-order ltr|rtl] [--physical]
+# --physical additionally patches materials/material.cuh:67 (sellmeier_C[i] = c[i]) and names the
+# library libsrt_ref_<order>_physical.so: the reference with physically meant glass.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${SRT_REFERENCE_DIR:-/root/reference}"
 OUT="$HERE/../_ref"
 ORDER="ltr"
-if [[ "${1:-}" == "--draw-order" ]]; then ORDER="$2"; fi
+PHYS=""
+SUFFIX=""
+while [[ $# -gt 0 ]]; do
+  case "$1" in
+    --draw-order) ORDER="$2"; shift 2 ;;
+    --physical) PHYS="--physical"; SUFFIX="_physical"; shift ;;
+    *) echo "build_ref.sh: unknown argument $1" >&2; exit 2 ;;
+  esac
+done
 if [[ ! -d "$REF" ]]; then
   echo "build_ref.sh: $REF not present (GPU box?) -- keeping prebuilt oracle/_ref" >&2
   exit 0
@@ -20,7 +30,7 @@ fi
 mkdir -p "$OUT"
 STAGE="$(mktemp -d /tmp/srt_ref_stage.XXXXXX)"
 trap 'rm -rf "$STAGE"' EXIT
-python3 "$HERE/patch_ref.py" --ref "$REF" --out "$STAGE/src" --draw-order "$ORDER"
+python3 "$HERE/patch_ref.py" --ref "$REF" --out "$STAGE/src" --draw-order "$ORDER" $PHYS
 
 INC=("-I$STAGE/src")
 for d in materials primitives bvh utils rendering refraction color spectrum ray math io scene _log_; do
@@ -47,5 +57,5 @@ pids+=($!)
 gcc -O2 -ffp-contract=off -fPIC -I"$HERE/.." -c "$HERE/../rgb2spec.c" -o "$STAGE/rgb2spec.o" &
 pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
-g++ -shared -fopenmp -o "$OUT/libsrt_ref_${ORDER}.so" "${OBJS[@]}" "$STAGE/ref_driver.o" "$STAGE/ref_table.o" "$STAGE/rgb2spec.o" -lm
-echo "build_ref.sh: built $OUT/libsrt_ref_${ORDER}.so"
+g++ -shared -fopenmp -o "$OUT/libsrt_ref_${ORDER}${SUFFIX}.so" "${OBJS[@]}" "$STAGE/ref_driver.o" "$STAGE/ref_table.o" "$STAGE/rgb2spec.o" -lm
+echo "build_ref.sh: built $OUT/libsrt_ref_${ORDER}${SUFFIX}.so"

@@ -18,6 +18,9 @@ Edits (all listed in DESIGN.md "oracle/_ref"):
      code left-to-right).  --draw-order {ltr,rtl} selects which order is baked in.
   5. rendering/rendering.cu:140-142 -- call srt_ref_xyz_hook() at the top of save_to_fb so the
      driver can read the pre-tonemap XYZ sum of every pixel.
+  6. only with --physical: materials/material.cuh:67 `sellmeier_C[i] = b[i];` -> `= c[i];`, the
+     physically meant Sellmeier coefficients (the library's opt-in srt_set_ref_compat(0) mode);
+     built as a separate libsrt_ref_<order>_physical.so.
 """
 import argparse, pathlib, re, shutil, sys
 
@@ -66,6 +69,7 @@ def main():
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", required=True)
     ap.add_argument("--draw-order", choices=["ltr", "rtl"], default="ltr")
+    ap.add_argument("--physical", action="store_true", help="edit 6: materials/material.cuh:67 sellmeier_C[i] = c[i]")
     a = ap.parse_args()
     ref, out = pathlib.Path(a.ref), pathlib.Path(a.out)
     for d in NEEDED_DIRS:
@@ -125,6 +129,12 @@ def main():
                  r"\1\n\tsrt_ref_xyz_hook(pixel_color.e, coalesced_global_idx);", t, "xyz hook")
     t = "void srt_ref_xyz_hook(const float* xyz_sum, unsigned int idx);\n" + t
     p.write_text(t)
+    # 6. (only with --physical) the one-token fix of the dielectric constructor: the reference as its author meant it
+    if a.physical:
+        p = out / "materials/material.cuh"
+        t = p.read_text()
+        t = must_sub(r"sellmeier_C\[i\] = b\[i\];", "sellmeier_C[i] = c[i];", t, "material.cuh:67 sellmeier_C")
+        p.write_text(t)
     print("patch_ref.py: staged patched reference sources in", out)
 
 

@@ -199,12 +199,16 @@ static omat mat_make(ov3 col, float fuzz, float ir, float power, int type) { /* 
 static omat mat_lambertian(ov3 c) { return mat_make(c, 1.0f, 1.0f, 0.0f, O_LAMBERTIAN); }       /* :111-113 */
 static omat mat_metallic(ov3 c, float fuzz) { return mat_make(c, fuzz, 1.0f, 0.0f, O_METALLIC); } /* :116-118 */
 static omat mat_emissive(ov3 c, float p) { return mat_make(c, 1.0f, 1.0f, p, O_EMISSIVE); }      /* :106-108 */
-static omat mat_dielectric(const float b[3], const float c[3]) { /* :63-69: sellmeier_C[i] = b[i] (sic) */
+/* 0 (default): the reference as shipped, sellmeier_C[i] = b[i] (material.cuh:67, sic).  1: the same constructor with the
+ * one-token fix sellmeier_C[i] = c[i] -- the physically meant Sellmeier equation.  Pinned against oracle/_ref built with
+ * exactly that token patched (build_ref.sh --physical, tests/golden/ref_physical.npz). */
+static int g_physical_sellmeier = 0;
+void srt_oracle_set_physical_sellmeier(int on) { g_physical_sellmeier = on != 0; }
+static omat mat_dielectric(const float b[3], const float c[3]) { /* :63-69 */
     omat m;
     memset(&m, 0, sizeof m);
-    (void)c;
     m.col = V(1.0f, 1.0f, 1.0f); m.fuzz = 1.0f; m.type = O_DIELECTRIC; m.power = 0.0f;
-    for (int i = 0; i < 3; i++) { m.B[i] = b[i]; m.C[i] = b[i]; }
+    for (int i = 0; i < 3; i++) { m.B[i] = b[i]; m.C[i] = g_physical_sellmeier ? c[i] : b[i]; }
     return m;
 }
 static void mat_compute_spectral_distr(omat* m) { /* :71-84 */
@@ -217,9 +221,17 @@ static void mat_compute_spectral_distr(omat* m) { /* :71-84 */
 /* refraction/sellmeier.cuh:6-13 */
 static const float BK7_b[3] = {1.03961212f, 0.231792344f, 1.01046945f};
 static const float BK7_c[3] = {6.00069867e-3f, 2.00179144e-2f, 1.03560653e2f};
+static const float fused_silica_b[3] = {0.6961663f, 0.4079426f, 0.8974794f};
+static const float fused_silica_c[3] = {0.0684043f, 0.1162414f, 9.896161f};
 static const float flint_glass_b[3] = {1.34533359f, 0.209073176f, 0.937357162f};
 static const float flint_glass_c[3] = {0.00997743871f, 0.0470450767f, 111.886764f};
 
+/* the three coefficient tables of refraction/sellmeier.cuh:6-13: 0 BK7, 1 fused silica, 2 flint glass */
+void srt_oracle_glass(int which, float b[3], float c[3]) {
+    const float* sb = which == 0 ? BK7_b : (which == 1 ? fused_silica_b : flint_glass_b);
+    const float* sc = which == 0 ? BK7_c : (which == 1 ? fused_silica_c : flint_glass_c);
+    for (int i = 0; i < 3; i++) { b[i] = sb[i]; c[i] = sc[i]; }
+}
 float srt_oracle_sellmeier(const float b[3], const float c[3], float lambda) { /* sellmeier.cu:11-23 */
     lambda *= 1e-3f;
     float l2 = lambda * lambda;

@@ -88,6 +88,8 @@ int srt_oracle_bvh_hit(const oscene*, const float o[3], const float d[3], float 
 int srt_oracle_brute_hit(const oscene*, const float o[3], const float d[3], float out[10], int* tri_index);
 int srt_oracle_scatter(const oscene*, int mat, float ray_io[21], const float rec_in[8], uint32_t rng[6]);
 float srt_oracle_sellmeier(const float b[3], const float c[3], float lambda);
+void srt_oracle_glass(int which, float b[3], float c[3]);       /* sellmeier.cuh:6-13: 0 BK7, 1 fused silica, 2 flint */
+void srt_oracle_set_physical_sellmeier(int on);                 /* scenes created afterwards: material.cuh:67 as shipped (0) or fixed (1) */
 float srt_oracle_spectrum_interp(const float* table95, float lambda);
 void srt_oracle_spectrum_to_xyz(const float wl[7], const float pw[7], int nvalid, float xyz[3]);
 void srt_oracle_tonemap(const float xyz_mean[3], float rgb255[3]);

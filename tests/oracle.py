@@ -78,6 +78,8 @@ def lib():
         L.srt_oracle_get_ray_stratified.argtypes = [C.POINTER(OCam), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
         L.srt_oracle_render_opts.argtypes = [C.c_void_p, C.POINTER(OCam)] + [C.c_int] * 5 + [C.c_void_p] * 3 + [C.c_int]
         L.srt_oracle_debug_pixel.argtypes = [C.c_void_p, C.POINTER(OCam), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.srt_oracle_set_physical_sellmeier.argtypes = [C.c_int]
+        L.srt_oracle_glass.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.srt_oracle_sellmeier.restype = C.c_float
         L.srt_oracle_sellmeier.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
         L.srt_oracle_spectrum_interp.restype = C.c_float
@@ -97,9 +99,14 @@ def lib():
 
 
 class Scene:
-    def __init__(self, scene_id=None, soup=None, seed=1984):
+    def __init__(self, scene_id=None, soup=None, seed=1984, physical=False):
+        """physical=True: dielectrics with the one-token fix of materials/material.cuh:67 (C[i] = c[i])"""
         L = lib()
-        self.h = L.srt_oracle_scene_soup(soup, seed) if soup is not None else L.srt_oracle_scene_create(scene_id)
+        L.srt_oracle_set_physical_sellmeier(1 if physical else 0)
+        try:
+            self.h = L.srt_oracle_scene_soup(soup, seed) if soup is not None else L.srt_oracle_scene_create(scene_id)
+        finally:
+            L.srt_oracle_set_physical_sellmeier(0)
         self.ntris = L.srt_oracle_scene_ntris(self.h)
         self.nmats = L.srt_oracle_scene_nmats(self.h)
 

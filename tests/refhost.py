@@ -9,6 +9,7 @@ ROOT = pathlib.Path(__file__).resolve().parents[1]
 
 
 def lib_path(order="ltr"):
+    """order: ltr | rtl (RNG draw order baked in), or ltr_physical (materials/material.cuh:67 fixed as well)"""
     return ROOT / "oracle" / "_ref" / ("libsrt_ref_%s.so" % order)
 
 

@@ -352,6 +352,21 @@ def test_rounds_do_not_change_the_film(srt, strict):
         assert other[2]["rounds"] >= 2
 
 
+@pytest.mark.parametrize("scene", [1, 2])
+def test_physical_sellmeier_image_strict(srt, scene):
+    """srt_set_ref_compat(0) (physically meant Sellmeier coefficients) against the real reference host-compiled with
+    materials/material.cuh:67 fixed: strict FP mode must reproduce its raw XYZ bit for bit (tests/golden/ref_physical.npz)"""
+    g = np.load(ROOT / "tests" / "golden" / "ref_physical.npz")
+    L = srt.lib()
+    try:
+        L.srt_set_ref_compat(0)
+        rgb, xyz, _ = srt.render(scene_id=scene, w=400, h=225, spp=8, bounce=10, strict=True)
+    finally:
+        L.srt_set_ref_compat(1)
+    assert np.array_equal(xyz.view(np.uint32), g["scene%d_xyz" % scene].view(np.uint32))
+    assert np.array_equal(rgb.astype(np.uint8), g["scene%d_rgb" % scene])
+
+
 def _run_ranks(world, tmp_path, scene, w, h, spp, strict):
     import subprocess
     import sys
@@ -483,3 +498,23 @@ def test_cli_drop_in(srt, tmp_path):
     assert np.array_equal(film.view(np.uint32), want.view(np.uint32))
     bad = subprocess.run([str(exe), "-s", "0", "-xr", "64", "-ns", "5", "--no-show", "--stratified"], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert bad.returncode != 0 and "square" in (bad.stdout + bad.stderr)
+    # --physical: the Sellmeier fix; the film equals the patched real reference (tests/golden/ref_physical.npz)
+    g = np.load(ROOT / "tests" / "golden" / "ref_physical.npz")
+    out = subprocess.run([str(exe), "-s", "1", "-xr", "400", "-ar", "16/9", "-ns", "8", "-bl", "10", "--no-show", "--strict-fp", "--physical", "--xyz", str(xyz_file)],
+                         capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stdout[-1000:] + out.stderr[-1000:]
+    film = np.fromfile(xyz_file, np.float32).reshape(3, 225, 400)
+    assert np.array_equal(film.view(np.uint32), g["scene1_xyz"].view(np.uint32))
+    # --gpus N: one thread and one NCCL rank per device inside ONE process; same film as one GPU
+    ndev = srt.lib().srt_device_count()
+    if ndev >= 2:
+        n = 2 if ndev < 4 else 4
+        out = subprocess.run([str(exe), "-s", "0", "-xr", "320", "-ar", "16/9", "-ns", "16", "-bl", "10", "--no-show", "--strict-fp", "--gpus", str(n), "--xyz", str(xyz_file)],
+                             capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+        assert out.returncode == 0, out.stdout[-1000:] + out.stderr[-1000:]
+        assert "gpus: %d" % n in out.stdout
+        film = np.fromfile(xyz_file, np.float32).reshape(3, 180, 320)
+        _, want, _ = srt.render(scene_id=0, w=320, h=180, spp=16, bounce=10, strict=True)
+        assert np.array_equal(film.view(np.uint32), want.view(np.uint32))
+    too_many = subprocess.run([str(exe), "-s", "0", "-xr", "64", "-ns", "1", "--no-show", "--gpus", "99"], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert too_many.returncode != 0 and "CUDA devices" in too_many.stderr

@@ -115,6 +115,28 @@ def test_physical_sellmeier_switch(srt):
     assert np.array_equal(mf[2, 8:11], mf[2, 5:8])  # reference quirk F4: C := B
 
 
+def test_physical_mode_materials_match_the_patched_reference(srt):
+    """srt_set_ref_compat(0): host materials equal those of the real reference built with materials/material.cuh:67 fixed
+    (tests/golden/ref_physical.npz), and srt_glass_coefficients carries the three tables of refraction/sellmeier.cuh:6-13"""
+    import oracle
+
+    g = np.load(ROOT / "tests" / "golden" / "ref_physical.npz")
+    L = srt.lib()
+    try:
+        L.srt_set_ref_compat(0)
+        for scene in (1, 2):
+            mf, _ = srt.Scene(scene, host_only=True).materials()
+            assert np.array_equal(bits(mf), bits(g["scene%d_mats_f" % scene]))
+    finally:
+        L.srt_set_ref_compat(1)
+    for which in (0, 1, 2):
+        b = np.zeros(3, np.float32); c = np.zeros(3, np.float32); ob = np.zeros(3, np.float32); oc = np.zeros(3, np.float32)
+        assert L.srt_glass_coefficients(which, b.ctypes.data, c.ctypes.data) == 0
+        oracle.lib().srt_oracle_glass(which, ob.ctypes.data, oc.ctypes.data)
+        assert np.array_equal(b, ob) and np.array_equal(c, oc)
+    assert L.srt_glass_coefficients(7, b.ctypes.data, c.ctypes.data) != 0
+
+
 def test_soup_and_mesh_host_side(srt):
     import oracle
 

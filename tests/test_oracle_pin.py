@@ -2,6 +2,7 @@
 tests/golden/make_golden.py produced by running the REAL reference host-compiled (oracle/_ref).
 Everything here is bit-exact: integers, indices and float32 values compare as raw bits."""
 import ctypes as C
+import pathlib
 
 import numpy as np
 import pytest
@@ -201,3 +202,31 @@ def test_lbvh_spec_fixture():
         kids = np.concatenate([r["left"], r["right"]])
         assert sorted(kids.tolist()) == list(range(1, 2 * n - 1))  # every node but the root is a child exactly once
         assert r["parent"][0] == -1
+
+
+def test_physical_sellmeier_mode_bit_exact():
+    """The oracle's physical mode (materials/material.cuh:67 with the one-token fix C[i] = c[i]) against the REAL reference
+    host-compiled with exactly that token patched (tests/golden/make_golden_physical.py): materials, images and raw XYZ of the
+    Prism and Different-Materials scenes bit for bit; and the fused-silica table (refraction/sellmeier.cuh:9-10), which no
+    reference scene uses, through sellmeier_index at 64 wavelengths."""
+    g = np.load(pathlib.Path(__file__).resolve().parent / "golden" / "ref_physical.npz")
+    for scene in (1, 2):
+        S = oracle.Scene(scene, physical=True)
+        mf, _ = S.materials()
+        assert np.array_equal(mf.view(np.uint32), g["scene%d_mats_f" % scene].view(np.uint32))
+        rgb, xyz = oracle.render(S, oracle.camera(400, 225), 8, 10)
+        assert np.array_equal(xyz.view(np.uint32), g["scene%d_xyz" % scene].view(np.uint32))
+        assert np.array_equal(rgb.astype(np.uint8), g["scene%d_rgb" % scene])
+        # the shipped (C := B) mode gives a different image: the switch really switches
+        _, xyz_compat = oracle.render(oracle.Scene(scene), oracle.camera(400, 225), 8, 10)
+        assert not np.array_equal(xyz_compat, xyz)
+    b = np.zeros(3, np.float32); c = np.zeros(3, np.float32)
+    oracle.lib().srt_oracle_glass(1, b.ctypes.data, c.ctypes.data)
+    n = np.array([oracle.lib().srt_oracle_sellmeier(b.ctypes.data, c.ctypes.data, float(l)) for l in g["silica_lambda"]], np.float32)
+    assert np.array_equal(n.view(np.uint32), g["silica_n"].view(np.uint32))
+    # quirk (carried verbatim): the reference's fused-silica row lists the resonance WAVELENGTHS (0.0684 um ...) where the
+    # Sellmeier equation wants their squares, so its n_d is 1.563; with the squares the same B give the textbook 1.4585
+    l2 = (587.6e-3) ** 2
+    n_d = float(np.sqrt(1.0 + sum(float(b[i]) * l2 / (l2 - float(c[i]) ** 2) for i in range(3))))
+    assert abs(n_d - 1.4585) < 1e-3
+    assert abs(float(n[np.argmin(abs(g["silica_lambda"] - 587.6))]) - 1.563) < 2e-3
