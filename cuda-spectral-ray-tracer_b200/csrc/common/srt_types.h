@@ -34,13 +34,15 @@ struct alignas(16) SrtTri {
 #define SRT_FLAT_MAX_TRIS 64  // scenes up to this size are one wide leaf: no tree walk at all
 
 // ---- wide-leaf pre-test unit, 64 B: one triangle or one parallelogram pair (host/flat_leaf.cpp) ----
-// q0 = plane; q1 = (A.xyz, a_w + eps); q2 = (B.xyz, b_w + eps); q3 = (c1, c2, c3, tol)
+// q0 = plane; q1 = (A.xyz, a_w + eps); q2 = (B.xyz, b_w + eps); q3 = (c1, c2, c3, near)
+// near: 0, or -- pairs whose two triangles store planes that differ in the last bits -- how close to the plane a grazing
+// ray must start for the second triangle to stay a candidate without a verdict (host/flat_leaf.cpp)
 // unit u covers flat triangle positions 2u (first half) and 2u+1 (second half, if c2 >= 0)
 struct alignas(16) SrtFlatUnit {
     float nx, ny, nz, D;
     float ax, ay, az, aw;
     float bx, by, bz, bw;
-    float c1, c2, c3, tol;
+    float c1, c2, c3, near;
 };
 #define SRT_FLAT_MAX_UNITS 32
 

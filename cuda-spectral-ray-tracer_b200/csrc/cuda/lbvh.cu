@@ -71,7 +71,9 @@ struct DeviceScene {
     // wide leaf (scenes of <= 32 pre-test units): flat-order triangles + units, built on the host
     SrtFlatUnit* flat_units = nullptr;
     SrtTri* flat_tris = nullptr;
+    uint32_t* flat_to_orig = nullptr;  // flat triangle position -> original triangle index
     uint32_t n_units = 0;
+    float flat_guard = 0.f, flat_tol = 0.f;
     double origin_l1_bound = 0;
     float host_lo[3] = {0, 0, 0}, host_hi[3] = {0, 0, 0};  // union of the triangle boxes (host)
     uint32_t tiles = 0;
@@ -510,7 +512,9 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
     s->origin_l1_bound = origin_l1_bound;
     if (ok && build_flat_leaf(tris, mats, prio, origin_l1_bound, flat)) {
         s->n_units = (uint32_t)flat.units.size();
-        ok = dalloc(s->flat_units, flat.units.size()) && dalloc(s->flat_tris, flat.tris.size()) &&
+        s->flat_guard = flat.guard; s->flat_tol = flat.tol;
+        ok = dalloc(s->flat_units, flat.units.size()) && dalloc(s->flat_tris, flat.tris.size()) && dalloc(s->flat_to_orig, flat.to_orig.size()) &&
+             cuda_ok(cudaMemcpy(s->flat_to_orig, flat.to_orig.data(), flat.to_orig.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "upload flat order", __FILE__, __LINE__) &&
              cuda_ok(cudaMemcpy(s->flat_units, flat.units.data(), flat.units.size() * sizeof(SrtFlatUnit), cudaMemcpyHostToDevice), "upload units", __FILE__, __LINE__) &&
              cuda_ok(cudaMemcpy(s->flat_tris, flat.tris.data(), flat.tris.size() * sizeof(SrtTri), cudaMemcpyHostToDevice), "upload flat tris", __FILE__, __LINE__);
     }
@@ -525,7 +529,7 @@ void device_scene_destroy(DeviceScene* s) {
     dfree(s->verts); dfree(s->tris_in); dfree(s->mats); dfree(s->leaf_boxes); dfree(s->centroids); dfree(s->scene_box);
     dfree(s->codes); dfree(s->keys[0]); dfree(s->keys[1]); dfree(s->vals[0]); dfree(s->vals[1]); dfree(s->hist);
     dfree(s->lookback); dfree(s->tile_counter); dfree(s->left); dfree(s->right); dfree(s->parent); dfree(s->node_box_lo); dfree(s->node_box_hi);
-    dfree(s->visit); dfree(s->nodes); dfree(s->tris); dfree(s->flat_units); dfree(s->flat_tris);
+    dfree(s->visit); dfree(s->nodes); dfree(s->tris); dfree(s->flat_units); dfree(s->flat_tris); dfree(s->flat_to_orig);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     delete s;
 }
@@ -622,6 +626,9 @@ const SrtTri* device_scene_tris(const DeviceScene* s) { return s->tris; }
 const SrtFlatUnit* device_scene_flat_units(const DeviceScene* s) { return s->flat_units; }
 const SrtTri* device_scene_flat_tris(const DeviceScene* s) { return s->flat_tris; }
 uint32_t device_scene_n_units(const DeviceScene* s) { return s->n_units; }
+uint32_t device_scene_num_units(const DeviceScene* s) { return s->n_units; }
+const uint32_t* device_scene_flat_to_orig(const DeviceScene* s) { return s->flat_to_orig; }
+void device_scene_flat_guard(const DeviceScene* s, float* guard, float* tol) { *guard = s->flat_guard; *tol = s->flat_tol; }
 double device_scene_origin_bound(const DeviceScene* s) { return s->origin_l1_bound; }
 void device_scene_bounds(const DeviceScene* s, float lo[3], float hi[3]) { for (int a = 0; a < 3; a++) { lo[a] = s->host_lo[a]; hi[a] = s->host_hi[a]; } }
 const SrtMaterial* device_scene_mats(const DeviceScene* s) { return s->mats; }

@@ -25,6 +25,8 @@ const SrtMaterial* device_scene_mats(const DeviceScene* s);
 uint32_t device_scene_ntris(const DeviceScene* s);
 uint32_t device_scene_nmats(const DeviceScene* s);
 const uint32_t* device_scene_sorted_idx(const DeviceScene* s);
+const uint32_t* device_scene_flat_to_orig(const DeviceScene* s);
+void device_scene_flat_guard(const DeviceScene* s, float* guard, float* tol);
 
 namespace {
 constexpr int kMaxRounds = 8;
@@ -231,6 +233,10 @@ static bool ensure_staging(DeviceRenderer* r, size_t dev_bytes, size_t host_byte
     return true;
 }
 
+// shared memory of a wavefront block ahead of the staged scene: queues [2][4][S] u16 | pixel slot [S] u32 | samples
+// started [S] u16 | passes [S] u16 | pixel xy [S] u32
+static void set_queue_layout(WaveParams& P) { P.queue_bytes = (28u * P.block_slots + 15u) & ~15u; }
+
 static bool renderer_setup(DeviceRenderer* r) {
     const RenderConfig& c = r->cfg;
     WaveParams& P = r->P;
@@ -242,6 +248,7 @@ static bool renderer_setup(DeviceRenderer* r) {
     P.flat_units = device_scene_flat_units(r->scene);
     P.flat_tris = device_scene_flat_tris(r->scene);
     P.n_units = (int)device_scene_n_units(r->scene);
+    device_scene_flat_guard(r->scene, &P.flat_guard, &P.flat_tol);
     P.mats = device_scene_mats(r->scene);
     P.n_tris = (int)device_scene_ntris(r->scene);
     P.n_mats = (int)device_scene_nmats(r->scene);
@@ -355,14 +362,14 @@ static bool renderer_setup(DeviceRenderer* r) {
     // (4 per thread); a rank with few pixels takes fewer paths per block so that every SM still gets work
     uint32_t resident = 0;
     for (P.block_slots = 1024;; P.block_slots >>= 1) {
-        P.queue_bytes = (28u * P.block_slots + 15u) & ~15u;  // queues [2][4][S] u16 | pixel slot [S] u32 | samples started [S] u16 (padded to 4 B) | pixel xy [S] u32
+        set_queue_layout(P);
         SRT_CUDA(T.configure(r->smem + P.queue_bytes));
         resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.block_threads, r->smem + P.queue_bytes));
         if (P.block_slots <= P.block_threads || (uint64_t)resident * P.block_slots <= (uint64_t)P.nslots) break;
     }
     if (c.block_slots >= 32 && c.block_slots <= 4096 && !(c.block_slots & (c.block_slots - 1))) {
         P.block_slots = (uint32_t)c.block_slots;
-        P.queue_bytes = (28u * P.block_slots + 15u) & ~15u;
+        set_queue_layout(P);
         SRT_CUDA(T.configure(r->smem + P.queue_bytes));
         resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.block_threads, r->smem + P.queue_bytes));
     }
@@ -721,51 +728,93 @@ void device_renderer_stats(const DeviceRenderer* r, srt_stats* s) {
     s->order_ms = r->cat_ms[0]; s->wavefront_ms = r->cat_ms[1]; s->megakernel_ms = r->cat_ms[2]; s->other_ms = r->cat_ms[3];
 }
 
+static std::atomic<int> g_query_strict{1};
+void set_query_fp_mode(int strict) { g_query_strict = strict ? 1 : 0; }
+
+namespace {
+struct QueryBuffers {  // device buffers and events of one closest-hit query call, released on every exit path
+    float *o = nullptr, *d = nullptr, *t = nullptr;
+    int32_t* tri = nullptr;
+    uint32_t* next = nullptr;
+    unsigned long long* cnt = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool init(uint32_t n, const float* ho, const float* hd) {
+        SRT_CUDA(cudaEventCreate(&e0));
+        SRT_CUDA(cudaEventCreate(&e1));
+        if (!device_pool_alloc((void**)&o, 3ull * n * sizeof(float)) || !device_pool_alloc((void**)&d, 3ull * n * sizeof(float)) ||
+            !device_pool_alloc((void**)&t, (size_t)n * sizeof(float)) || !device_pool_alloc((void**)&tri, (size_t)n * sizeof(int32_t)) ||
+            !device_pool_alloc((void**)&next, sizeof(uint32_t)) || !device_pool_alloc((void**)&cnt, 2 * sizeof(unsigned long long)))
+            return false;
+        SRT_CUDA(cudaMemcpy(o, ho, 3ull * n * sizeof(float), cudaMemcpyHostToDevice));
+        SRT_CUDA(cudaMemcpy(d, hd, 3ull * n * sizeof(float), cudaMemcpyHostToDevice));
+        return true;
+    }
+    bool read_back(uint32_t n, float* ht, int32_t* htri) {
+        SRT_CUDA(cudaMemcpy(ht, t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+        SRT_CUDA(cudaMemcpy(htri, tri, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        return true;
+    }
+    ~QueryBuffers() {
+        device_pool_free(o); device_pool_free(d); device_pool_free(t); device_pool_free(tri); device_pool_free(next); device_pool_free(cnt);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+};
+}  // namespace
+
 bool device_scene_trace(const DeviceScene* s, uint32_t n, const float* o, const float* d, float* t, int32_t* tri, float* ms, uint64_t* visits) {
     WaveParams P{};
     P.nodes = device_scene_nodes(s); P.tris = device_scene_tris(s); P.mats = device_scene_mats(s); P.n_tris = (int)device_scene_ntris(s);
-    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
-    int32_t* d_tri = nullptr;
-    cudaEvent_t e0, e1;
-    SRT_CUDA(cudaEventCreate(&e0));
-    SRT_CUDA(cudaEventCreate(&e1));
-    SRT_CUDA(cudaMalloc((void**)&d_o, 3ull * n * sizeof(float)));
-    SRT_CUDA(cudaMalloc((void**)&d_d, 3ull * n * sizeof(float)));
-    SRT_CUDA(cudaMalloc((void**)&d_t, (size_t)n * sizeof(float)));
-    SRT_CUDA(cudaMalloc((void**)&d_tri, (size_t)n * sizeof(int32_t)));
-    SRT_CUDA(cudaMemcpy(d_o, o, 3ull * n * sizeof(float), cudaMemcpyHostToDevice));
-    SRT_CUDA(cudaMemcpy(d_d, d, 3ull * n * sizeof(float), cudaMemcpyHostToDevice));
+    QueryBuffers q;
+    if (!q.init(n, o, d)) return false;
     // persistent warps that refill themselves from a ray counter: one resident wave is the whole grid
     const int grid = (int)std::min<uint64_t>((n + SRT_BLOCK - 1) / SRT_BLOCK, (uint64_t)sm_count() * 6);
-    uint32_t* d_next = nullptr;
-    SRT_CUDA(cudaMalloc((void**)&d_next, sizeof(uint32_t)));
-    const LaunchTable& T = table(1);
-    T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, nullptr, d_next, grid, nullptr);  // warm-up
-    SRT_CUDA(cudaEventRecord(e0));
-    T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, nullptr, d_next, grid, nullptr);
-    SRT_CUDA(cudaEventRecord(e1));
+    const LaunchTable& T = table(g_query_strict);
+    T.trace_rays(P, n, q.o, q.d, device_scene_sorted_idx(s), q.t, q.tri, nullptr, q.next, grid, nullptr);  // warm-up
+    SRT_CUDA(cudaEventRecord(q.e0));
+    T.trace_rays(P, n, q.o, q.d, device_scene_sorted_idx(s), q.t, q.tri, nullptr, q.next, grid, nullptr);
+    SRT_CUDA(cudaEventRecord(q.e1));
     count_launch(2);
     if (visits) {  // untimed third pass that counts node visits and leaf tests (algorithmic bytes of the walk)
-        unsigned long long* d_cnt = nullptr;
-        SRT_CUDA(cudaMalloc((void**)&d_cnt, 2 * sizeof(unsigned long long)));
-        SRT_CUDA(cudaMemset(d_cnt, 0, 2 * sizeof(unsigned long long)));
-        T.trace_rays(P, n, d_o, d_d, device_scene_sorted_idx(s), d_t, d_tri, d_cnt, d_next, grid, nullptr);
+        SRT_CUDA(cudaMemset(q.cnt, 0, 2 * sizeof(unsigned long long)));
+        T.trace_rays(P, n, q.o, q.d, device_scene_sorted_idx(s), q.t, q.tri, q.cnt, q.next, grid, nullptr);
         count_launch();
         unsigned long long h[2] = {0, 0};
-        SRT_CUDA(cudaMemcpy(h, d_cnt, sizeof h, cudaMemcpyDeviceToHost));
+        SRT_CUDA(cudaMemcpy(h, q.cnt, sizeof h, cudaMemcpyDeviceToHost));
         visits[0] = h[0]; visits[1] = h[1];
-        cudaFree(d_cnt);
     }
-    SRT_CUDA(cudaEventSynchronize(e1));
+    SRT_CUDA(cudaEventSynchronize(q.e1));
     SRT_CUDA_LAST();
     float el = 0;
-    SRT_CUDA(cudaEventElapsedTime(&el, e0, e1));
+    SRT_CUDA(cudaEventElapsedTime(&el, q.e0, q.e1));
     if (ms) *ms = el;
-    SRT_CUDA(cudaMemcpy(t, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
-    SRT_CUDA(cudaMemcpy(tri, d_tri, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_tri); cudaFree(d_next);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    return true;
+    return q.read_back(n, t, tri);
+}
+
+// the same queries through the wide-leaf closest hit the renderer uses for scenes of <= 32 units
+bool device_scene_trace_flat(const DeviceScene* s, uint32_t n, const float* o, const float* d, float* t, int32_t* tri) {
+    if (device_scene_n_units(s) == 0) { set_error("the scene has no wide leaf (more than 64 triangles or 32 units)"); return false; }
+    WaveParams P{};
+    P.flat_units = device_scene_flat_units(s); P.flat_tris = device_scene_flat_tris(s); P.n_units = (int)device_scene_n_units(s);
+    device_scene_flat_guard(s, &P.flat_guard, &P.flat_tol);
+    P.mats = device_scene_mats(s); P.n_tris = (int)device_scene_ntris(s); P.n_mats = (int)device_scene_nmats(s);
+    QueryBuffers q;
+    if (!q.init(n, o, d)) return false;
+    float zeros[4 * SRT_NS] = {0};  // load_scene also stages the CIE / background tables; the queries never read them
+    float* d_tables = nullptr;
+    if (!device_pool_alloc((void**)&d_tables, sizeof zeros)) return false;
+    struct Free { float* p; ~Free() { device_pool_free(p); } } free_tables{d_tables};
+    SRT_CUDA(cudaMemcpy(d_tables, zeros, sizeof zeros, cudaMemcpyHostToDevice));
+    P.cie = d_tables; P.bg = d_tables + 3 * SRT_NS;
+    const LaunchTable& T = table(g_query_strict);
+    const size_t smem = T.smem_bytes(P, 2);
+    SRT_CUDA(T.configure(smem));
+    const int grid = (int)std::min<uint64_t>((n + SRT_BLOCK - 1) / SRT_BLOCK, (uint64_t)sm_count() * 4);
+    T.trace_rays_flat(P, n, q.o, q.d, device_scene_flat_to_orig(s), q.t, q.tri, grid, smem, nullptr);
+    count_launch();
+    SRT_CUDA_LAST();
+    SRT_CUDA(cudaDeviceSynchronize());
+    return q.read_back(n, t, tri);
 }
 
 }  // namespace srt

@@ -71,6 +71,7 @@ struct SceneRef {
     const SrtTri* tris;
     const SrtFlatUnit* units;  // wide leaf only
     int n_units;
+    float flat_guard, flat_tol;
     const SrtMaterial* mats;
     const float* cie;  // x[95] y[95] z[95]
     const float* bg;   // [95]
@@ -104,12 +105,16 @@ __device__ __forceinline__ void hero_rotations(float hero, float wl[SRT_N_WL]) {
 }
 
 // ------------------------------------------------------------------------------ intersection
+// The plane part of tri::hit (primitives/tri.cu:10-16): denom = n.d and the numerator D - n.o of t.  ONE definition for the
+// exact test and for the wide-leaf pre-test, so that both see the same bits whatever the compiler contracts into FMAs.
+__device__ __forceinline__ float plane_denom(float4 q, V3 d) { return q.x * d.x + q.y * d.y + q.z * d.z; }
+__device__ __forceinline__ float plane_num(float4 q, V3 o) { return q.w - (q.x * o.x + q.y * o.y + q.z * o.z); }
 // tri::hit (primitives/tri.cu:3-45) on the packed 48-B triangle; returns t through t_out.
 __device__ __forceinline__ bool tri_test(const SrtTri* __restrict__ tp, V3 o, V3 d, float closest, float& t_out) {
     const float4 q0 = *reinterpret_cast<const float4*>(tp);
-    const float denom = q0.x * d.x + q0.y * d.y + q0.z * d.z;
+    const float denom = plane_denom(q0, d);
     if (fabsf(denom) < 1e-8f) return false;
-    const float t = (q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z)) / denom;
+    const float t = plane_num(q0, o) / denom;
     if (!(0.0f <= t && t <= closest)) return false;
     const float4 q1 = *(reinterpret_cast<const float4*>(tp) + 1);
     const float4 q2 = *(reinterpret_cast<const float4*>(tp) + 2);
@@ -171,10 +176,13 @@ __device__ __forceinline__ void consider_hit(const SrtTri* __restrict__ tris, in
 // Phase 1 only ever rejects pairs the exact test rejects too, so the result equals testing every
 // triangle exactly -- which is what "closest hit" means in the reference (bvh.cu:98-166).
 template <uint32_t BIT>
-__device__ __forceinline__ void flat_unit_test(const float4* __restrict__ up, int u, V3 o, V3 d, uint32_t& mask) {
+__device__ __forceinline__ void flat_unit_test(const float4* __restrict__ up, int u, V3 o, V3 d, float gd, float tol, uint32_t& mask) {
     const float4 pl = up[4 * u], A = up[4 * u + 1], B = up[4 * u + 2], C = up[4 * u + 3];
-    const float denom = __fmaf_rn(pl.z, d.z, __fmaf_rn(pl.y, d.y, pl.x * d.x));
-    const float num = pl.w - __fmaf_rn(pl.z, o.z, __fmaf_rn(pl.y, o.y, pl.x * o.x));
+    // the SAME two expressions the exact test evaluates (plane_denom / plane_num): for the unit's head triangle -- and for
+    // a partner whose plane is bit-identical -- numerator and denominator carry the reference's own rounding, and the
+    // approximate t below differs from the reference's quotient by the reciprocal's 2^-22 only, at ANY incidence angle
+    const float denom = plane_denom(pl, d);
+    const float num = plane_num(pl, o);
     const float t = num * rcp_approx(denom);
     const float px = __fmaf_rn(t, d.x, o.x), py = __fmaf_rn(t, d.y, o.y), pz = __fmaf_rn(t, d.z, o.z);
     const float al = __fmaf_rn(A.z, pz, __fmaf_rn(A.y, py, __fmaf_rn(A.x, px, A.w)));
@@ -184,13 +192,20 @@ __device__ __forceinline__ void flat_unit_test(const float4* __restrict__ up, in
     //   behind = t < 0 & |num| > tol
     //   out_i  = behind | alpha' < 0 | beta' < 0 | alpha'+beta' > c1       (first half)
     //   out_j  = behind | alpha' > c2 | beta' > c2 | alpha'+beta' < c3     (second half)
-    // Every comparison is false for a NaN operand, so NaN / inf can only ever keep a candidate (the
-    // exact test decides).  Written in PTX because the compiler otherwise builds the two mask bits
-    // through chains of selects (twice the instructions).
+    //   unsure = |num| < near & |denom| < gd                              (second half kept without a verdict)
+    // `unsure` only exists for pairs whose second triangle stores a plane that differs from the head's in the last bits
+    // (faces of a rotated box; near = 0 everywhere else): the partner's own numerator / denominator round differently,
+    // which moves its hit point by error / cos(incidence).  A grazing ray (|denom| < gd = guard |d|) can only hit inside
+    // the scene when it starts next to the plane (|num| < near); host/flat_leaf.cpp derives both constants.
+    // Every comparison is false for a NaN operand, so NaN / inf can only ever keep a candidate (the exact test
+    // decides).  Written in PTX because the compiler otherwise builds the two mask bits through chains of selects
+    // (twice the instructions).  ONE loop body for all units: a second, guard-free copy of it costs more in
+    // instruction-cache misses (measured: +7 %) than the three extra instructions do (+4 %).
     asm("{\n\t"
-        ".reg .pred pb, pi, pj;\n\t"
-        ".reg .f32 an;\n\t"
+        ".reg .pred pb, pi, pj, pg;\n\t"
+        ".reg .f32 an, ad;\n\t"
         "abs.f32 an, %2;\n\t"
+        "abs.f32 ad, %12;\n\t"
         "setp.lt.f32 pb, %1, 0f00000000;\n\t"
         "setp.gt.and.f32 pb, an, %3, pb;\n\t"
         "setp.lt.or.f32 pi, %4, 0f00000000, pb;\n\t"
@@ -199,32 +214,45 @@ __device__ __forceinline__ void flat_unit_test(const float4* __restrict__ up, in
         "setp.gt.or.f32 pj, %5, %8, pj;\n\t"
         "setp.gt.or.f32 pi, %6, %7, pi;\n\t"
         "setp.lt.or.f32 pj, %6, %9, pj;\n\t"
+        "setp.ge.f32 pg, an, %14;\n\t"
+        "setp.ge.or.f32 pg, ad, %13, pg;\n\t"
         "@!pi or.b32 %0, %0, %10;\n\t"
         "@!pj or.b32 %0, %0, %11;\n\t"
+        "@!pg or.b32 %0, %0, %11;\n\t"
         "}"
         : "+r"(mask)
-        : "f"(t), "f"(num), "f"(C.w), "f"(al), "f"(be), "f"(s), "f"(C.x), "f"(C.y), "f"(C.z), "n"(BIT), "n"(BIT << 1));
+        : "f"(t), "f"(num), "f"(tol), "f"(al), "f"(be), "f"(s), "f"(C.x), "f"(C.y), "f"(C.z), "n"(BIT), "n"(BIT << 1), "f"(denom), "f"(gd), "f"(C.w));
 }
-__device__ __forceinline__ int closest_hit_flat(const SceneRef& sc, V3 o, V3 d, float& t_hit) {
+// phase 1: the candidate mask of one ray (bit 2u / 2u+1: first / second triangle of unit u)
+__device__ __forceinline__ unsigned long long flat_candidates(const SceneRef& sc, V3 o, V3 d) {
     const float4* __restrict__ up = reinterpret_cast<const float4*>(sc.units);
     // groups of four units: inside a group the candidate bits are compile-time constants (predicated ORs
     // of immediates), one shift per group places them in the 64-bit mask; the <= 3 left-over units follow
     unsigned long long m = 0;
     const int n = sc.n_units, groups = n >> 2;
+    float gd;  // grazing threshold of this ray: guard * |d|, |d| to a relative 2^-22 and rounded up
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(gd) : "f"(len2(d)));
+    gd *= sc.flat_guard * 1.0001f;
+    const float tol = sc.flat_tol;
     for (int g = 0; g < groups; g++) {
         uint32_t loc = 0;
-        flat_unit_test<1u>(up, 4 * g, o, d, loc);
-        flat_unit_test<4u>(up, 4 * g + 1, o, d, loc);
-        flat_unit_test<16u>(up, 4 * g + 2, o, d, loc);
-        flat_unit_test<64u>(up, 4 * g + 3, o, d, loc);
+        flat_unit_test<1u>(up, 4 * g, o, d, gd, tol, loc);
+        flat_unit_test<4u>(up, 4 * g + 1, o, d, gd, tol, loc);
+        flat_unit_test<16u>(up, 4 * g + 2, o, d, gd, tol, loc);
+        flat_unit_test<64u>(up, 4 * g + 3, o, d, gd, tol, loc);
         m |= (unsigned long long)loc << (8 * g);
     }
 #pragma unroll 1
     for (int u = 4 * groups; u < n; u++) {
         uint32_t loc = 0;
-        flat_unit_test<1u>(up, u, o, d, loc);
+        flat_unit_test<1u>(up, u, o, d, gd, tol, loc);
         m |= (unsigned long long)loc << (2 * u);
     }
+    return m;
+}
+// phase 2, one ray per lane on its own: the megakernel, whose lanes sit in divergent loops
+__device__ __forceinline__ int closest_hit_flat(const SceneRef& sc, V3 o, V3 d, float& t_hit) {
+    const unsigned long long m = flat_candidates(sc, o, d);
     uint32_t m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
     float closest = FLT_MAX;
     int best = -1;
@@ -487,7 +515,7 @@ __device__ __forceinline__ int extend(const SceneRef& sc, const WaveParams& P, P
     float t = 0.f;
     int tri = -1;
     // camera rays of a whole warp often all pass beside the scene (46 % of the 16:9 frame lies outside
-    // the box): one cheap slab test spares the warp the whole wide-leaf loop.  `primary` is warp-uniform.
+    // the box): one cheap slab test spares the warp the whole wide-leaf loop.
     bool skip = false;
     if (FLAT && primary) skip = __all_sync(__activemask(), misses_scene_box(P, p.o, p.d));
     if (!skip) tri = closest_hit<FLAT>(sc, p.o, p.d, t);
@@ -517,7 +545,7 @@ __device__ __forceinline__ SceneRef load_scene(const WaveParams& P, unsigned cha
     SceneRef sc;
     sc.n_tris = P.n_tris;
     if (!SMEM) {
-        sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.mats = P.mats; sc.cie = P.cie; sc.bg = P.bg;
+        sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.flat_guard = 0.f; sc.flat_tol = 0.f; sc.mats = P.mats; sc.cie = P.cie; sc.bg = P.bg;
         return sc;
     }
     // layout: [nodes | pre-test records (flat scenes)] | tris | mats | cie | bg
@@ -538,6 +566,7 @@ __device__ __forceinline__ SceneRef load_scene(const WaveParams& P, unsigned cha
     sc.nodes = FLAT ? nullptr : reinterpret_cast<const SrtNode*>(dst);
     sc.units = FLAT ? reinterpret_cast<const SrtFlatUnit*>(dst) : nullptr;
     sc.n_units = FLAT ? P.n_units : 0;
+    sc.flat_guard = P.flat_guard; sc.flat_tol = P.flat_tol;
     sc.tris = reinterpret_cast<const SrtTri*>(dst + v_head);
     sc.mats = reinterpret_cast<const SrtMaterial*>(dst + v_head + v_tris);
     sc.cie = f;
@@ -632,7 +661,7 @@ __global__ void __launch_bounds__(256) k_prior_cost(WaveParams P) {
         const V3 o = mk(cam.center[0], cam.center[1], cam.center[2]);
         const V3 d = ((mk(cam.p00[0], cam.p00[1], cam.p00[2]) + ((float)(P.off_x + ci) * du)) + ((float)(P.off_y + cj) * dv)) - o;
         SceneRef sc;
-        sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
+        sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.flat_guard = 0.f; sc.flat_tol = 0.f; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
         float t;
         const int tri = closest_hit<false>(sc, o, d, t);
         c = 1;
@@ -898,7 +927,7 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_trace_rays(WaveParams P, uint32_t
                                                           const uint32_t* __restrict__ sorted_idx, float* __restrict__ t_out,
                                                           int32_t* __restrict__ tri_out, unsigned long long* counters, uint32_t* next_ray) {
     SceneRef sc;
-    sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
+    sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.flat_guard = 0.f; sc.flat_tol = 0.f; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
     const uint32_t lane = threadIdx.x & 31;
     int stack[64];
     int sp = 0, node = 0, best = -1;
@@ -951,6 +980,21 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_trace_rays(WaveParams P, uint32_t
     if (COUNT) { atomicAdd(counters, (unsigned long long)visits[0]); atomicAdd(counters + 1, (unsigned long long)visits[1]); }
 }
 
+// The same queries through the render path's wide-leaf closest hit (scenes of <= 32 units): one ray per thread, the scene
+// staged in shared memory exactly as k_wavefront stages it.  Exists so that tests can compare the conservative pre-test +
+// exact re-test with the plain LBVH walk ray by ray (tests/test_gpu_parity.py).
+__global__ void __launch_bounds__(SRT_BLOCK) k_trace_rays_flat(WaveParams P, uint32_t n, const float* __restrict__ o, const float* __restrict__ d,
+                                                               const uint32_t* __restrict__ flat_to_orig, float* __restrict__ t_out, int32_t* __restrict__ tri_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SceneRef sc = load_scene<true, true>(P, smem);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float t = 0.f;
+        const int tri = closest_hit<true>(sc, mk(o[3ull * i], o[3ull * i + 1], o[3ull * i + 2]), mk(d[3ull * i], d[3ull * i + 1], d[3ull * i + 2]), t);
+        t_out[i] = tri >= 0 ? t : -1.0f;
+        tri_out[i] = tri >= 0 ? (int32_t)flat_to_orig[tri] : -1;
+    }
+}
+
 // ------------------------------------------------------------------------------ launchers
 // mode 0: scene in global memory, LBVH walk; 1: scene staged in shared memory, LBVH walk;
 // 2: scene staged in shared memory, <= 64 triangles, wide-leaf closest hit (no tree walk)
@@ -979,6 +1023,7 @@ LaunchTable make_launch_table() {
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wavefront<false, false>, attr, b);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_megakernel<true, false>, attr, b);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_megakernel<true, true>, attr, b);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace_rays_flat, attr, b);
         }
         return e;
     };
@@ -1004,6 +1049,10 @@ LaunchTable make_launch_table() {
                    cudaStream_t st) { k_resolve<<<(w * h + 255) / 256, 256, 0, st>>>(acc, plane, img_w, ox, oy, w, h, spp, rgb); };
     t.resolve_slice = [](const float* acc, size_t plane, size_t first, uint32_t count, uint32_t out_plane, uint32_t spp, unsigned char* rgb, cudaStream_t st) {
         if (count) k_resolve_slice<<<(count + 255) / 256, 256, 0, st>>>(acc, plane, first, count, out_plane, spp, rgb);
+    };
+    t.trace_rays_flat = [](const WaveParams& P, uint32_t n, const float* o, const float* d, const uint32_t* flat_to_orig, float* t_out, int32_t* tri_out,
+                           int grid, size_t smem, cudaStream_t st) {
+        k_trace_rays_flat<<<grid, SRT_BLOCK, smem, st>>>(P, n, o, d, flat_to_orig, t_out, tri_out);
     };
     t.trace_rays = [](const WaveParams& P, uint32_t n, const float* o, const float* d, const uint32_t* sorted_idx, float* t_out, int32_t* tri_out,
                       unsigned long long* counters, uint32_t* next_ray, int grid, cudaStream_t st) {

@@ -21,6 +21,7 @@ struct WaveParams {
     const SrtFlatUnit* flat_units;  // wide-leaf pre-test units (mode 2), triangles in flat order follow
     const SrtTri* flat_tris;
     int n_units;
+    float flat_guard, flat_tol;     // wide leaf: grazing threshold on |n.d| / |d| (pairs with differing plane bits), and the `behind` tolerance on |D - n.o|
     const SrtMaterial* mats;
     const float* cie;    // x[95] y[95] z[95]
     const float* bg;     // background spectrum [95]
@@ -80,6 +81,8 @@ struct LaunchTable {
     void (*resolve)(const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,
                     cudaStream_t);
     void (*resolve_slice)(const float* acc, size_t plane, size_t first, uint32_t count, uint32_t out_plane, uint32_t spp, unsigned char* rgb, cudaStream_t);
+    void (*trace_rays_flat)(const WaveParams&, uint32_t n, const float* o, const float* d, const uint32_t* flat_to_orig, float* t_out, int32_t* tri_out,
+                            int grid, size_t smem, cudaStream_t);
     void (*trace_rays)(const WaveParams&, uint32_t n, const float* o, const float* d, const uint32_t* sorted_idx, float* t_out, int32_t* tri_out,
                        unsigned long long* counters, uint32_t* next_ray, int grid, cudaStream_t);
 };

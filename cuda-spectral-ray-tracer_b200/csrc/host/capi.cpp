@@ -131,6 +131,7 @@ int srt_scene_camera(const srt_scene* s, srt_camera* out) {
     return srt_scene_camera_res(s, p.xres, p.yres, out);
 }
 uint32_t srt_scene_num_tris(const srt_scene* s) { return s ? (uint32_t)s->s.desc.tris.size() : 0; }
+uint32_t srt_scene_num_units(const srt_scene* s) { return s && s->s.dev ? device_scene_num_units(s->s.dev) : 0; }
 uint32_t srt_scene_num_materials(const srt_scene* s) { return s ? (uint32_t)s->s.desc.mats.size() : 0; }
 int srt_scene_get_tris(const srt_scene* s, float* f, int32_t* iv) {
     if (!s || !f || !iv) { set_error("null argument"); return SRT_ERR_ARG; }
@@ -177,6 +178,12 @@ int srt_scene_trace_rays(const srt_scene* s, uint32_t n, const float* o, const f
     if (!s || !s->s.dev || !o || !d || !t_out || !tri_out) { set_error("bad argument"); return SRT_ERR_ARG; }
     if (n == 0) return SRT_OK;
     return device_scene_trace(s->s.dev, n, o, d, t_out, tri_out, ms_out, nullptr) ? SRT_OK : SRT_ERR_CUDA;
+}
+void srt_set_query_fp_mode(int strict) { set_query_fp_mode(strict); }
+int srt_scene_trace_rays_flat(const srt_scene* s, uint32_t n, const float* o, const float* d, float* t_out, int32_t* tri_out) {
+    if (!s || !s->s.dev || !o || !d || !t_out || !tri_out) { set_error("bad argument"); return SRT_ERR_ARG; }
+    if (n == 0) return SRT_OK;
+    return device_scene_trace_flat(s->s.dev, n, o, d, t_out, tri_out) ? SRT_OK : SRT_ERR_STATE;
 }
 int srt_scene_trace_rays_counted(const srt_scene* s, uint32_t n, const float* o, const float* d, float* t_out, int32_t* tri_out, float* ms_out,
                                  uint64_t visits_out[2]) {

@@ -121,6 +121,8 @@ struct FlatLeaf {
     std::vector<SrtFlatUnit> units;   // <= 32
     std::vector<SrtTri> tris;         // 2 per unit
     std::vector<uint32_t> to_orig;    // flat position -> original triangle index
+    float guard = 0.f;                // grazing threshold on |n.d| / |d| for pairs whose partner plane differs from the head's in the last bits
+    float tol = 0.f;                  // `behind` tolerance on |D - n.o| (the largest over the units)
 };
 bool build_flat_leaf(const std::vector<HostTri>& tris, const std::vector<HostMaterial>& mats, const std::vector<uint32_t>& prio,
                      double origin_l1_bound, FlatLeaf& out);
@@ -156,7 +158,10 @@ void device_scene_destroy(DeviceScene*);
 bool device_scene_build_lbvh(DeviceScene*, int repeats, float ms_out[5]);
 bool device_scene_download_lbvh(const DeviceScene*, LbvhDump& out);
 bool device_scene_trace(const DeviceScene*, uint32_t n, const float* o, const float* d, float* t, int32_t* tri, float* ms, uint64_t* visits);
+void set_query_fp_mode(int strict);
+bool device_scene_trace_flat(const DeviceScene*, uint32_t n, const float* o, const float* d, float* t, int32_t* tri);
 double device_scene_lbvh_ms(const DeviceScene*);
+uint32_t device_scene_num_units(const DeviceScene*);
 
 struct RenderConfig {
     srt_camera cam;

@@ -10,7 +10,7 @@ import pathlib
 import numpy as np
 
 PKG_DIR = pathlib.Path(__file__).resolve().parents[1]
-LIB_PATH = PKG_DIR / "libsrt.so"
+LIB_PATH = pathlib.Path(os.environ.get("SRT_LIB", PKG_DIR / "libsrt.so"))  # SRT_LIB: A/B runs against another build of the library
 
 
 class SrtError(RuntimeError):
@@ -81,13 +81,15 @@ _SIGS = [
     ("srt_scene_result", C.c_int, [_P, C.POINTER(C.c_char_p)]),
     ("srt_scene_camera", C.c_int, [_P, C.POINTER(Camera)]),
     ("srt_scene_camera_res", C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(Camera)]),
-    ("srt_scene_num_tris", C.c_uint32, [_P]), ("srt_scene_num_materials", C.c_uint32, [_P]),
+    ("srt_scene_num_tris", C.c_uint32, [_P]), ("srt_scene_num_materials", C.c_uint32, [_P]), ("srt_scene_num_units", C.c_uint32, [_P]),
     ("srt_set_ref_compat", None, [C.c_int]),
     ("srt_glass_coefficients", C.c_int, [C.c_int, _P, _P]),
     ("srt_scene_get_tris", C.c_int, [_P, _P, _P]), ("srt_scene_get_materials", C.c_int, [_P, _P, _P]),
     ("srt_scene_get_lbvh", C.c_int, [_P] * 8),
     ("srt_scene_rebuild_lbvh", C.c_int, [_P, C.c_int, _P]),
     ("srt_scene_trace_rays", C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, _P]),
+    ("srt_set_query_fp_mode", None, [C.c_int]),
+    ("srt_scene_trace_rays_flat", C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     ("srt_scene_trace_rays_counted", C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, _P, _P]),
     ("srt_render_manager_create", _P, [_P, C.POINTER(Camera), _P, _P, _P]),
     ("srt_render_manager_destroy", None, [_P]),
@@ -131,6 +133,8 @@ def lib():
             raise SrtError("libsrt.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
         L = C.CDLL(str(LIB_PATH))
         for name, res, args in _SIGS:
+            if "SRT_LIB" in os.environ and not hasattr(L, name):
+                continue  # A/B runs against an older build
             f = getattr(L, name)
             f.restype = res
             f.argtypes = args
@@ -235,6 +239,7 @@ class Scene:
             raise SrtError(self.msg)
         self.ntris = L.srt_scene_num_tris(self.h)
         self.nmats = L.srt_scene_num_materials(self.h)
+        self.nunits = L.srt_scene_num_units(self.h) if hasattr(L, "srt_scene_num_units") else -1
 
     def __del__(self):
         if getattr(self, "h", None) and lib is not None:  # `lib` is gone when the interpreter shuts down
@@ -285,6 +290,17 @@ class Scene:
             return t, tri, ms.value, (int(v[0]), int(v[1]))
         _check(lib().srt_scene_trace_rays(self.h, n, o.ctypes.data, d.ctypes.data, t.ctypes.data, tri.ctypes.data, C.byref(ms)))
         return t, tri, ms.value
+
+
+def _trace_rays_flat(self, o, d):
+    o = np.ascontiguousarray(o, np.float32); d = np.ascontiguousarray(d, np.float32)
+    n = o.shape[0]
+    t = np.zeros(n, np.float32); tri = np.zeros(n, np.int32)
+    _check(lib().srt_scene_trace_rays_flat(self.h, n, o.ctypes.data, d.ctypes.data, t.ctypes.data, tri.ctypes.data))
+    return t, tri
+
+
+Scene.trace_rays_flat = _trace_rays_flat
 
 
 class Comm:

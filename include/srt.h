@@ -118,6 +118,9 @@ int srt_scene_camera(const srt_scene*, srt_camera* out);
 int srt_scene_camera_res(const srt_scene*, uint32_t w, uint32_t h, srt_camera* out);
 uint32_t srt_scene_num_tris(const srt_scene*);
 uint32_t srt_scene_num_materials(const srt_scene*);
+/* pre-test units of the wide-leaf closest hit (a triangle, or a coplanar parallelogram pair such as every tri_quad of the
+ * reference emits); 0 when the scene is too large for it (> 64 triangles or > 32 units) and is traversed through the LBVH */
+uint32_t srt_scene_num_units(const srt_scene*);
 /* 1 = dielectrics reproduce material.cuh:67 (C := B), the default; 0 = physical Sellmeier.
  * Must be set before srt_scene_create*. */
 void srt_set_ref_compat(int on);
@@ -144,6 +147,13 @@ int srt_scene_rebuild_lbvh(srt_scene*, int repeats, float ms_out[5]);
  * ms_out (optional) = kernel time from CUDA events. */
 int srt_scene_trace_rays(const srt_scene*, uint32_t n, const float* o, const float* d, float* t_out,
                          int32_t* tri_out, float* ms_out);
+
+/* FP mode of the kernels behind the srt_scene_trace_rays* queries: 1 (default) = strict (-fmad=false), 0 = fast (FMA contraction) */
+void srt_set_query_fp_mode(int strict);
+/* the same queries answered by the wide-leaf closest hit the renderer uses for scenes of <= 32 units (conservative
+ * pre-test over all units, exact reference arithmetic on the survivors); fails when srt_scene_num_units() is 0.
+ * Must agree with srt_scene_trace_rays ray by ray. */
+int srt_scene_trace_rays_flat(const srt_scene*, uint32_t n, const float* o, const float* d, float* t_out, int32_t* tri_out);
 
 /* same, plus visits_out = {BVH nodes visited, leaf triangles tested} summed over all rays (counted in an
  * extra untimed pass): the algorithmic traffic of the walk is 32 B per node visit + 48 B per triangle test */
