@@ -501,6 +501,26 @@ def test_pretest_is_conservative_on_adversarial_rays(srt):
         srt.lib().srt_set_query_fp_mode(1)
 
 
+def test_integration_shim_renders_like_the_library(srt, tmp_path):
+    """the reference's main.cpp call sequence (scene_manager -> frame_buffer -> render_manager -> init_renderer ->
+    init_device_params -> render_cycle + update_fb loop -> end_render) on include/srt_shim.h, chunked and threaded like the
+    reference runs it: the picture equals the library's own render of the same arguments"""
+    import subprocess
+    from test_host_cpu import build_shim_driver
+
+    exe = build_shim_driver(tmp_path)
+    for extra, kw in ((["-xc", "48", "-yc", "27"], dict(chunk=(48, 27))), (["--single-thread"], {})):
+        ppm = tmp_path / "shim.ppm"
+        out = subprocess.run([str(exe), "-s", "2", "-xr", "96", "-ar", "16/9", "-ns", "4", "-bl", "10", "--no-show", "--strict-fp", "--out", str(ppm)] + extra,
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-500:] + out.stderr[-500:]
+        raw = ppm.read_bytes()
+        assert raw.startswith(b"P6\n96 54\n255\n")
+        img = np.frombuffer(raw[len(b"P6\n96 54\n255\n"):], np.uint8).reshape(54, 96, 3).transpose(2, 0, 1)
+        want, _, _ = srt.render(scene_id=2, w=96, h=54, spp=4, bounce=10, strict=True, **kw)
+        assert np.array_equal(img, want.astype(np.uint8))
+
+
 def _run_ranks(world, tmp_path, scene, w, h, spp, strict):
     import subprocess
     import sys

@@ -137,6 +137,26 @@ def test_physical_mode_materials_match_the_patched_reference(srt):
     assert L.srt_glass_coefficients(7, b.ctypes.data, c.ctypes.data) != 0
 
 
+def build_shim_driver(out_dir):
+    """compiles tests/shim/shim_main.cpp -- the reference's main.cpp:16-133 call sequence on the class names of include/srt_shim.h --
+    and links it against libsrt.so"""
+    exe = pathlib.Path(out_dir) / "shim_main"
+    pkg = ROOT / "cuda-spectral-ray-tracer_b200"
+    out = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I" + str(ROOT / "include"), str(ROOT / "tests" / "shim" / "shim_main.cpp"), "-o", str(exe),
+                          "-L" + str(pkg), "-lsrt", "-Wl,-rpath," + str(pkg)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    return exe
+
+
+def test_integration_shim_compiles_and_links(srt, tmp_path):
+    """INTEGRATION.md section 2 is real code: include/srt_shim.h + a main.cpp-shaped driver build warning-free against the C-ABI;
+    without a GPU the driver stops at the scene with the library's no-device error (no CPU fallback)"""
+    exe = build_shim_driver(tmp_path)
+    if srt.lib().srt_device_count() == 0:
+        out = subprocess.run([str(exe), "-s", "1", "-xr", "32", "--no-show"], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 1 and "no CUDA device" in out.stderr
+
+
 def test_soup_and_mesh_host_side(srt):
     import oracle
 
