@@ -1,13 +1,15 @@
 // LBVH construction on the device (Karras 2012) + the standalone closest-hit query kernel.
 //
-//   bounds   : leaf box = padded triangle box, centroid, scene box (float atomics on ordered ints)
-//   morton   : 30-bit code per triangle (10 bits per axis, x highest)
+//   bounds   : leaf box = padded triangle box, centroid, one partial scene box per block; also clears what the later
+//              phases count in (refit arrival flags, look-back status words, digit histograms, tile tickets)
+//   morton   : scene box = union of the partial boxes; 30-bit code per triangle (10 bits per axis, x highest)
 //   sort     : hand-written ONESWEEP least-significant-digit radix sort, 4 passes of 8 bits,
 //              one global histogram pre-pass, decoupled look-back, warp match/ballot ranking,
 //              stable => equal codes stay in triangle-index order
 //   hierarchy: one thread per internal node, clz(key_i ^ key_j) prefix lengths, ties broken by index
-//   refit    : bottom-up, one thread per leaf, second arrival at a node does the union
-//   emit     : 64-B traversal nodes carrying both child boxes + triangles permuted to leaf order
+//   refit    : bottom-up, one thread per leaf, second arrival at a node does the union and emits the 64-B traversal node
+//              carrying both child boxes (no fences: published boxes carry the build's epoch)
+//   permute  : triangles to leaf order -- a pure gather, on a second stream next to hierarchy + refit
 //
 // Specification and bit-exactness oracle: oracle/lbvh_oracle.c.  The reference
 // itself builds its BVH serially in one thread (bvh/bvh.cu:206-345, scene/scene.cu:9-20); this
@@ -23,6 +25,7 @@
 namespace srt {
 
 std::atomic<uint64_t> g_kernel_launches{0};
+static std::atomic<uint32_t> g_refit_epoch{0};  // marks the node boxes a build has published (k_refit_emit)
 uint64_t kernel_launches() { return g_kernel_launches.load(); }
 
 bool cuda_ok(cudaError_t e, const char* what, const char* file, int line) {
@@ -64,6 +67,7 @@ struct DeviceScene {
     uint32_t* lookback = nullptr; // SORT_PASSES x tiles x RADIX status words
     uint32_t* tile_counter = nullptr;  // SORT_PASSES dynamic tile ids
     int32_t *left = nullptr, *right = nullptr, *parent = nullptr;
+    float* block_boxes = nullptr;  // kBoundsBlocks x 6 partial scene boxes
     float4 *node_box_lo = nullptr, *node_box_hi = nullptr;  // (2n-1) each: (xmin,ymin,zmin,-), (xmax,ymax,zmax,-)
     uint32_t* visit = nullptr;    // n-1 refit arrival flags
     SrtNode* nodes = nullptr;     // n-1 traversal nodes
@@ -79,7 +83,9 @@ struct DeviceScene {
     uint32_t tiles = 0;
     cudaEvent_t ev[6];
     double last_build_ms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // the caller's stream (null = default)
+    cudaStream_t side = nullptr;     // triangle permutation next to hierarchy + refit
+    cudaEvent_t ev_sorted = nullptr, ev_side = nullptr;
 };
 
 // ---- float <-> order-preserving uint for atomic min/max ----
@@ -91,22 +97,23 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
 
-// resets everything small the build accumulates into: scene box, digit histograms, the sort's tile tickets
-__global__ void k_reset_build(uint32_t* box, uint32_t* hist, uint32_t n_hist, uint32_t* tickets, uint32_t n_tickets) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 6) box[i] = (i & 1) ? f2ord(-INFINITY) : f2ord(INFINITY);
-    if (i < n_hist) hist[i] = 0;
-    if (i < n_tickets) tickets[i] = 0;
-}
+constexpr int kBoundsBlocks = 296;  // 2 per SM: few enough that every Morton block can afford to re-reduce the partial boxes
 
-// leaf box (bvh/aabb.cuh:49-57 + pad :93-102), centroid (primitives/tri.cuh:73-77), scene box
+// leaf box (bvh/aabb.cuh:49-57 + pad :93-102), centroid (primitives/tri.cuh:73-77), one partial scene box per block
+// (min / max are exact, so any reduction order gives the bits of the serial union); and the housekeeping of the build:
+// refit arrival flags, look-back status words, digit histograms and tile tickets start at zero.
 __global__ void __launch_bounds__(256) k_bounds(const float* __restrict__ verts, uint32_t n, float4* __restrict__ leaf_boxes,
-                                                float* __restrict__ centroids, uint32_t* __restrict__ scene_box) {
-    __shared__ uint32_t sbox[6];
-    if (threadIdx.x < 6) sbox[threadIdx.x] = (threadIdx.x & 1) ? f2ord(-INFINITY) : f2ord(INFINITY);
-    __syncthreads();
+                                                float* __restrict__ centroids, float* __restrict__ block_boxes, uint32_t* __restrict__ visit,
+                                                uint32_t* __restrict__ lookback, uint32_t n_lookback, uint32_t* __restrict__ hist, uint32_t n_hist,
+                                                uint32_t* __restrict__ tickets, uint32_t n_tickets) {
+    __shared__ float sbox[8][6];
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    for (uint32_t i = gtid; i < n; i += gsize) visit[i] = 0;
+    for (uint32_t i = gtid; i < n_lookback; i += gsize) lookback[i] = 0;
+    if (gtid < n_hist) hist[gtid] = 0;
+    if (gtid < n_tickets) tickets[gtid] = 0;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (uint32_t i = gtid; i < n; i += gsize) {
         float v[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) v[k] = verts[9ull * i + k];
@@ -137,19 +144,14 @@ __global__ void __launch_bounds__(256) k_bounds(const float* __restrict__ verts,
             lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
             hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicMin(&sbox[2 * a], f2ord(lo[a]));
-            atomicMax(&sbox[2 * a + 1], f2ord(hi[a]));
-        }
+        if ((threadIdx.x & 31) == 0) { sbox[threadIdx.x >> 5][2 * a] = lo[a]; sbox[threadIdx.x >> 5][2 * a + 1] = hi[a]; }
     }
     __syncthreads();
     if (threadIdx.x < 6) {
-        if (threadIdx.x & 1) atomicMax(&scene_box[threadIdx.x], sbox[threadIdx.x]);
-        else atomicMin(&scene_box[threadIdx.x], sbox[threadIdx.x]);
+        float v = sbox[0][threadIdx.x];
+        for (int w = 1; w < 8; w++) v = (threadIdx.x & 1) ? fmaxf(v, sbox[w][threadIdx.x]) : fminf(v, sbox[w][threadIdx.x]);
+        block_boxes[6 * blockIdx.x + threadIdx.x] = v;
     }
-}
-__global__ void k_decode_scene_box(uint32_t* box) {
-    if (threadIdx.x < 6) box[threadIdx.x] = __float_as_uint(ord2f(box[threadIdx.x]));
 }
 
 __device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
@@ -165,13 +167,36 @@ __device__ __forceinline__ uint32_t quant10(float c, float lo, float hi) {
     return (uint32_t)x;
 }
 // Morton code per triangle + identity payload + the global digit histogram of all 4 passes
-__global__ void __launch_bounds__(256) k_morton_hist(const float* __restrict__ centroids, const float* __restrict__ scene_box, uint32_t n,
-                                                     uint32_t* __restrict__ codes, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                     uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(256) k_morton_hist(const float* __restrict__ centroids, const float* __restrict__ block_boxes, int n_block_boxes,
+                                                     float* __restrict__ scene_box, uint32_t n, uint32_t* __restrict__ codes, uint32_t* __restrict__ keys,
+                                                     uint32_t* __restrict__ vals, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[SORT_PASSES * RADIX];
+    __shared__ float sbox[8][6], box[6];
     for (int i = threadIdx.x; i < SORT_PASSES * RADIX; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    const float b0 = scene_box[0], b1 = scene_box[1], b2 = scene_box[2], b3 = scene_box[3], b4 = scene_box[4], b5 = scene_box[5];
+    {  // scene box = union of k_bounds' partial boxes (a few KB, L2 resident); block 0 also publishes it
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = threadIdx.x; i < n_block_boxes; i += blockDim.x)
+#pragma unroll
+            for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], block_boxes[6 * i + 2 * a]); hi[a] = fmaxf(hi[a], block_boxes[6 * i + 2 * a + 1]); }
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            }
+            if ((threadIdx.x & 31) == 0) { sbox[threadIdx.x >> 5][2 * a] = lo[a]; sbox[threadIdx.x >> 5][2 * a + 1] = hi[a]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            float v = sbox[0][threadIdx.x];
+            for (int w = 1; w < 8; w++) v = (threadIdx.x & 1) ? fmaxf(v, sbox[w][threadIdx.x]) : fminf(v, sbox[w][threadIdx.x]);
+            box[threadIdx.x] = v;
+            if (blockIdx.x == 0) scene_box[threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+    const float b0 = box[0], b1 = box[1], b2 = box[2], b3 = box[3], b4 = box[4], b5 = box[5];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t xx = expand_bits(quant10(centroids[3ull * i], b0, b1));
         const uint32_t yy = expand_bits(quant10(centroids[3ull * i + 1], b2, b3));
@@ -187,33 +212,13 @@ __global__ void __launch_bounds__(256) k_morton_hist(const float* __restrict__ c
     for (int i = threadIdx.x; i < SORT_PASSES * RADIX; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
-// exclusive scan of each pass' 256 digit counts (one block, one warp-scan per 32 digits)
-__global__ void k_scan_hist(uint32_t* hist, int rows) {
-    __shared__ uint32_t warp_tot[RADIX / 32];
-    for (int p = 0; p < rows; p++) {
-        const uint32_t v = hist[p * RADIX + threadIdx.x];
-        uint32_t inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if ((threadIdx.x & 31) >= o) inc += t;
-        }
-        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
-        __syncthreads();
-        uint32_t base = 0;
-        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += warp_tot[w];
-        hist[p * RADIX + threadIdx.x] = base + inc - v;
-        __syncthreads();
-    }
-}
-
 // ---- one onesweep pass --------------------------------------------------------------------
 // status word: [31:30] 0 = empty, 1 = tile-local count, 2 = inclusive prefix; [29:0] value
 constexpr uint32_t LB_LOCAL = 1u << 30, LB_INCL = 2u << 30, LB_MASK = (1u << 30) - 1;
 
 __global__ void __launch_bounds__(SORT_THREADS) k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                            uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
-                                                           const uint32_t* __restrict__ digit_base, volatile uint32_t* lookback,
+                                                           const uint32_t* __restrict__ digit_count, volatile uint32_t* lookback,
                                                            uint32_t* tile_counter) {
     __shared__ uint32_t s_warp_hist[SORT_WARPS][RADIX];  // per-warp digit counts -> per-warp exclusive offsets
     __shared__ uint32_t s_tile_off[RADIX];               // exclusive offset of each digit inside the sorted tile
@@ -221,10 +226,25 @@ __global__ void __launch_bounds__(SORT_THREADS) k_onesweep(const uint32_t* __res
     __shared__ uint32_t s_keys[SORT_TILE];
     __shared__ uint32_t s_vals[SORT_TILE];
     __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_dtot[SORT_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // global base of every digit = exclusive scan of the pass' 256 digit counts: every block does the tiny scan itself
+    uint32_t digit_base;
+    {
+        const uint32_t c = digit_count[tid];  // SORT_THREADS == RADIX
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_dtot[warp] = inc;
+        digit_base = inc - c;  // + the totals of the warps before, added after the first barrier below
+    }
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);  // dynamic tile id: earlier tiles are always already running
     for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_warp_hist[0][0])[i] = 0;
     __syncthreads();
+    for (int w = 0; w < warp; w++) digit_base += s_dtot[w];
     const uint32_t tile = s_tile;
     const uint32_t tile_base = tile * SORT_TILE;
     // warp-striped load: warp w owns [w*512, (w+1)*512), item i of lane l = w*512 + i*32 + l
@@ -281,7 +301,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_onesweep(const uint32_t* __res
         }
         __threadfence();
         *lb = LB_INCL | (excl + local_count);
-        s_glob_off[d] = digit_base[d] + excl;
+        s_glob_off[d] = digit_base + excl;
     }
     // exclusive scan of the tile-local digit counts -> position of each digit inside the sorted tile
     {
@@ -376,9 +396,8 @@ const uint32_t* pixel_order_build(PixelOrder* o, const uint32_t* cost, uint32_t 
     if (cudaMemsetAsync(o->small, 0, ((size_t)RADIX + 64 + (size_t)tiles * RADIX) * sizeof(uint32_t), st) != cudaSuccess) return nullptr;
     const int grid = (int)min((uint32_t)(148 * 8), (n + 255) / 256);
     k_cost_keys<<<grid, 256, 0, st>>>(cost, n, samples, o->keys[0], o->vals[0], hist);
-    k_scan_hist<<<1, RADIX, 0, st>>>(hist, 1);
     k_onesweep<<<tiles, SORT_THREADS, 0, st>>>(o->keys[0], o->vals[0], o->keys[1], o->vals[1], n, 0, hist, lookback, ticket);
-    count_launch(3);
+    count_launch(2);
     return o->vals[1];
 }
 
@@ -418,33 +437,45 @@ __global__ void __launch_bounds__(256) k_hierarchy(const uint32_t* __restrict__ 
     parent[R] = i;
 }
 
-// ---- refit + emit (one kernel) ------------------------------------------------------------------
-// One thread per leaf: writes its leaf-order triangle, then climbs.  The first thread to reach an
-// internal node leaves (its subtree's box is already published); the second one owns both child
-// boxes -- its own running box and the sibling's published one -- so it unions them (fmin/fmax:
-// order independent, hence deterministic), publishes the node's box for the level above AND writes
-// the 64-byte traversal node right there.  Boxes travel as two 16-byte vectors (lo.xyz, hi.xyz).
+// ---- refit + emit ---------------------------------------------------------------------------------
+// One thread per leaf climbs.  The first thread to reach an internal node leaves (its subtree's box is already
+// published); the second one owns both child boxes -- its own running box and the sibling's published one -- so it
+// unions them (fmin/fmax: order independent, hence deterministic), publishes the node's box for the level above AND
+// writes the 64-byte traversal node right there.  Boxes travel as two 16-byte vectors (lo.xyz | epoch, hi.xyz | epoch).
 __device__ __forceinline__ float widen_lo(float v) { return v - fabsf(v) * 2.4e-7f; }
 __device__ __forceinline__ float widen_hi(float v) { return v + fabsf(v) * 2.4e-7f; }
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 __global__ void __launch_bounds__(256) k_refit_emit(int n, const uint32_t* __restrict__ sorted_idx, const float4* __restrict__ leaf_boxes,
                                                     const int32_t* __restrict__ left, const int32_t* __restrict__ right,
-                                                    const int32_t* __restrict__ parent, float4* node_box_lo, float4* node_box_hi, uint32_t* visit,
-                                                    const SrtTri* __restrict__ tris_in, SrtNode* __restrict__ nodes, SrtTri* __restrict__ tris) {
+                                                    const int32_t* __restrict__ parent, float4* node_box_lo,
+                                                    float4* node_box_hi, uint32_t* visit, SrtNode* __restrict__ nodes, uint32_t epoch_bits) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint32_t src = sorted_idx[k];
-    tris[k] = tris_in[src];
     float4 lo = leaf_boxes[2ull * src], hi = leaf_boxes[2ull * src + 1];
+    const float epoch = __uint_as_float(epoch_bits);  // only ever compared as bits
+    lo.w = hi.w = epoch;
     int from = n - 1 + k;
     node_box_lo[from] = lo;
     node_box_hi[from] = hi;
     int node = parent[from];
     while (node >= 0) {
-        __threadfence();
+        // the node's topology is requested before the counter is bumped: three independent loads whose latency overlaps the atomic's
+        const int L = __ldcg(left + node), R = __ldcg(right + node), up = __ldcg(parent + node);
         if (atomicAdd(&visit[node], 1u) == 0) return;  // the sibling subtree finishes this node
-        const int L = left[node], R = right[node];
         const int other = L == from ? R : L;
-        const float4 olo = __ldcg(node_box_lo + other), ohi = __ldcg(node_box_hi + other);
+        // No fence anywhere: a published box carries this build's epoch in the fourth lane of both of its 16-byte halves
+        // (a 16-byte store lands as one piece), so the finisher simply re-reads the sibling's halves until both show the
+        // epoch -- its counter increment may have overtaken the sibling's stores, which were issued before the sibling's own.
+        float4 olo, ohi;
+        do {
+            olo = ld_volatile_f4(node_box_lo + other);
+            ohi = ld_volatile_f4(node_box_hi + other);
+        } while (__float_as_uint(olo.w) != epoch_bits || __float_as_uint(ohi.w) != epoch_bits);
         const float4 llo = L == from ? lo : olo, lhi = L == from ? hi : ohi;  // left child's box
         const float4 rlo = L == from ? olo : lo, rhi = L == from ? ohi : hi;  // right child's box
         SrtNode nd;
@@ -455,13 +486,22 @@ __global__ void __launch_bounds__(256) k_refit_emit(int n, const uint32_t* __res
         nd.child1 = R >= n - 1 ? ~(R - (n - 1)) : R;
         nd.pad0 = nd.pad1 = 0;
         nodes[node] = nd;
-        lo = make_float4(fminf(lo.x, olo.x), fminf(lo.y, olo.y), fminf(lo.z, olo.z), 0.f);
-        hi = make_float4(fmaxf(hi.x, ohi.x), fmaxf(hi.y, ohi.y), fmaxf(hi.z, ohi.z), 0.f);
+        lo = make_float4(fminf(lo.x, olo.x), fminf(lo.y, olo.y), fminf(lo.z, olo.z), epoch);
+        hi = make_float4(fmaxf(hi.x, ohi.x), fmaxf(hi.y, ohi.y), fmaxf(hi.z, ohi.z), epoch);
         node_box_lo[node] = lo;
         node_box_hi[node] = hi;
         from = node;
-        node = parent[node];
+        node = up;
     }
+}
+// triangles to leaf order: three lanes move one 48-byte triangle, 16 bytes each, so the stores are fully coalesced.
+// A pure gather that needs nothing but the sorted order: it runs on a second stream next to hierarchy + refit.
+__global__ void __launch_bounds__(256) k_permute_tris(uint32_t n, const uint32_t* __restrict__ sorted_idx, const float4* __restrict__ tris_in,
+                                                      float4* __restrict__ tris) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3u * n) return;
+    const uint32_t k = t / 3u, part = t - 3u * k;
+    tris[t] = __ldg(tris_in + 3ull * sorted_idx[k] + part);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -499,9 +539,15 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
               dalloc(s->centroids, 3ull * n) && dalloc(s->scene_box, 6) && dalloc(s->codes, n) && dalloc(s->keys[0], n) && dalloc(s->keys[1], n) &&
               dalloc(s->vals[0], n) && dalloc(s->vals[1], n) && dalloc(s->hist, SORT_PASSES * RADIX) &&
               dalloc(s->lookback, (size_t)SORT_PASSES * (s->tiles ? s->tiles : 1) * RADIX) && dalloc(s->tile_counter, SORT_PASSES) &&
-              dalloc(s->left, n) && dalloc(s->right, n) && dalloc(s->parent, 2ull * n) && dalloc(s->node_box_lo, 2ull * n) && dalloc(s->node_box_hi, 2ull * n) && dalloc(s->visit, n) &&
+              dalloc(s->left, n) && dalloc(s->right, n) && dalloc(s->parent, 2ull * n) && dalloc(s->block_boxes, 6 * kBoundsBlocks) && dalloc(s->node_box_lo, 2ull * n) && dalloc(s->node_box_hi, 2ull * n) && dalloc(s->visit, n) &&
               dalloc(s->nodes, n) && dalloc(s->tris, n);
     for (auto& e : s->ev) ok = ok && cuda_ok(cudaEventCreate(&e), "cudaEventCreate", __FILE__, __LINE__);
+    ok = ok && cuda_ok(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking), "cudaStreamCreate", __FILE__, __LINE__) &&
+         cuda_ok(cudaEventCreateWithFlags(&s->ev_sorted, cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__) &&
+         cuda_ok(cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__);
+    // pooled blocks carry whatever their last owner wrote: the refit tells published boxes by an epoch in their fourth lane
+    if (ok) ok = cuda_ok(cudaMemset(s->node_box_lo, 0, 2ull * std::max(n, 1u) * sizeof(float4)), "clear node boxes", __FILE__, __LINE__) &&
+                 cuda_ok(cudaMemset(s->node_box_hi, 0, 2ull * std::max(n, 1u) * sizeof(float4)), "clear node boxes", __FILE__, __LINE__);
     if (ok && n) {
         ok = cuda_ok(cudaMemcpy(s->verts, verts.data(), verts.size() * sizeof(float), cudaMemcpyHostToDevice), "upload verts", __FILE__, __LINE__) &&
              cuda_ok(cudaMemcpy(s->tris_in, packed.data(), packed.size() * sizeof(SrtTri), cudaMemcpyHostToDevice), "upload tris", __FILE__, __LINE__);
@@ -528,6 +574,10 @@ void device_scene_destroy(DeviceScene* s) {
     if (!s) return;
     dfree(s->verts); dfree(s->tris_in); dfree(s->mats); dfree(s->leaf_boxes); dfree(s->centroids); dfree(s->scene_box);
     dfree(s->codes); dfree(s->keys[0]); dfree(s->keys[1]); dfree(s->vals[0]); dfree(s->vals[1]); dfree(s->hist);
+    dfree(s->block_boxes);
+    if (s->side) cudaStreamDestroy(s->side);
+    if (s->ev_sorted) cudaEventDestroy(s->ev_sorted);
+    if (s->ev_side) cudaEventDestroy(s->ev_side);
     dfree(s->lookback); dfree(s->tile_counter); dfree(s->left); dfree(s->right); dfree(s->parent); dfree(s->node_box_lo); dfree(s->node_box_hi);
     dfree(s->visit); dfree(s->nodes); dfree(s->tris); dfree(s->flat_units); dfree(s->flat_tris); dfree(s->flat_to_orig);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
@@ -556,31 +606,36 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
     // every launch of one build.  (Replaying the sequence as a CUDA graph was measured: 0.362 -> 0.359 ms at 1M triangles,
     // the launches already queue back to back, so the plain stream stays.)
     auto enqueue = [&]() -> bool {
-        k_reset_build<<<(SORT_PASSES * RADIX + 255) / 256, 256, 0, st>>>((uint32_t*)s->scene_box, s->hist, SORT_PASSES * RADIX, s->tile_counter, SORT_PASSES);
-        SRT_CUDA(cudaMemsetAsync(s->lookback, 0, (size_t)SORT_PASSES * s->tiles * RADIX * sizeof(uint32_t), st));
-        SRT_CUDA(cudaMemsetAsync(s->visit, 0, n * sizeof(uint32_t), st));
-        k_bounds<<<grid_stride, 256, 0, st>>>(s->verts, n, s->leaf_boxes, s->centroids, (uint32_t*)s->scene_box);
-        k_decode_scene_box<<<1, 32, 0, st>>>((uint32_t*)s->scene_box);
-        k_morton_hist<<<grid_stride, 256, 0, st>>>(s->centroids, s->scene_box, n, s->codes, s->keys[0], s->vals[0], s->hist);
+        const uint32_t n_lookback = (uint32_t)((size_t)SORT_PASSES * s->tiles * RADIX);
+        k_bounds<<<kBoundsBlocks, 256, 0, st>>>(s->verts, n, s->leaf_boxes, s->centroids, s->block_boxes, s->visit, s->lookback, n_lookback, s->hist,
+                                                SORT_PASSES * RADIX, s->tile_counter, SORT_PASSES);
+        k_morton_hist<<<grid_stride, 256, 0, st>>>(s->centroids, s->block_boxes, kBoundsBlocks, s->scene_box, n, s->codes, s->keys[0], s->vals[0], s->hist);
         SRT_CUDA(cudaEventRecord(s->ev[1], st));
-        k_scan_hist<<<1, RADIX, 0, st>>>(s->hist, SORT_PASSES);
         for (int p = 0; p < SORT_PASSES; p++) {
             k_onesweep<<<s->tiles, SORT_THREADS, 0, st>>>(s->keys[p & 1], s->vals[p & 1], s->keys[(p + 1) & 1], s->vals[(p + 1) & 1], n, p * RADIX_BITS,
                                                          s->hist + p * RADIX, s->lookback + (size_t)p * s->tiles * RADIX, s->tile_counter + p);
         }
         SRT_CUDA(cudaEventRecord(s->ev[2], st));
+        // the triangle permutation only needs the sorted order: second stream, next to hierarchy + refit
+        SRT_CUDA(cudaEventRecord(s->ev_sorted, st));
+        SRT_CUDA(cudaStreamWaitEvent(s->side, s->ev_sorted, 0));
+        k_permute_tris<<<(3 * n + 255) / 256, 256, 0, s->side>>>(n, s->vals[0], reinterpret_cast<const float4*>(s->tris_in), reinterpret_cast<float4*>(s->tris));
+        SRT_CUDA(cudaEventRecord(s->ev_side, s->side));
         if (n > 1) k_hierarchy<<<grid_n, 256, 0, st>>>(s->keys[0], (int)n, s->left, s->right, s->parent);
         else SRT_CUDA(cudaMemsetAsync(s->parent, 0xFF, sizeof(int32_t), st));
         SRT_CUDA(cudaEventRecord(s->ev[3], st));
-        k_refit_emit<<<grid_n, 256, 0, st>>>((int)n, s->vals[0], s->leaf_boxes, s->left, s->right, s->parent, s->node_box_lo, s->node_box_hi, s->visit,
-                                             s->tris_in, s->nodes, s->tris);
+        // process-wide counter: an epoch is never used twice, and the box arrays were zeroed when the scene was created (epoch 0 is never handed out)
+        uint32_t epoch = g_refit_epoch.fetch_add(1u) + 1u;
+        if (epoch == 0) epoch = g_refit_epoch.fetch_add(1u) + 1u;
+        k_refit_emit<<<grid_n, 256, 0, st>>>((int)n, s->vals[0], s->leaf_boxes, s->left, s->right, s->parent, s->node_box_lo, s->node_box_hi, s->visit, s->nodes, epoch);
+        SRT_CUDA(cudaStreamWaitEvent(st, s->ev_side, 0));
         return true;
     };
     for (int rep = 0; rep < repeats; rep++) {
         SRT_CUDA(cudaEventRecord(s->ev[0], st));
         if (!enqueue()) return false;
         SRT_CUDA(cudaEventRecord(s->ev[4], st));
-        count_launch(4 + SORT_PASSES + (n > 1 ? 1 : 0));
+        count_launch(4 + SORT_PASSES + (n > 1 ? 1 : 0));  // bounds, morton, passes, permute, hierarchy, refit
         SRT_CUDA_LAST();
     }
     SRT_CUDA(cudaEventSynchronize(s->ev[4]));
