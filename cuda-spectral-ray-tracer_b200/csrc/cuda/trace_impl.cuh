@@ -386,12 +386,25 @@ __device__ __forceinline__ void camera_ray(const WaveParams& P, uint32_t i, uint
     p.bounce = 0;
 }
 
-__device__ __forceinline__ void mul_spectrum(Path& p, const float* __restrict__ spec) {  // ray/ray.cuh:60-69
+// One out-of-line copy for its two callers (scatter, and the miss / emitter end of a sample): the hot loop of k_wavefront
+// sits at the edge of the 32 KB instruction cache, where every inlined copy of the seven interpolations costs more in
+// fetch stalls than a call does.  Scalars in, scalars out, so the path state stays in registers.
+struct Pw7 { float w0, w1, w2, w3, w4, w5, w6; };
+__device__ __noinline__ Pw7 mul_spectrum_scalars(const float* __restrict__ spec, float hero, uint32_t valid, float w0, float w1, float w2, float w3, float w4,
+                                                float w5, float w6) {
     float wl[SRT_N_WL];
-    hero_rotations(p.hero, wl);
+    hero_rotations(hero, wl);
+    float pw[SRT_N_WL] = {w0, w1, w2, w3, w4, w5, w6};
 #pragma unroll
     for (int k = 0; k < SRT_N_WL; k++)
-        if ((uint32_t)k < p.valid) p.pw[k] *= interp95(spec, wl[k]);
+        if ((uint32_t)k < valid) pw[k] *= interp95(spec, wl[k]);
+    Pw7 r;
+    r.w0 = pw[0]; r.w1 = pw[1]; r.w2 = pw[2]; r.w3 = pw[3]; r.w4 = pw[4]; r.w5 = pw[5]; r.w6 = pw[6];
+    return r;
+}
+__device__ __forceinline__ void mul_spectrum(Path& p, const float* __restrict__ spec) {  // ray/ray.cuh:60-69
+    const Pw7 r = mul_spectrum_scalars(spec, p.hero, p.valid, p.pw[0], p.pw[1], p.pw[2], p.pw[3], p.pw[4], p.pw[5], p.pw[6]);
+    p.pw[0] = r.w0; p.pw[1] = r.w1; p.pw[2] = r.w2; p.pw[3] = r.w3; p.pw[4] = r.w4; p.pw[5] = r.w5; p.pw[6] = r.w6;
 }
 
 // dev_spectrum_to_XYZ (color/color.cu:88-104) added into the film accumulator of one pixel.
@@ -592,16 +605,17 @@ __device__ __forceinline__ uint32_t ref_thread_index(const WaveParams& P, uint32
     return (cj % 16u) * 28u + (ci % 28u) + 448u * ((cj / 16u) * P.ref_grid_x + ci / 28u);
 }
 
-// warp-aggregated push into a block-local (shared memory) queue of local slot ids:
-// ballot + one shared-memory atomicAdd per warp, lanes write at base + rank-in-ballot
-__device__ __forceinline__ void queue_push(uint16_t* __restrict__ q, int* counter, bool pred, uint32_t local_slot) {
-    const uint32_t mask = __ballot_sync(0xffffffffu, pred);
-    if (mask == 0) return;
-    const int lane = threadIdx.x & 31;
+// warp-aggregated push into the block's four shared-memory queues of local slot ids, all four at once: lanes that go to
+// the same queue find each other with one __match_any_sync, the first lane of every group reserves the group's room with
+// one shared-memory atomicAdd (up to four addresses in one instruction), lanes write at base + rank-in-group.
+// which = 0..3 (regenerate, lambertian, metallic, dielectric), or 4 = this lane pushes nothing.
+__device__ __forceinline__ void queue_push_all(uint16_t* __restrict__ q, uint32_t S, int* counters, uint32_t which, uint32_t local_slot) {
+    const uint32_t peers = __match_any_sync(0xffffffffu, which);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
     int base = 0;
-    if (lane == __ffs(mask) - 1) base = atomicAdd(counter, __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
-    if (pred) q[base + __popc(mask & ((1u << lane) - 1))] = (uint16_t)local_slot;
+    if (lane == leader && which < 4u) base = atomicAdd(counters + which, __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (which < 4u) q[which * S + base + __popc(peers & ((1u << lane) - 1))] = (uint16_t)local_slot;
 }
 
 __device__ __forceinline__ void store_hit_state(const WaveParams& P, uint32_t slot, const Path& p, int tri) {
@@ -834,10 +848,8 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
                     if (ev != EV_DONE) store_hit_state(P, rec, p, tri);
                 }
             }
-            queue_push(qo, co + 0, have && !retired && ev == EV_DONE, l);  // next sample, or next pixel
-            queue_push(qo + S, co + 1, ev == 1, l);
-            queue_push(qo + 2 * S, co + 2, ev == 2, l);
-            queue_push(qo + 3 * S, co + 3, ev == 3, l);
+            // next sample or next pixel (queue 0), or the queue of the material that was hit; retired slots and empty lanes push nothing
+            queue_push_all(qo, S, co, ev != EV_DONE ? (uint32_t)ev : ((have && !retired) ? 0u : 4u), l);
         }
         __syncthreads();
         if (threadIdx.x < 4) cnt[cur][threadIdx.x] = 0;  // becomes the output buffer of the next pass
