@@ -27,6 +27,17 @@
 namespace srt {
 namespace SRT_FP_NS {
 
+#ifdef SRT_PHASE_CLOCKS
+// probe build: cycles of warp 0 / block 0 between fine-grained points, summed over the launch (g_fine[2k] = cycles, [2k+1] = visits)
+__device__ unsigned long long g_fine[32];
+#define SRT_FINE_BEGIN unsigned long long fine_t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(fine_t_))
+#define SRT_FINE(k) do { unsigned long long n_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(n_)); \
+        if (blockIdx.x == 0 && threadIdx.x == 0) { g_fine[2 * (k)] += n_ - fine_t_; g_fine[2 * (k) + 1] += 1; } fine_t_ = n_; } while (0)
+#else
+#define SRT_FINE_BEGIN do { } while (0)
+#define SRT_FINE(k) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------ small math
 struct V3 { float x, y, z; };
 __device__ __forceinline__ V3 mk(float x, float y, float z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }
@@ -252,8 +263,10 @@ __device__ __forceinline__ unsigned long long flat_candidates(const SceneRef& sc
 }
 // phase 2, one ray per lane on its own: the megakernel, whose lanes sit in divergent loops
 __device__ __forceinline__ int closest_hit_flat(const SceneRef& sc, V3 o, V3 d, float& t_hit) {
+    SRT_FINE_BEGIN;
     const unsigned long long m = flat_candidates(sc, o, d);
     uint32_t m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
+    SRT_FINE(0);
     float closest = FLT_MAX;
     int best = -1;
     uint32_t best_prio = 0;
@@ -263,6 +276,7 @@ __device__ __forceinline__ int closest_hit_flat(const SceneRef& sc, V3 o, V3 d, 
         else { i = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
         consider_hit(sc.tris, i, o, d, closest, best, best_prio);
     }
+    SRT_FINE(1);
     t_hit = closest;
     return best;
 }
@@ -458,6 +472,7 @@ __device__ __forceinline__ float sellmeier(const SrtMaterial* __restrict__ m, fl
 // Returns false when the path ends here (metal absorbed the ray).  `mtype` is warp-uniform in the
 // wavefront (queues are sorted by material), so the branches below do not diverge there.
 __device__ __forceinline__ bool scatter(const SceneRef& sc, const SrtTri* __restrict__ tri, uint32_t mtype, Path& p, Rng& rng) {
+    SRT_FINE_BEGIN;
     const float4 q0 = *reinterpret_cast<const float4*>(tri);
     const uint32_t bits = __float_as_uint((reinterpret_cast<const float4*>(tri) + 2)->z);
     const SrtMaterial* m = sc.mats + SRT_TRI_MAT(bits);
@@ -465,6 +480,7 @@ __device__ __forceinline__ bool scatter(const SceneRef& sc, const SrtTri* __rest
     const bool front = dot(p.d, n) < 0;  // hit_record::set_face_normal, primitives/hit_record.cuh:30-43
     if (!front) n = -n;
     const V3 uin = unit(p.d);
+    SRT_FINE(6);
     V3 out;
     float eps_sign = 1.0f;
     bool alive = true;
@@ -501,7 +517,9 @@ __device__ __forceinline__ bool scatter(const SceneRef& sc, const SrtTri* __rest
             if ((fabsf(out.x) < s) && (fabsf(out.y) < s) && (fabsf(out.z) < s)) out = n;
         }
     }
+    SRT_FINE(7);
     mul_spectrum(p, m->spec);
+    SRT_FINE(8);
     p.o = p.o + ((eps_sign * SRT_EPSILON) * n);
     p.d = out;
     return alive;
@@ -527,11 +545,14 @@ template <bool FLAT>
 __device__ __forceinline__ int extend(const SceneRef& sc, const WaveParams& P, Path& p, int& tri_out, float* acc, size_t pix, bool primary = false) {
     float t = 0.f;
     int tri = -1;
+    SRT_FINE_BEGIN;
     // camera rays of a whole warp often all pass beside the scene (46 % of the 16:9 frame lies outside
     // the box): one cheap slab test spares the warp the whole wide-leaf loop.
     bool skip = false;
     if (FLAT && primary) skip = __all_sync(__activemask(), misses_scene_box(P, p.o, p.d));
+    SRT_FINE(2);
     if (!skip) tri = closest_hit<FLAT>(sc, p.o, p.d, t);
+    SRT_FINE(3);
     uint32_t bits = 0, mtype = SRT_LAMBERTIAN;
     if (tri >= 0) {
         bits = __float_as_uint((reinterpret_cast<const float4*>(sc.tris + tri) + 2)->z);
@@ -544,8 +565,10 @@ __device__ __forceinline__ int extend(const SceneRef& sc, const WaveParams& P, P
             mul_spectrum(p, tri < 0 ? sc.bg : sc.mats[SRT_TRI_MAT(bits)].spec);
             film_add(sc, p, acc, P.plane, pix);
         }
+        SRT_FINE(4);
         return EV_DONE;
     }
+    SRT_FINE(5);
     p.o = mk(p.o.x + t * p.d.x, p.o.y + t * p.d.y, p.o.z + t * p.d.z);  // ray::at, ray/ray.cuh:44-47
     tri_out = tri;
     return mtype == SRT_METALLIC ? 2 : (mtype == SRT_DIELECTRIC ? 3 : 1);
@@ -697,6 +720,14 @@ __global__ void __launch_bounds__(256) k_prior_cost(WaveParams P) {
 // chunk, no host round trips.  The ray trace (extend) has ONE call site so the hot loop stays inside
 // the instruction cache.
 #define SRT_NO_SLOT 0xFFFFFFFFu
+// probe builds only (make EXTRA=-DSRT_PHASE_CLOCKS, tools/latency_probe.py): warp 0 of blocks 0..3 records the SM cycles its first
+// task of every pass spends in {task fetch + state addresses, regenerate / scatter, closest hit, state store + queue push}
+// into the pass-log rows of blocks 4..7
+#ifdef SRT_PHASE_CLOCKS
+#define SRT_CLK(v) do { asm volatile("mov.u64 %0, %%clock64;" : "=l"(v)); } while (0)
+#else
+#define SRT_CLK(v) do { } while (0)
+#endif
 template <bool SMEM, bool FLAT>
 __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefront(WaveParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -727,7 +758,11 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
     while (true) {
         const int nR = cnt[cur][0], nL = cnt[cur][1], nM = cnt[cur][2], nD = cnt[cur][3];
         if ((nR | nL | nM | nD) == 0) break;
+#ifdef SRT_PHASE_CLOCKS
+        if (P.pass_log && blockIdx.x < 4 && threadIdx.x == 0 && npass < SRT_PASS_LOG_PASSES) {
+#else
         if (P.pass_log && blockIdx.x < SRT_PASS_LOG_BLOCKS && threadIdx.x == 0 && npass < SRT_PASS_LOG_PASSES) {
+#endif
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             P.pass_log[blockIdx.x * SRT_PASS_LOG_PASSES + npass] = make_uint4((uint32_t)now, (uint32_t)nR, (uint32_t)nL, (uint32_t)nM | ((uint32_t)nD << 16));
@@ -742,7 +777,12 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
         const uint16_t* qi = qbuf + (size_t)cur * 4 * S;
         uint16_t* qo = qbuf + (size_t)(cur ^ 1) * 4 * S;
         int* co = cnt[cur ^ 1];
+#ifdef SRT_PHASE_CLOCKS
+        bool first_task = true;
+#endif
         while (true) {
+            unsigned long long ck0 = 0, ck1 = 0, ck2 = 0, ck3 = 0, ck4 = 0;
+            SRT_CLK(ck0);
             int task = 0;
             if (lane == 0) task = atomicAdd(&next_task, 1);
             task = __shfl_sync(0xffffffffu, task, 0);
@@ -807,6 +847,7 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
                     atomicMin(P.drain_clock, now);
                 }
             }
+            SRT_CLK(ck1);
             if (have && slot != SRT_NO_SLOT) {
                 if (kind == 0) {
                     if (!fetch) {
@@ -833,10 +874,12 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
                     trace = alive && p.bounce < P.bounce_limit;  // absorbed, or bounce limit: valid = 0 (rendering.cu:38)
                 }
             }
+            SRT_CLK(ck2);
             if (trace) {
                 rays++;
                 ev = extend<FLAT>(sc, P, p, tri, P.acc, pix, kind == 0);
             }
+            SRT_CLK(ck3);
             if (have && slot != SRT_NO_SLOT) {
                 if (ev == EV_DONE && s >= P.s_end) {  // pixel finished: its RNG state goes back to the pixel (carried into the next round / chunk)
                     store_rng(P.G0, P.G1, slot, rng);
@@ -850,6 +893,13 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
             }
             // next sample or next pixel (queue 0), or the queue of the material that was hit; retired slots and empty lanes push nothing
             queue_push_all(qo, S, co, ev != EV_DONE ? (uint32_t)ev : ((have && !retired) ? 0u : 4u), l);
+            SRT_CLK(ck4);
+#ifdef SRT_PHASE_CLOCKS
+            if (first_task && P.pass_log && blockIdx.x < 4 && threadIdx.x == 0 && npass < SRT_PASS_LOG_PASSES)
+                P.pass_log[(blockIdx.x + 4) * SRT_PASS_LOG_PASSES + npass] = make_uint4((uint32_t)(ck1 - ck0), (uint32_t)(ck2 - ck1), (uint32_t)(ck3 - ck2), (uint32_t)(ck4 - ck3) | ((uint32_t)kind << 28));
+            first_task = false;
+#endif
+            (void)ck0; (void)ck1; (void)ck2; (void)ck3; (void)ck4;
         }
         __syncthreads();
         if (threadIdx.x < 4) cnt[cur][threadIdx.x] = 0;  // becomes the output buffer of the next pass
@@ -858,6 +908,13 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
         npass++;
         __syncthreads();
     }
+#ifdef SRT_PHASE_CLOCKS
+    if (P.pass_log && blockIdx.x == 0 && threadIdx.x == 0)
+        for (int k = 0; k < 16; k++) {
+            P.pass_log[7 * SRT_PASS_LOG_PASSES + k] = make_uint4((uint32_t)g_fine[2 * k], (uint32_t)(g_fine[2 * k] >> 32), (uint32_t)g_fine[2 * k + 1], 0u);
+            g_fine[2 * k] = 0; g_fine[2 * k + 1] = 0;
+        }
+#endif
     if (P.ray_counter && rays) atomicAdd(P.ray_counter, rays);
     if (P.drain_clock && threadIdx.x == 0) {
         unsigned long long now;
