@@ -6,10 +6,12 @@
 //   sort     : hand-written ONESWEEP least-significant-digit radix sort, 4 passes of 8 bits,
 //              one global histogram pre-pass, decoupled look-back, warp match/ballot ranking,
 //              stable => equal codes stay in triangle-index order
-//   hierarchy: one thread per internal node, clz(key_i ^ key_j) prefix lengths, ties broken by index
-//   refit    : bottom-up, one thread per leaf, second arrival at a node does the union and emits the 64-B traversal node
-//              carrying both child boxes (no fences: published boxes carry the build's epoch)
-//   permute  : triangles to leaf order -- a pure gather, on a second stream next to hierarchy + refit
+//   tree     : hierarchy AND refit in one bottom-up kernel, one thread per leaf: a finished subtree [a, b] picks its parent by
+//              comparing the key differences at its two ends (the split with the longer common prefix is the nearer ancestor),
+//              the second subtree to arrive at a split owns both child boxes, unions them and emits the 64-B traversal node
+//              under the node's Karras index (no fences: published boxes carry the build's epoch).  There is no separate
+//              top-down split search; left / right / parent arrays are derived from the nodes only when a caller dumps them
+//   permute  : triangles to leaf order -- a pure gather, on a second stream next to the tree kernel
 //
 // Specification and bit-exactness oracle: oracle/lbvh_oracle.c.  The reference
 // itself builds its BVH serially in one thread (bvh/bvh.cu:206-345, scene/scene.cu:9-20); this
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) k_bounds(const float* __restrict__ verts,
                                                 uint32_t* __restrict__ tickets, uint32_t n_tickets) {
     __shared__ float sbox[8][6];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-    for (uint32_t i = gtid; i < n; i += gsize) visit[i] = 0;
+    for (uint32_t i = gtid; i < n; i += gsize) visit[i] = 0xFFFFFFFFu;  // k_build_tree: no subtree has arrived at this split yet
     for (uint32_t i = gtid; i < n_lookback; i += gsize) lookback[i] = 0;
     if (gtid < n_hist) hist[gtid] = 0;
     if (gtid < n_tickets) tickets[gtid] = 0;
@@ -401,47 +403,15 @@ const uint32_t* pixel_order_build(PixelOrder* o, const uint32_t* cost, uint32_t 
     return o->vals[1];
 }
 
-// ---- hierarchy ------------------------------------------------------------------------------
-__device__ __forceinline__ int lcp(const uint32_t* __restrict__ keys, int n, int i, int j) {
-    if (j < 0 || j >= n) return -1;
-    const uint32_t a = keys[i], b = keys[j];
-    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
-    return __clz(a ^ b);
-}
-__global__ void __launch_bounds__(256) k_hierarchy(const uint32_t* __restrict__ keys, int n, int32_t* __restrict__ left, int32_t* __restrict__ right,
-                                                   int32_t* __restrict__ parent) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) parent[0] = -1;
-    if (i >= n - 1) return;
-    const int d = (lcp(keys, n, i, i + 1) - lcp(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-    const int dmin = lcp(keys, n, i, i - d);
-    int lmax = 2;
-    while (lcp(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
-    int l = 0;
-    for (int t = lmax / 2; t >= 1; t /= 2)
-        if (lcp(keys, n, i, i + (l + t) * d) > dmin) l += t;
-    const int j = i + l * d;
-    const int dnode = lcp(keys, n, i, j);
-    int s = 0, t = l;
-    do {
-        t = (t + 1) >> 1;
-        if (lcp(keys, n, i, i + (s + t) * d) > dnode) s += t;
-    } while (t > 1);
-    const int gamma = i + s * d + min(d, 0);
-    const int lo = min(i, j), hi = max(i, j);
-    const int L = (lo == gamma) ? (n - 1 + gamma) : gamma;
-    const int R = (hi == gamma + 1) ? (n - 1 + gamma + 1) : gamma + 1;
-    left[i] = L;
-    right[i] = R;
-    parent[L] = i;
-    parent[R] = i;
-}
-
-// ---- refit + emit ---------------------------------------------------------------------------------
-// One thread per leaf climbs.  The first thread to reach an internal node leaves (its subtree's box is already
-// published); the second one owns both child boxes -- its own running box and the sibling's published one -- so it
-// unions them (fmin/fmax: order independent, hence deterministic), publishes the node's box for the level above AND
-// writes the 64-byte traversal node right there.  Boxes travel as two 16-byte vectors (lo.xyz | epoch, hi.xyz | epoch).
+// ---- hierarchy + refit + emit, bottom-up ------------------------------------------------------------
+// The binary radix tree over the sorted (code, index) keys is unique, so it can be grown from the leaves (Apetrei 2014) instead of
+// searched top-down per internal node (Karras 2012, what oracle/lbvh_oracle.c restates): a finished subtree covering leaves [a, b] is
+// the LEFT child of the split after b when the keys differ less across that split than across the one before a (longer common prefix =
+// nearer ancestor), else the RIGHT child of the split before a.  The first subtree to arrive at a split leaves its far end there and
+// stops; the second one takes it, owns both child boxes and goes on as the merged subtree.  Node NUMBERS are Karras': a left child is
+// numbered by the last leaf of its range, a right child by the first, the root is 0 -- so a node learns its number at the moment it
+// learns which child it is, and its children are `split` (or leaf n-1+split) and `split+1` (or leaf n-1+split+1), exactly the oracle's
+// left[] / right[].  Boxes travel as two 16-byte vectors (lo.xyz | epoch, hi.xyz | epoch) stored under the node's number.
 __device__ __forceinline__ float widen_lo(float v) { return v - fabsf(v) * 2.4e-7f; }
 __device__ __forceinline__ float widen_hi(float v) { return v + fabsf(v) * 2.4e-7f; }
 __device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
@@ -449,50 +419,73 @@ __device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
     asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
-__global__ void __launch_bounds__(256) k_refit_emit(int n, const uint32_t* __restrict__ sorted_idx, const float4* __restrict__ leaf_boxes,
-                                                    const int32_t* __restrict__ left, const int32_t* __restrict__ right,
-                                                    const int32_t* __restrict__ parent, float4* node_box_lo,
-                                                    float4* node_box_hi, uint32_t* visit, SrtNode* __restrict__ nodes, uint32_t epoch_bits) {
+// how much the augmented keys (code, position) differ across the split between sorted positions i and i + 1: smaller = longer common prefix
+__device__ __forceinline__ unsigned long long split_delta(const uint32_t* __restrict__ keys, int i) {
+    return ((unsigned long long)(__ldg(keys + i) ^ __ldg(keys + i + 1)) << 32) | (uint32_t)(i ^ (i + 1));
+}
+__global__ void __launch_bounds__(256) k_build_tree(int n, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ sorted_idx,
+                                                    const float4* __restrict__ leaf_boxes, int32_t* other, float4* node_box_lo, float4* node_box_hi,
+                                                    SrtNode* __restrict__ nodes, uint32_t epoch_bits) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint32_t src = sorted_idx[k];
     float4 lo = leaf_boxes[2ull * src], hi = leaf_boxes[2ull * src + 1];
     const float epoch = __uint_as_float(epoch_bits);  // only ever compared as bits
     lo.w = hi.w = epoch;
-    int from = n - 1 + k;
-    node_box_lo[from] = lo;
-    node_box_hi[from] = hi;
-    int node = parent[from];
-    while (node >= 0) {
-        // the node's topology is requested before the counter is bumped: three independent loads whose latency overlaps the atomic's
-        const int L = __ldcg(left + node), R = __ldcg(right + node), up = __ldcg(parent + node);
-        if (atomicAdd(&visit[node], 1u) == 0) return;  // the sibling subtree finishes this node
-        const int other = L == from ? R : L;
-        // No fence anywhere: a published box carries this build's epoch in the fourth lane of both of its 16-byte halves
-        // (a 16-byte store lands as one piece), so the finisher simply re-reads the sibling's halves until both show the
-        // epoch -- its counter increment may have overtaken the sibling's stores, which were issued before the sibling's own.
+    node_box_lo[n - 1 + k] = lo;
+    node_box_hi[n - 1 + k] = hi;
+    int a = k, b = k, split = -1;          // the subtree this thread carries: leaves [a, b], split between its children (-1: a leaf)
+    float4 llo, lhi, rlo, rhi;             // its children's boxes
+    llo = lhi = rlo = rhi = lo;
+    while (true) {
+        const bool root = a == 0 && b == n - 1;
+        const bool is_left = root ? false : (a == 0 ? true : (b == n - 1 ? false : split_delta(keys, b) < split_delta(keys, a - 1)));
+        if (split >= 0) {  // an internal node: now that its number is known, emit it and publish its box
+            const int self = root ? 0 : (is_left ? b : a);
+            const int L = a == split ? n - 1 + split : split, R = b == split + 1 ? n - 1 + split + 1 : split + 1;
+            SrtNode nd;
+            nd.c0xmin = widen_lo(llo.x); nd.c0xmax = widen_hi(lhi.x); nd.c0ymin = widen_lo(llo.y); nd.c0ymax = widen_hi(lhi.y);
+            nd.c1xmin = widen_lo(rlo.x); nd.c1xmax = widen_hi(rhi.x); nd.c1ymin = widen_lo(rlo.y); nd.c1ymax = widen_hi(rhi.y);
+            nd.c0zmin = widen_lo(llo.z); nd.c0zmax = widen_hi(lhi.z); nd.c1zmin = widen_lo(rlo.z); nd.c1zmax = widen_hi(rhi.z);
+            nd.child0 = L >= n - 1 ? ~(L - (n - 1)) : L;
+            nd.child1 = R >= n - 1 ? ~(R - (n - 1)) : R;
+            nd.pad0 = nd.pad1 = 0;
+            nodes[self] = nd;
+            node_box_lo[self] = lo;
+            node_box_hi[self] = hi;
+        }
+        if (root) return;
+        const int p = is_left ? b : a - 1;  // the parent's split
+        const int far = atomicExch(other + p, is_left ? a : b);
+        if (far < 0) return;  // the sibling subtree finishes this node
+        // No fence anywhere: a published box carries this build's epoch in the fourth lane of both of its 16-byte halves (a 16-byte
+        // store lands as one piece), so the finisher simply re-reads the sibling's halves until both show the epoch -- its exchange
+        // may have overtaken the sibling's stores, which were issued before the sibling's own.
+        const int sib = is_left ? (far == b + 1 ? n - 1 + far : b + 1) : (far == a - 1 ? n - 1 + far : a - 1);
         float4 olo, ohi;
         do {
-            olo = ld_volatile_f4(node_box_lo + other);
-            ohi = ld_volatile_f4(node_box_hi + other);
+            olo = ld_volatile_f4(node_box_lo + sib);
+            ohi = ld_volatile_f4(node_box_hi + sib);
         } while (__float_as_uint(olo.w) != epoch_bits || __float_as_uint(ohi.w) != epoch_bits);
-        const float4 llo = L == from ? lo : olo, lhi = L == from ? hi : ohi;  // left child's box
-        const float4 rlo = L == from ? olo : lo, rhi = L == from ? ohi : hi;  // right child's box
-        SrtNode nd;
-        nd.c0xmin = widen_lo(llo.x); nd.c0xmax = widen_hi(lhi.x); nd.c0ymin = widen_lo(llo.y); nd.c0ymax = widen_hi(lhi.y);
-        nd.c1xmin = widen_lo(rlo.x); nd.c1xmax = widen_hi(rhi.x); nd.c1ymin = widen_lo(rlo.y); nd.c1ymax = widen_hi(rhi.y);
-        nd.c0zmin = widen_lo(llo.z); nd.c0zmax = widen_hi(lhi.z); nd.c1zmin = widen_lo(rlo.z); nd.c1zmax = widen_hi(rhi.z);
-        nd.child0 = L >= n - 1 ? ~(L - (n - 1)) : L;
-        nd.child1 = R >= n - 1 ? ~(R - (n - 1)) : R;
-        nd.pad0 = nd.pad1 = 0;
-        nodes[node] = nd;
+        if (is_left) { llo = lo; lhi = hi; rlo = olo; rhi = ohi; b = far; }
+        else { llo = olo; lhi = ohi; rlo = lo; rhi = hi; a = far; }
+        split = p;
         lo = make_float4(fminf(lo.x, olo.x), fminf(lo.y, olo.y), fminf(lo.z, olo.z), epoch);
         hi = make_float4(fmaxf(hi.x, ohi.x), fmaxf(hi.y, ohi.y), fmaxf(hi.z, ohi.z), epoch);
-        node_box_lo[node] = lo;
-        node_box_hi[node] = hi;
-        from = node;
-        node = up;
     }
+}
+// left / right / parent in the oracle's numbering (internal i, leaf n-1+k), read off the emitted nodes: only dumps need them
+__global__ void __launch_bounds__(256) k_topology(int n, const SrtNode* __restrict__ nodes, int32_t* __restrict__ left, int32_t* __restrict__ right,
+                                                  int32_t* __restrict__ parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) parent[0] = -1;
+    if (i >= n - 1) return;
+    const int c0 = nodes[i].child0, c1 = nodes[i].child1;
+    const int L = c0 < 0 ? n - 1 + ~c0 : c0, R = c1 < 0 ? n - 1 + ~c1 : c1;
+    left[i] = L;
+    right[i] = R;
+    parent[L] = i;
+    parent[R] = i;
 }
 // triangles to leaf order: three lanes move one 48-byte triangle, 16 bytes each, so the stores are fully coalesced.
 // A pure gather that needs nothing but the sorted order: it runs on a second stream next to hierarchy + refit.
@@ -621,13 +614,11 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
         SRT_CUDA(cudaStreamWaitEvent(s->side, s->ev_sorted, 0));
         k_permute_tris<<<(3 * n + 255) / 256, 256, 0, s->side>>>(n, s->vals[0], reinterpret_cast<const float4*>(s->tris_in), reinterpret_cast<float4*>(s->tris));
         SRT_CUDA(cudaEventRecord(s->ev_side, s->side));
-        if (n > 1) k_hierarchy<<<grid_n, 256, 0, st>>>(s->keys[0], (int)n, s->left, s->right, s->parent);
-        else SRT_CUDA(cudaMemsetAsync(s->parent, 0xFF, sizeof(int32_t), st));
-        SRT_CUDA(cudaEventRecord(s->ev[3], st));
+        SRT_CUDA(cudaEventRecord(s->ev[3], st));  // (no separate hierarchy phase any more: ms_out[3] stays ~0)
         // process-wide counter: an epoch is never used twice, and the box arrays were zeroed when the scene was created (epoch 0 is never handed out)
         uint32_t epoch = g_refit_epoch.fetch_add(1u) + 1u;
         if (epoch == 0) epoch = g_refit_epoch.fetch_add(1u) + 1u;
-        k_refit_emit<<<grid_n, 256, 0, st>>>((int)n, s->vals[0], s->leaf_boxes, s->left, s->right, s->parent, s->node_box_lo, s->node_box_hi, s->visit, s->nodes, epoch);
+        k_build_tree<<<grid_n, 256, 0, st>>>((int)n, s->keys[0], s->vals[0], s->leaf_boxes, reinterpret_cast<int32_t*>(s->visit), s->node_box_lo, s->node_box_hi, s->nodes, epoch);
         SRT_CUDA(cudaStreamWaitEvent(st, s->ev_side, 0));
         return true;
     };
@@ -635,7 +626,7 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
         SRT_CUDA(cudaEventRecord(s->ev[0], st));
         if (!enqueue()) return false;
         SRT_CUDA(cudaEventRecord(s->ev[4], st));
-        count_launch(4 + SORT_PASSES + (n > 1 ? 1 : 0));  // bounds, morton, passes, permute, hierarchy, refit
+        count_launch(4 + SORT_PASSES);  // bounds, morton, passes, permute, tree
         SRT_CUDA_LAST();
     }
     SRT_CUDA(cudaEventSynchronize(s->ev[4]));
@@ -655,6 +646,10 @@ bool device_scene_download_lbvh(const DeviceScene* s, LbvhDump& o) {
     o.codes.resize(n); o.sorted_idx.resize(n); o.left.resize(n > 0 ? n - 1 : 0); o.right.resize(n > 0 ? n - 1 : 0);
     o.parent.resize(n ? 2 * n - 1 : 0); o.node_boxes.resize(n ? 6ull * (2 * n - 1) : 0);
     if (!n) return true;
+    if (n > 1) k_topology<<<(n + 255) / 256, 256, 0, s->stream>>>((int)n, s->nodes, s->left, s->right, s->parent);
+    else SRT_CUDA(cudaMemsetAsync(s->parent, 0xFF, sizeof(int32_t), s->stream));
+    count_launch();
+    SRT_CUDA(cudaStreamSynchronize(s->stream));
     SRT_CUDA(cudaMemcpy(o.codes.data(), s->codes, n * 4, cudaMemcpyDeviceToHost));
     SRT_CUDA(cudaMemcpy(o.sorted_idx.data(), s->vals[0], n * 4, cudaMemcpyDeviceToHost));
     if (n > 1) {

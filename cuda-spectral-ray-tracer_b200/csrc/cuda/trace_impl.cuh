@@ -737,13 +737,17 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
     uint16_t* started = reinterpret_cast<uint16_t*>(smem + 20u * S);           // [S] samples started of that pixel
     uint16_t* passes = reinterpret_cast<uint16_t*>(smem + 22u * S);            // [S] passes spent on that pixel in this launch
     uint32_t* pxy = reinterpret_cast<uint32_t*>(smem + 24u * S);               // [S] that pixel's chunk coordinates, y << 16 | x
-    __shared__ int cnt[2][4];
-    __shared__ int next_task;
+    // ONE block barrier per pass: queue lengths are triple buffered (pass k reads cnt[k % 3], counts its output in cnt[(k + 1) % 3] and
+    // clears cnt[(k + 2) % 3], which nobody has touched since the barrier before), the task ticket is double buffered likewise
+    __shared__ int cnt[3][4];
+    __shared__ int next_task[2];
     const SceneRef sc = load_scene<SMEM, FLAT>(P, smem + P.queue_bytes);
     const uint32_t first = blockIdx.x * S;  // this block's records in the in-flight state arrays
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x < 8) (&cnt[0][0])[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { next_task = 0; cnt[0][0] = (int)S; }
+    if (threadIdx.x < 12) (&cnt[0][0])[threadIdx.x] = 0;
+    if (threadIdx.x < 2) next_task[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) cnt[0][0] = (int)S;
     // pass 0 input: every local slot asks for a pixel
     for (uint32_t l = threadIdx.x; l < S; l += blockDim.x) {
         pslot[l] = SRT_NO_SLOT;
@@ -753,11 +757,14 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
     }
     __syncthreads();
     unsigned long long rays = 0;
-    int cur = 0;
+    int cur = 0, cset = 0;  // queue buffer (pass % 2) and counter set (pass % 3) this pass reads
     uint32_t npass = 0;
     while (true) {
-        const int nR = cnt[cur][0], nL = cnt[cur][1], nM = cnt[cur][2], nD = cnt[cur][3];
+        const int nR = cnt[cset][0], nL = cnt[cset][1], nM = cnt[cset][2], nD = cnt[cset][3];
         if ((nR | nL | nM | nD) == 0) break;
+        const int co_i = cset == 2 ? 0 : cset + 1, cz_i = co_i == 2 ? 0 : co_i + 1;
+        if (threadIdx.x < 4) cnt[cz_i][threadIdx.x] = 0;  // the output counters of the NEXT pass
+        if (threadIdx.x == 0) next_task[cur ^ 1] = 0;
 #ifdef SRT_PHASE_CLOCKS
         if (P.pass_log && blockIdx.x < 4 && threadIdx.x == 0 && npass < SRT_PASS_LOG_PASSES) {
 #else
@@ -776,7 +783,8 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
         const int n_tasks = tF + (pooled ? ((rem + 31) >> 5) : ((rR > 0) + (rL > 0) + (rM > 0) + (rD > 0)));
         const uint16_t* qi = qbuf + (size_t)cur * 4 * S;
         uint16_t* qo = qbuf + (size_t)(cur ^ 1) * 4 * S;
-        int* co = cnt[cur ^ 1];
+        int* co = cnt[co_i];
+        int* ticket = &next_task[cur];
 #ifdef SRT_PHASE_CLOCKS
         bool first_task = true;
 #endif
@@ -784,7 +792,7 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
             unsigned long long ck0 = 0, ck1 = 0, ck2 = 0, ck3 = 0, ck4 = 0;
             SRT_CLK(ck0);
             int task = 0;
-            if (lane == 0) task = atomicAdd(&next_task, 1);
+            if (lane == 0) task = atomicAdd(ticket, 1);
             task = __shfl_sync(0xffffffffu, task, 0);
             if (task >= n_tasks) break;
             int kind, k;
@@ -902,11 +910,9 @@ __global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefro
             (void)ck0; (void)ck1; (void)ck2; (void)ck3; (void)ck4;
         }
         __syncthreads();
-        if (threadIdx.x < 4) cnt[cur][threadIdx.x] = 0;  // becomes the output buffer of the next pass
-        if (threadIdx.x == 0) next_task = 0;
         cur ^= 1;
+        cset = co_i;
         npass++;
-        __syncthreads();
     }
 #ifdef SRT_PHASE_CLOCKS
     if (P.pass_log && blockIdx.x == 0 && threadIdx.x == 0)

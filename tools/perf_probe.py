@@ -29,6 +29,7 @@ for v in a.variants.split(","):
     elif v == "wave_t": run("wavefront+timing", pipeline=0, kernel_timing=True)
     elif v == "mega": run("megakernel", pipeline=1)
     elif v == "strict": run("wavefront strict", pipeline=0, strict=True)
+    elif v == "pass1": run("wavefront pass scheduler, 1 round", pipeline=0, sched_flags=0, rounds=1)
     elif v == "bvh": run("wavefront lbvh-walk smem", pipeline=0, traversal=1)
     elif v == "bvhg": run("wavefront lbvh-walk global", pipeline=0, traversal=3)
     elif v.startswith("rounds"): run("wavefront %s rounds" % v[6:], pipeline=0, rounds=int(v[6:]), kernel_timing=True)
