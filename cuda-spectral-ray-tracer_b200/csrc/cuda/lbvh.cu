@@ -99,7 +99,7 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
 
-constexpr int kBoundsBlocks = 296;  // 2 per SM: few enough that every Morton block can afford to re-reduce the partial boxes
+constexpr int kBoundsBlocks = 592;  // 4 per SM (2 per SM left the loads without enough warps to hide their latency); every Morton block re-reduces the partial boxes
 
 // leaf box (bvh/aabb.cuh:49-57 + pad :93-102), centroid (primitives/tri.cuh:73-77), one partial scene box per block
 // (min / max are exact, so any reduction order gives the bits of the serial union); and the housekeeping of the build:
