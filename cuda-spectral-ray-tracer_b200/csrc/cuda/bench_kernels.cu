@@ -65,4 +65,45 @@ double measure_copy_gbs(uint32_t mbytes) {
     return best;
 }
 
+// L2 read bandwidth: every block streams the same 32 MB buffer (well inside the 126 MB L2, also when a line is cached once per die)
+// with 16-byte loads, several times over; the first sweep (DRAM) is a separate, untimed launch.  Denominator for the LBVH walk on
+// scenes that live in L2 (bench.py: frac_of_l2).
+__global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ buf, size_t n_vec, int sweeps, uint32_t* out) {
+    uint32_t acc = 0;
+    for (int s = 0; s < sweeps; s++)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+            const uint4 v = __ldcg(buf + ((i + (size_t)s * 4099u) % n_vec));
+            acc += v.x ^ v.y ^ v.z ^ v.w;
+        }
+    if (acc == 0x9E3779B9u) out[0] = acc;  // keeps the loads alive
+}
+double measure_l2_read_gbs() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t bytes = 32u << 20, n_vec = bytes / sizeof(uint4);
+    uint4* d = nullptr;
+    uint32_t* out = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMalloc(&out, 4) != cudaSuccess) { cudaFree(d); return 0; }
+    cudaMemset(d, 1, bytes);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int sweeps = 8;
+    double best = 0;
+    k_l2_read<<<sms * 8, 256>>>(d, n_vec, 1, out);  // brings the buffer into L2
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        k_l2_read<<<sms * 8, 256>>>(d, n_vec, sweeps, out);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        count_launch();
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms > 0) best = std::max(best, (double)bytes * sweeps / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d); cudaFree(out);
+    return best;
+}
+
 }  // namespace srt

@@ -361,17 +361,29 @@ static bool renderer_setup(DeviceRenderer* r) {
     // wavefront grid: one resident wave of persistent blocks, each with up to 1024 paths in flight
     // (4 per thread); a rank with few pixels takes fewer paths per block so that every SM still gets work
     uint32_t resident = 0;
-    for (P.block_slots = 1024;; P.block_slots >>= 1) {
-        set_queue_layout(P);
-        SRT_CUDA(T.configure(r->smem + P.queue_bytes));
-        resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.block_threads, r->smem + P.queue_bytes));
-        if (P.block_slots <= P.block_threads || (uint64_t)resident * P.block_slots <= (uint64_t)P.nslots) break;
+    auto fit_block_slots = [&]() -> bool {
+        for (P.block_slots = 1024;; P.block_slots >>= 1) {
+            set_queue_layout(P);
+            SRT_CUDA(T.configure(r->smem + P.queue_bytes));
+            resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.min_blocks, (int)P.block_threads, r->smem + P.queue_bytes));
+            if (P.block_slots <= P.block_threads || (uint64_t)resident * P.block_slots <= (uint64_t)P.nslots) break;
+        }
+        return true;
+    };
+    P.min_blocks = 4;
+    if (!fit_block_slots()) return false;
+    // a rank whose pixels do not even fill the resident blocks once is bound by the serial chain of its longest pixels, not by
+    // throughput: the 80-register build of the kernel (3 blocks per SM) runs a task's dependent chain faster (sched flag 32 / 64 force 4 / 3)
+    const bool chain_bound = P.block_slots <= 256 && r->mode == 2;  // measured on the per-rank shares of C2: 1/8 of the frame 6.67 -> 6.14 ms, 1/4 (512 paths per block) 9.88 -> 10.42 ms
+    if (((c.sched_flags & 64) || (chain_bound && !(c.sched_flags & 32))) && c.pipeline != 1) {
+        P.min_blocks = 3;
+        if (!fit_block_slots()) return false;
     }
     if (c.block_slots >= 32 && c.block_slots <= 4096 && !(c.block_slots & (c.block_slots - 1))) {
         P.block_slots = (uint32_t)c.block_slots;
         set_queue_layout(P);
         SRT_CUDA(T.configure(r->smem + P.queue_bytes));
-        resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.block_threads, r->smem + P.queue_bytes));
+        resident = (uint32_t)sms * (uint32_t)std::max(1, T.wavefront_blocks_per_sm(r->mode, (int)P.min_blocks, (int)P.block_threads, r->smem + P.queue_bytes));
     }
     tr.mark("launch configuration");
     r->wave_grid = (int)std::min<uint64_t>(resident, ((uint64_t)P.nslots + P.block_slots - 1) / P.block_slots);
@@ -768,7 +780,7 @@ bool device_scene_trace(const DeviceScene* s, uint32_t n, const float* o, const 
     QueryBuffers q;
     if (!q.init(n, o, d)) return false;
     // persistent warps that refill themselves from a ray counter: one resident wave is the whole grid
-    const int grid = (int)std::min<uint64_t>((n + SRT_BLOCK - 1) / SRT_BLOCK, (uint64_t)sm_count() * 6);
+    const int grid = (int)std::min<uint64_t>((n + SRT_BLOCK - 1) / SRT_BLOCK, (uint64_t)sm_count() * SRT_TRACE_MIN_BLOCKS);
     const LaunchTable& T = table(g_query_strict);
     T.trace_rays(P, n, q.o, q.d, device_scene_sorted_idx(s), q.t, q.tri, nullptr, q.next, grid, nullptr);  // warm-up
     SRT_CUDA(cudaEventRecord(q.e0));

@@ -728,8 +728,11 @@ __global__ void __launch_bounds__(256) k_prior_cost(WaveParams P) {
 #else
 #define SRT_CLK(v) do { } while (0)
 #endif
-template <bool SMEM, bool FLAT>
-__global__ void __launch_bounds__(SRT_WAVE_BLOCK, SRT_WAVE_MIN_BLOCKS) k_wavefront(WaveParams P) {
+// MINB = resident blocks per SM the register allocation allows: 4 (64 registers, 32 warps per SM: the most work in flight, best when a
+// rank has more pixels than paths in flight) or 3 (80 registers, 24 warps: shorter dependent-issue chains per task, best when a rank's
+// render is bound by the serial chain of its longest pixels -- the per-rank share of an 8-GPU split)
+template <bool SMEM, bool FLAT, int MINB>
+__global__ void __launch_bounds__(SRT_WAVE_BLOCK, MINB) k_wavefront(WaveParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t S = P.block_slots;
     uint16_t* qbuf = reinterpret_cast<uint16_t*>(smem);                        // [2][4][S] queues of local slot ids
@@ -998,7 +1001,7 @@ __global__ void k_resolve_slice(const float* __restrict__ acc, size_t plane, siz
 // ends.  Every active lane processes exactly one BVH node per loop iteration.
 #define SRT_NO_RAY 0xFFFFFFFFu
 template <bool COUNT>
-__global__ void __launch_bounds__(SRT_BLOCK) k_trace_rays(WaveParams P, uint32_t n, const float* __restrict__ o, const float* __restrict__ d,
+__global__ void __launch_bounds__(SRT_BLOCK, SRT_TRACE_MIN_BLOCKS) k_trace_rays(WaveParams P, uint32_t n, const float* __restrict__ o, const float* __restrict__ d,
                                                           const uint32_t* __restrict__ sorted_idx, float* __restrict__ t_out,
                                                           int32_t* __restrict__ tri_out, unsigned long long* counters, uint32_t* next_ray) {
     SceneRef sc;
@@ -1093,9 +1096,12 @@ LaunchTable make_launch_table() {
         {
             const int b = (int)std::max<size_t>(bytes, 48 * 1024);
             const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-            e = cudaFuncSetAttribute(k_wavefront<true, false>, attr, b);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wavefront<true, true>, attr, b);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wavefront<false, false>, attr, b);
+            e = cudaFuncSetAttribute(k_wavefront<true, false, 4>, attr, b);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wavefront<true, true, 4>, attr, b);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wavefront<false, false, 4>, attr, b);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wavefront<true, false, 3>, attr, b);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wavefront<true, true, 3>, attr, b);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wavefront<false, false, 3>, attr, b);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_megakernel<true, false>, attr, b);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_megakernel<true, true>, attr, b);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace_rays_flat, attr, b);
@@ -1107,16 +1113,24 @@ LaunchTable make_launch_table() {
     t.wavefront = [](const WaveParams& P, int mode, int grid, size_t smem, cudaStream_t st) {
         // the queues always live in shared memory, also when the scene does not
         const int threads = (int)P.block_threads;  // <= SRT_WAVE_BLOCK, the launch bound the registers were allocated for
-        if (mode == 2) k_wavefront<true, true><<<grid, threads, smem, st>>>(P);
-        else if (mode == 1) k_wavefront<true, false><<<grid, threads, smem, st>>>(P);
-        else k_wavefront<false, false><<<grid, threads, smem, st>>>(P);
+        if (P.min_blocks == 3) {
+            if (mode == 2) k_wavefront<true, true, 3><<<grid, threads, smem, st>>>(P);
+            else if (mode == 1) k_wavefront<true, false, 3><<<grid, threads, smem, st>>>(P);
+            else k_wavefront<false, false, 3><<<grid, threads, smem, st>>>(P);
+        } else if (mode == 2) k_wavefront<true, true, 4><<<grid, threads, smem, st>>>(P);
+        else if (mode == 1) k_wavefront<true, false, 4><<<grid, threads, smem, st>>>(P);
+        else k_wavefront<false, false, 4><<<grid, threads, smem, st>>>(P);
     };
-    t.wavefront_blocks_per_sm = [](int mode, int threads, size_t smem) {
+    t.wavefront_blocks_per_sm = [](int mode, int min_blocks, int threads, size_t smem) {
         int n = 0;
         cudaError_t e;
-        if (mode == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront<true, true>, threads, smem);
-        else if (mode == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront<true, false>, threads, smem);
-        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront<false, false>, threads, smem);
+        if (min_blocks == 3) {
+            if (mode == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront<true, true, 3>, threads, smem);
+            else if (mode == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront<true, false, 3>, threads, smem);
+            else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront<false, false, 3>, threads, smem);
+        } else if (mode == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront<true, true, 4>, threads, smem);
+        else if (mode == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront<true, false, 4>, threads, smem);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront<false, false, 4>, threads, smem);
         return e == cudaSuccess ? n : 0;
     };
     t.megakernel = [](const WaveParams& P, int mode, int grid, size_t smem, cudaStream_t st) { SRT_DISPATCH(k_megakernel, mode, grid, smem, st, P); };

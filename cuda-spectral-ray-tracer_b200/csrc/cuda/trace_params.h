@@ -7,9 +7,11 @@
 
 #define SRT_BLOCK 256
 #define SRT_REFILL_LANES 8  // k_trace_rays fetches new rays once this many lanes of a warp are idle
+#ifndef SRT_TRACE_MIN_BLOCKS
+#define SRT_TRACE_MIN_BLOCKS 6   // resident blocks per SM of k_trace_rays (the walk is bound by memory latency: warps in flight are what hides it)
+#endif
 #ifndef SRT_WAVE_BLOCK
 #define SRT_WAVE_BLOCK 256      // threads of a persistent wavefront block
-#define SRT_WAVE_MIN_BLOCKS 4   // resident blocks per SM the register allocation must allow
 #endif
 
 namespace srt {
@@ -63,6 +65,7 @@ struct WaveParams {
     uint32_t block_slots, queue_bytes;
     uint32_t tile_slots_log2, tile_w_log2;  // log2(tile_w * tile_h), log2(tile_w)
     uint32_t block_threads;  // threads of a wavefront block (128 or 256)
+    uint32_t min_blocks;     // k_wavefront variant: 4 = 64 registers, 4 blocks per SM; 3 = 80 registers, 3 blocks per SM
     float scene_lo[3], scene_hi[3];  // bounding box of all triangles (host)
     unsigned long long* ray_counter;
     uint4* pass_log;  // debug (SRT_OPT_PASS_LOG): blocks 0..7 record {globaltimer ns (low 32 bits), regenerate, lambertian, metallic | dielectric << 16} per pass
@@ -76,7 +79,7 @@ struct LaunchTable {
     void (*init_slots)(const WaveParams&, cudaStream_t);
     void (*prior_cost)(const WaveParams&, cudaStream_t);
     void (*wavefront)(const WaveParams&, int mode, int grid, size_t smem, cudaStream_t);
-    int (*wavefront_blocks_per_sm)(int mode, int threads, size_t smem);  // resident blocks the hardware grants
+    int (*wavefront_blocks_per_sm)(int mode, int min_blocks, int threads, size_t smem);  // resident blocks the hardware grants
     void (*megakernel)(const WaveParams&, int mode, int grid, size_t smem, cudaStream_t);
     void (*resolve)(const float* acc, size_t plane, uint32_t img_w, uint32_t ox, uint32_t oy, uint32_t w, uint32_t h, uint32_t spp, unsigned char* rgb,
                     cudaStream_t);

@@ -247,6 +247,7 @@ void srt_trim_caches(void) { trim_caches(); }
 
 double srt_measure_fp32_tflops(void) { return measure_fp32_tflops(); }
 double srt_measure_copy_gbs(uint32_t mbytes) { return measure_copy_gbs(mbytes); }
+double srt_measure_l2_read_gbs(void) { return measure_l2_read_gbs(); }
 
 int srt_write_ppm(const char* path, const float* r, const float* g, const float* b, uint32_t w, uint32_t h) { return write_ppm(path, r, g, b, w, h) ? SRT_OK : SRT_ERR_ARG; }
 int srt_write_bmp(const char* path, const float* r, const float* g, const float* b, uint32_t w, uint32_t h) { return write_bmp(path, r, g, b, w, h) ? SRT_OK : SRT_ERR_ARG; }

@@ -199,6 +199,7 @@ void device_renderer_stats(const DeviceRenderer*, srt_stats* s);
 uint64_t kernel_launches();
 double measure_fp32_tflops();
 double measure_copy_gbs(uint32_t mbytes);
+double measure_l2_read_gbs();
 bool cuda_select_device(int dev);
 int cuda_device_count();
 

@@ -118,6 +118,7 @@ _SIGS = [
     ("srt_trim_caches", None, []),
     ("srt_measure_fp32_tflops", C.c_double, []),
     ("srt_measure_copy_gbs", C.c_double, [C.c_uint32]),
+    ("srt_measure_l2_read_gbs", C.c_double, []),
     ("srt_write_ppm", C.c_int, [C.c_char_p, _P, _P, _P, C.c_uint32, C.c_uint32]),
     ("srt_write_bmp", C.c_int, [C.c_char_p, _P, _P, _P, C.c_uint32, C.c_uint32]),
 ]

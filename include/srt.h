@@ -210,7 +210,10 @@ int srt_rm_render_all(srt_render_manager*);
 #define SRT_OPT_PASS_LOG 16      /* debug: 1 = the first 8 blocks of the LAST k_wavefront launch record a time stamp and their queue lengths
                                     every pass; read back with srt_rm_get_pass_log */
 #define SRT_OPT_SCHED_FLAGS 17   /* debug / ablation, bit mask: 1 = first round in slot order (no first-guess cost order),
-                                    4 = queue remainders are not pooled into mixed warps */
+                                    4 = queue remainders are not pooled into mixed warps,
+                                    32 / 64 = force the 64-register (4 blocks per SM) / 80-register (3 blocks per SM) build of the
+                                    wavefront kernel (default: the second one only when the rank's pixels do not fill the
+                                    resident blocks with more than 256 paths each) */
 #define SRT_OPT_TRAVERSAL 10     /* 0 auto (wide-leaf closest hit when the scene has <= 64 triangles), 1 force the LBVH walk
                                     (scene in shared memory), 3 force the LBVH walk with the scene in global memory */
 int srt_rm_set_option(srt_render_manager*, int option, int value);
@@ -279,6 +282,8 @@ void srt_trim_caches(void);
 double srt_measure_fp32_tflops(void);
 /* measured device-to-device copy bandwidth in GB/s (read + write bytes) over `mbytes` MiB */
 double srt_measure_copy_gbs(uint32_t mbytes);
+/* measured L2 read bandwidth in GB/s (all SMs stream a 32 MiB buffer that stays in L2): the second roofline of the LBVH walk */
+double srt_measure_l2_read_gbs(void);
 
 /* ------------------------------------------------------------------ output (io/save_image.cpp:8-13, io/io.cuh:10-23) */
 int srt_write_ppm(const char* path, const float* r, const float* g, const float* b, uint32_t w, uint32_t h);
