@@ -551,7 +551,7 @@ static void widen_rows(const unsigned char* stage, size_t stage_plane, float* co
             for (unsigned y = y0; y < y1; y++) {
                 const unsigned char* src = stage + c * stage_plane + (size_t)y * w;
                 float* o = dst[c] + (size_t)(off_y + y) * img_w + off_x;
-                for (unsigned x = 0; x < w; x++) o[x] = (float)src[x];
+                widen_u8_to_f32(src, o, w);
             }
         }
     };
@@ -632,7 +632,7 @@ bool device_renderer_exchange_film(DeviceRenderer* r, float* fr, float* fg, floa
                 if (!planes[ch]) continue;
                 const unsigned char* src = r->h_stage + (k * 3 + ch) * cnt;
                 float* o = planes[ch] + f;
-                for (size_t i = 0; i < n; i++) o[i] = (float)src[i];
+                widen_u8_to_f32(src, o, n);
             }
         };
         if (npx >= (1u << 18) && world > 1) {

@@ -45,4 +45,10 @@ bool write_bmp(const char* path, const float* r, const float* g, const float* b,
     std::fclose(f);
     return true;
 }
+// frame_buffer holds 0..255 as float (frame_buffer.cuh:6-44) while the film crosses PCIe as one byte per channel: the widening loop,
+// compiled once per instruction set the host may have (the loader picks the clone), vectorised by the compiler
+__attribute__((target_clones("avx2", "default"), optimize("O3"))) void widen_u8_to_f32(const unsigned char* __restrict__ src, float* __restrict__ dst, size_t n) {
+    for (size_t i = 0; i < n; i++) dst[i] = (float)src[i];
+}
+
 }  // namespace srt

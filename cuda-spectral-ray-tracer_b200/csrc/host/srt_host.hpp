@@ -123,6 +123,7 @@ struct FlatLeaf {
     std::vector<uint32_t> to_orig;    // flat position -> original triangle index
     float guard = 0.f;                // grazing threshold on |n.d| / |d| for pairs whose partner plane differs from the head's in the last bits
     float tol = 0.f;                  // `behind` tolerance on |D - n.o| (the largest over the units)
+    uint32_t ymask = 0;               // bit g: units 4g..4g+3 are all y-aligned (normal +-y, frame rows without a y term) and stored in the short form
 };
 bool build_flat_leaf(const std::vector<HostTri>& tris, const std::vector<HostMaterial>& mats, const std::vector<uint32_t>& prio,
                      double origin_l1_bound, FlatLeaf& out);
@@ -199,6 +200,7 @@ void device_renderer_stats(const DeviceRenderer*, srt_stats* s);
 uint64_t kernel_launches();
 double measure_fp32_tflops();
 double measure_copy_gbs(uint32_t mbytes);
+void widen_u8_to_f32(const unsigned char* src, float* dst, size_t n);  // image_io.cpp
 double measure_l2_read_gbs();
 bool cuda_select_device(int dev);
 int cuda_device_count();
