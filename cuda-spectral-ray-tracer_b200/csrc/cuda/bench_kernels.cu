@@ -68,12 +68,13 @@ double measure_copy_gbs(uint32_t mbytes) {
 // L2 read bandwidth: every block streams the same 32 MB buffer (well inside the 126 MB L2, also when a line is cached once per die)
 // with 16-byte loads, several times over; the first sweep (DRAM) is a separate, untimed launch.  Denominator for the LBVH walk on
 // scenes that live in L2 (bench.py: frac_of_l2).
-__global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ buf, size_t n_vec, int sweeps, uint32_t* out) {
+__global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ buf, uint32_t n_vec, int sweeps, uint32_t* out) {
     uint32_t acc = 0;
+    const uint32_t stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;  // n_vec is a multiple of 4 * stride
     for (int s = 0; s < sweeps; s++)
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
-            const uint4 v = __ldcg(buf + ((i + (size_t)s * 4099u) % n_vec));
-            acc += v.x ^ v.y ^ v.z ^ v.w;
+        for (uint32_t i = first; i < n_vec; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
+            const uint4 v0 = __ldcg(buf + i), v1 = __ldcg(buf + i + stride), v2 = __ldcg(buf + i + 2 * stride), v3 = __ldcg(buf + i + 3 * stride);
+            acc += (v0.x ^ v1.y) + (v2.z ^ v3.w);
         }
     if (acc == 0x9E3779B9u) out[0] = acc;  // keeps the loads alive
 }
@@ -81,7 +82,9 @@ double measure_l2_read_gbs() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t bytes = 32u << 20, n_vec = bytes / sizeof(uint4);
+    const uint32_t stride = (uint32_t)sms * 8u * 256u;
+    const uint32_t n_vec = ((32u << 20) / (uint32_t)sizeof(uint4)) / (4u * stride) * (4u * stride);  // ~32 MiB, a whole number of grid strides
+    const size_t bytes = (size_t)n_vec * sizeof(uint4);
     uint4* d = nullptr;
     uint32_t* out = nullptr;
     if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMalloc(&out, 4) != cudaSuccess) { cudaFree(d); return 0; }

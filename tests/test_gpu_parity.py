@@ -359,6 +359,18 @@ def test_paths_in_flight_do_not_change_the_film(srt):
         assert np.array_equal(base[1].view(np.uint32), other[1].view(np.uint32)), kw
 
 
+def test_kernel_builds_do_not_change_the_film(srt):
+    """the wavefront kernel exists in a 64-register (4 blocks per SM) and an 80-register (3 blocks per SM) build; the renderer picks by
+    how many pixels a rank has (SRT_OPT_SCHED_FLAGS 32 / 64 force one).  Strict FP mode pins every rounding, so the films must agree
+    bit for bit, on all three scenes, whole and as one rank's share of a four-way split"""
+    for scene in (0, 1, 2):
+        for tiles in (None, (0, 0, 1, 4)):
+            a = srt.render(scene_id=scene, w=256, h=144, spp=6, bounce=10, strict=True, sched_flags=32, tiles=tiles)
+            b = srt.render(scene_id=scene, w=256, h=144, spp=6, bounce=10, strict=True, sched_flags=64, tiles=tiles)
+            assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), (scene, tiles)
+            assert a[2]["rays"] == b[2]["rays"] > 0
+
+
 @pytest.mark.parametrize("strict", [True, False])
 def test_rounds_do_not_change_the_film(srt, strict):
     """SRT_OPT_ROUNDS: the samples of a pixel rendered in K launches (XORWOW state parked in HBM between them, pixels handed out

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box call: GPU tests, bench (ours + reference arm), ncu launch list, ncu --set full captures.
+# One GPU-box call: GPU tests, bench (ours + reference arm), ncu launch list, ncu captures of the three kernel groups.
 # usage: tools/gpu_baseline.sh <tag> [skip_tests]
 TAG=${1:-r2}
 O=gpurun_out
@@ -16,21 +16,22 @@ CMD="python bench.py --steps 2 --warmup 3 --no-ref-cuda --no-cpu-baseline --no-e
 timeout 300 $CMD > $O/${TAG}_plain_bench.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
-# top kernel
+# top kernel: both launches (rounds) of one warm C2 render
 CMD="python tools/perf_probe.py --variants wave"
 timeout 300 $CMD > $O/${TAG}_plain_wave.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_wavefront -s 1 -c 1 -f -o $O/${TAG}_k_wavefront $CMD > $O/${TAG}_ncu_wave.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_wavefront -s 2 -c 2 -f -o $O/${TAG}_k_wavefront $CMD > $O/${TAG}_ncu_wave.log 2>&1
 echo "wave ncu rc=$?"
 cat $O/${TAG}_plain_wave.log
-# LBVH build at 1M: all kernels of one warm build
+# LBVH build at 1M: the eight launches of one warm build
 CMD="python tools/lbvh_only.py"
 timeout 300 $CMD > $O/${TAG}_plain_lbvh.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -s 18 -c 9 -f -o $O/${TAG}_lbvh_1m $CMD > $O/${TAG}_ncu_lbvh.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -s 16 -c 8 -f -o $O/${TAG}_lbvh_1m $CMD > $O/${TAG}_ncu_lbvh.log 2>&1
 echo "lbvh ncu rc=$?"
 cat $O/${TAG}_plain_lbvh.log
-CMD="python tools/trace_only.py"
+# soup queries of the bench (primary + secondary rays at 1M and 10M): DRAM traffic per launch
+CMD="python tools/lbvh_probe.py"
 timeout 300 $CMD > $O/${TAG}_plain_trace.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_trace_rays -s 1 -c 1 -f -o $O/${TAG}_k_trace_rays $CMD > $O/${TAG}_ncu_trace.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum --clock-control none -k regex:'k_trace_rays|k_bounds|k_morton|k_onesweep|k_permute|k_build_tree' -c 200 --csv --log-file $O/${TAG}_soup_traffic.csv $CMD > $O/${TAG}_ncu_trace.log 2>&1
 echo "trace ncu rc=$?"
 cat $O/${TAG}_plain_trace.log
-ls -la $O
+ls -la $O | tail -30

@@ -2,7 +2,7 @@
 """Attribute an ncu report's per-SASS-instruction counters of one kernel to the source functions / lines of
 trace_impl.cuh.  ncu's own source page needs the original paths; this joins the report's SASS rows with the line table
 nvdisasm prints for the same (unchanged) build of libsrt.so.
-usage: ncu_by_function.py report.ncu-rep mangled_kernel_name [n_lines]"""
+usage: [SRT_NCU_LAUNCH=k] ncu_by_function.py report.ncu-rep mangled_kernel_name [n_lines]   (k-th profiled launch of the report, default the last)"""
 import collections, csv, io, pathlib, re, subprocess, sys, tempfile
 
 ROOT = pathlib.Path(__file__).resolve().parents[1]
@@ -26,7 +26,11 @@ for l in dis[start + 1:]:
         ins.append((m.group(2), cur))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, data = rows[1], rows[2:]
+# one section per profiled launch: a "Kernel Name" row, a header row, then one row per SASS instruction; SRT_NCU_LAUNCH picks one (default: the last)
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+import os
+which = int(os.environ.get("SRT_NCU_LAUNCH", len(starts) - 2))
+hdr, data = rows[starts[which] + 1], rows[starts[which] + 2:starts[which + 1]]
 H = {h: i for i, h in enumerate(hdr)}
 if len(data) != len(ins):
     sys.exit("SASS of the report (%d instructions) and of libsrt.so (%d) differ: rebuild the profiled commit" % (len(data), len(ins)))
