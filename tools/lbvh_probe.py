@@ -3,7 +3,7 @@ import numpy as np
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT / "cuda-spectral-ray-tracer_b200"))
 import srt_b200 as S
-for n in (1 << 20, 10 * (1 << 20)):
+for n in ([int(x) for x in sys.argv[1].split(',')] if len(sys.argv) > 1 else (1 << 20, 10 * (1 << 20))):
     t0 = time.time(); sc = S.Scene(soup=n, seed=1984); t1 = time.time()
     sc.rebuild_lbvh(3)
     rs = [sc.rebuild_lbvh(1) for _ in range(10)]
