@@ -46,17 +46,25 @@ struct alignas(16) SrtFlatUnit {
 };
 #define SRT_FLAT_MAX_UNITS 32
 
-// ---- device BVH node, 64 B = 4 x 16-B vectors (both child boxes in the parent) -----------
-// q0 = (c0.xmin, c0.xmax, c0.ymin, c0.ymax)   q1 = (c1.xmin, c1.xmax, c1.ymin, c1.ymax)
-// q2 = (c0.zmin, c0.zmax, c1.zmin, c1.zmax)   q3 = (child0, child1, -, -)
-// child >= 0: internal node index; child < 0: leaf, triangle index = ~child
-struct alignas(16) SrtNode {
-    float c0xmin, c0xmax, c0ymin, c0ymax;
-    float c1xmin, c1xmax, c1ymin, c1ymax;
-    float c0zmin, c0zmax, c1zmin, c1zmax;
+// ---- device BVH node, 32 B = ONE 32-byte sector, one LDG.256 (both child boxes live in the parent) ----
+// The walk is bound by the L1 / L2 traffic of divergent node fetches (tools/micro/gather_probe.cu: 64-B records as 4 x LDG.128
+// gather at 96 G records/s on a B200, 32-B records as one LDG.256 at 250 G), so the traversal copy of a node stores its child
+// boxes on a uniform 16-bit grid over the scene box (cell = largest extent / 65529, grid coordinate g(x) = (x - lo) / cell + 3):
+//   w0..w2 = child 0: (xmin | xmax << 16), (ymin | ymax << 16), (zmin | zmax << 16)      w3..w5 = child 1, same
+//   w6, w7 = child0, child1: >= 0 internal node index, < 0 leaf with triangle index ~child
+// min = floor(g) - 3, max = ceil(g) + 3: three cells of margin on every side.  The walk's roundings (csrc/cuda/trace_impl.cuh
+// grid_ray: the origin snaps to the grid's integer lattice, <= 0.5 cell; one more rounding of origin / direction, <= 1 cell;
+// build and transform, < 0.05) stay inside that margin, so a stored box always contains, for the walk's arithmetic, the
+// exact float box the reference's closest hit is defined on.  The exact boxes (Karras artefacts, bit-exact vs the oracle) live in
+// node_box_lo / node_box_hi and never enter the walk.
+struct alignas(32) SrtNode {
+    uint32_t c0x, c0y, c0z;
+    uint32_t c1x, c1y, c1z;
     int32_t child0, child1;
-    int32_t pad0, pad1;
 };
+#define SRT_GRID_MARGIN 3
+#define SRT_GRID_CELLS 65529.0f   // 65535 - 2 * margin
+#define SRT_GRID_OFFSET 3.0f     // = margin: the scene box starts at grid coordinate 3, so min - margin >= 0
 
 // ---- device material, 400 B: 95-sample spectrum + parameters ------------------------------
 struct alignas(16) SrtMaterial {

@@ -8,7 +8,7 @@
 //              stable => equal codes stay in triangle-index order
 //   tree     : hierarchy AND refit in one bottom-up kernel, one thread per leaf: a finished subtree [a, b] picks its parent by
 //              comparing the key differences at its two ends (the split with the longer common prefix is the nearer ancestor),
-//              the second subtree to arrive at a split owns both child boxes, unions them and emits the 64-B traversal node
+//              the second subtree to arrive at a split owns both child boxes, unions them and emits the 32-B traversal node (child boxes on the 16-bit scene grid)
 //              under the node's Karras index (no fences: published boxes carry the build's epoch).  There is no separate
 //              top-down split search; left / right / parent arrays are derived from the nodes only when a caller dumps them
 //   permute  : triangles to leaf order -- a pure gather, on a second stream next to the tree kernel
@@ -62,7 +62,7 @@ struct DeviceScene {
     // build products
     float4* leaf_boxes = nullptr;  // n x (lo.xyz -, hi.xyz -), original order: one 32-byte sector per leaf for the refit's gather
     float* centroids = nullptr;   // n x 3
-    float* scene_box = nullptr;   // 6 floats (as ordered ints during the reduction)
+    float* scene_box = nullptr;   // 6 floats + at [8..11] the grid of the traversal nodes: lo.xyz, 1 / cell
     uint32_t* codes = nullptr;    // n, original order
     uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
     uint32_t* hist = nullptr;     // SORT_PASSES x RADIX global digit counts -> exclusive bases
@@ -197,6 +197,11 @@ __global__ void __launch_bounds__(256) k_morton_hist(const float* __restrict__ c
             if (blockIdx.x == 0) scene_box[threadIdx.x] = v;
         }
         __syncthreads();
+        // the quantisation grid of the traversal nodes (srt_types.h): origin and 1 / cell, cell = largest extent / SRT_GRID_CELLS
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const float extent = fmaxf(fmaxf(box[1] - box[0], box[3] - box[2]), fmaxf(box[5] - box[4], 1e-30f));
+            scene_box[8] = box[0]; scene_box[9] = box[2]; scene_box[10] = box[4]; scene_box[11] = SRT_GRID_CELLS / extent;
+        }
     }
     const float b0 = box[0], b1 = box[1], b2 = box[2], b3 = box[3], b4 = box[4], b5 = box[5];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -412,8 +417,12 @@ const uint32_t* pixel_order_build(PixelOrder* o, const uint32_t* cost, uint32_t 
 // numbered by the last leaf of its range, a right child by the first, the root is 0 -- so a node learns its number at the moment it
 // learns which child it is, and its children are `split` (or leaf n-1+split) and `split+1` (or leaf n-1+split+1), exactly the oracle's
 // left[] / right[].  Boxes travel as two 16-byte vectors (lo.xyz | epoch, hi.xyz | epoch) stored under the node's number.
-__device__ __forceinline__ float widen_lo(float v) { return v - fabsf(v) * 2.4e-7f; }
-__device__ __forceinline__ float widen_hi(float v) { return v + fabsf(v) * 2.4e-7f; }
+// a child box on the 16-bit scene grid, SRT_GRID_MARGIN cells of margin (srt_types.h); min in the low half, max in the high half
+__device__ __forceinline__ uint32_t grid_pack(float mn, float mx, float lo, float inv_cell) {
+    const float gl = (mn - lo) * inv_cell + SRT_GRID_OFFSET, gh = (mx - lo) * inv_cell + SRT_GRID_OFFSET;
+    const int ql = max((int)floorf(gl) - SRT_GRID_MARGIN, 0), qh = min((int)ceilf(gh) + SRT_GRID_MARGIN, 65535);
+    return (uint32_t)ql | ((uint32_t)qh << 16);
+}
 __device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
     float4 v;
     asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -425,9 +434,10 @@ __device__ __forceinline__ unsigned long long split_delta(const uint32_t* __rest
 }
 __global__ void __launch_bounds__(256) k_build_tree(int n, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ sorted_idx,
                                                     const float4* __restrict__ leaf_boxes, int32_t* other, float4* node_box_lo, float4* node_box_hi,
-                                                    SrtNode* __restrict__ nodes, uint32_t epoch_bits) {
+                                                    SrtNode* __restrict__ nodes, const float4* __restrict__ grid, uint32_t epoch_bits) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
+    const float4 G = __ldg(grid);
     const uint32_t src = sorted_idx[k];
     float4 lo = leaf_boxes[2ull * src], hi = leaf_boxes[2ull * src + 1];
     const float epoch = __uint_as_float(epoch_bits);  // only ever compared as bits
@@ -444,12 +454,10 @@ __global__ void __launch_bounds__(256) k_build_tree(int n, const uint32_t* __res
             const int self = root ? 0 : (is_left ? b : a);
             const int L = a == split ? n - 1 + split : split, R = b == split + 1 ? n - 1 + split + 1 : split + 1;
             SrtNode nd;
-            nd.c0xmin = widen_lo(llo.x); nd.c0xmax = widen_hi(lhi.x); nd.c0ymin = widen_lo(llo.y); nd.c0ymax = widen_hi(lhi.y);
-            nd.c1xmin = widen_lo(rlo.x); nd.c1xmax = widen_hi(rhi.x); nd.c1ymin = widen_lo(rlo.y); nd.c1ymax = widen_hi(rhi.y);
-            nd.c0zmin = widen_lo(llo.z); nd.c0zmax = widen_hi(lhi.z); nd.c1zmin = widen_lo(rlo.z); nd.c1zmax = widen_hi(rhi.z);
+            nd.c0x = grid_pack(llo.x, lhi.x, G.x, G.w); nd.c0y = grid_pack(llo.y, lhi.y, G.y, G.w); nd.c0z = grid_pack(llo.z, lhi.z, G.z, G.w);
+            nd.c1x = grid_pack(rlo.x, rhi.x, G.x, G.w); nd.c1y = grid_pack(rlo.y, rhi.y, G.y, G.w); nd.c1z = grid_pack(rlo.z, rhi.z, G.z, G.w);
             nd.child0 = L >= n - 1 ? ~(L - (n - 1)) : L;
             nd.child1 = R >= n - 1 ? ~(R - (n - 1)) : R;
-            nd.pad0 = nd.pad1 = 0;
             nodes[self] = nd;
             node_box_lo[self] = lo;
             node_box_hi[self] = hi;
@@ -529,7 +537,7 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
     }
     s->tiles = (n + SORT_TILE - 1) / SORT_TILE;
     bool ok = dalloc(s->verts, 9ull * n) && dalloc(s->tris_in, n) && dalloc(s->mats, mats.size()) && dalloc(s->leaf_boxes, 2ull * n) &&
-              dalloc(s->centroids, 3ull * n) && dalloc(s->scene_box, 6) && dalloc(s->codes, n) && dalloc(s->keys[0], n) && dalloc(s->keys[1], n) &&
+              dalloc(s->centroids, 3ull * n) && dalloc(s->scene_box, 12) && dalloc(s->codes, n) && dalloc(s->keys[0], n) && dalloc(s->keys[1], n) &&
               dalloc(s->vals[0], n) && dalloc(s->vals[1], n) && dalloc(s->hist, SORT_PASSES * RADIX) &&
               dalloc(s->lookback, (size_t)SORT_PASSES * (s->tiles ? s->tiles : 1) * RADIX) && dalloc(s->tile_counter, SORT_PASSES) &&
               dalloc(s->left, n) && dalloc(s->right, n) && dalloc(s->parent, 2ull * n) && dalloc(s->block_boxes, 6 * kBoundsBlocks) && dalloc(s->node_box_lo, 2ull * n) && dalloc(s->node_box_hi, 2ull * n) && dalloc(s->visit, n) &&
@@ -618,7 +626,7 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
         // process-wide counter: an epoch is never used twice, and the box arrays were zeroed when the scene was created (epoch 0 is never handed out)
         uint32_t epoch = g_refit_epoch.fetch_add(1u) + 1u;
         if (epoch == 0) epoch = g_refit_epoch.fetch_add(1u) + 1u;
-        k_build_tree<<<grid_n, 256, 0, st>>>((int)n, s->keys[0], s->vals[0], s->leaf_boxes, reinterpret_cast<int32_t*>(s->visit), s->node_box_lo, s->node_box_hi, s->nodes, epoch);
+        k_build_tree<<<grid_n, 256, 0, st>>>((int)n, s->keys[0], s->vals[0], s->leaf_boxes, reinterpret_cast<int32_t*>(s->visit), s->node_box_lo, s->node_box_hi, s->nodes, reinterpret_cast<const float4*>(s->scene_box + 8), epoch);
         SRT_CUDA(cudaStreamWaitEvent(st, s->ev_side, 0));
         return true;
     };
@@ -672,6 +680,7 @@ bool device_scene_download_lbvh(const DeviceScene* s, LbvhDump& o) {
 
 // accessors for the renderer translation units
 const SrtNode* device_scene_nodes(const DeviceScene* s) { return s->nodes; }
+const float4* device_scene_grid(const DeviceScene* s) { return reinterpret_cast<const float4*>(s->scene_box + 8); }
 const SrtTri* device_scene_tris(const DeviceScene* s) { return s->tris; }
 const SrtFlatUnit* device_scene_flat_units(const DeviceScene* s) { return s->flat_units; }
 const SrtTri* device_scene_flat_tris(const DeviceScene* s) { return s->flat_tris; }

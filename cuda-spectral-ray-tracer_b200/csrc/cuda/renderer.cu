@@ -15,6 +15,7 @@
 namespace srt {
 
 const SrtNode* device_scene_nodes(const DeviceScene* s);
+const float4* device_scene_grid(const DeviceScene* s);
 const SrtTri* device_scene_tris(const DeviceScene* s);
 const SrtFlatUnit* device_scene_flat_units(const DeviceScene* s);
 const SrtTri* device_scene_flat_tris(const DeviceScene* s);
@@ -244,6 +245,7 @@ static bool renderer_setup(DeviceRenderer* r) {
     SRT_CUDA(cudaGetDevice(&r->device));
     if (c.comm && comm_device(c.comm) != r->device) { set_error("the communicator was created on another CUDA device"); return false; }
     P.nodes = device_scene_nodes(r->scene);
+    P.grid = device_scene_grid(r->scene);
     P.tris = device_scene_tris(r->scene);
     P.flat_units = device_scene_flat_units(r->scene);
     P.flat_tris = device_scene_flat_tris(r->scene);
@@ -776,7 +778,7 @@ struct QueryBuffers {  // device buffers and events of one closest-hit query cal
 
 bool device_scene_trace(const DeviceScene* s, uint32_t n, const float* o, const float* d, float* t, int32_t* tri, float* ms, uint64_t* visits) {
     WaveParams P{};
-    P.nodes = device_scene_nodes(s); P.tris = device_scene_tris(s); P.mats = device_scene_mats(s); P.n_tris = (int)device_scene_ntris(s);
+    P.nodes = device_scene_nodes(s); P.grid = device_scene_grid(s); P.tris = device_scene_tris(s); P.mats = device_scene_mats(s); P.n_tris = (int)device_scene_ntris(s);
     QueryBuffers q;
     if (!q.init(n, o, d)) return false;
     // persistent warps that refill themselves from a ray counter: one resident wave is the whole grid

@@ -79,6 +79,8 @@ __device__ __forceinline__ float rng_range(Rng& s, float lo, float hi) {  // uti
 // ------------------------------------------------------------------------------ scene access
 struct SceneRef {
     const SrtNode* nodes;
+    const float4* grid;   // quantisation grid of the node boxes (global memory): lo.xyz, 1 / cell
+    bool nodes_global;    // nodes in global memory (one LDG.256 per node) or staged in shared memory (two 16-byte loads)
     const SrtTri* tris;
     const SrtFlatUnit* units;  // wide leaf only
     int n_units;
@@ -148,26 +150,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 // equal-t ties go to the triangle the reference would have tested last (SrtTri::prio, host/ref_order.cpp)
-// leaf test of the LBVH walk: most leaves whose box the ray enters are still missed, so look at the
-// plane distance with an approximate reciprocal first and only run the exact arithmetic (IEEE
-// division, 2-D edge functions) when the hit could matter.  The skip is conservative: it needs the
-// approximate t to be outside [0, closest] by far more than its error (relative 1e-5 + the
-// cancellation bound of D - n.o), NaN falls through to the exact test.
-__device__ __forceinline__ void consider_leaf(const SrtTri* __restrict__ tris, int i, V3 o, V3 d, float& closest, int& best, uint32_t& best_prio) {
-    const float4 q0 = *reinterpret_cast<const float4*>(tris + i);
-    const float denom = __fmaf_rn(q0.z, d.z, __fmaf_rn(q0.y, d.y, q0.x * d.x));
-    const float no = __fmaf_rn(q0.z, o.z, __fmaf_rn(q0.y, o.y, q0.x * o.x));
-    const float num = q0.w - no;
-    const float slack = 8e-6f * (fabsf(q0.w) + fabsf(q0.x * o.x) + fabsf(q0.y * o.y) + fabsf(q0.z * o.z));
-    const float ta = num * rcp_approx(denom);
-    const bool far_behind = (ta < 0.0f) & (fabsf(num) > slack);
-    const bool far_beyond = ta > closest * 1.00002f + 1e-30f;
-    if (far_behind | (far_beyond & (fabsf(num) > slack))) return;
-    float t;
-    if (!tri_test(tris + i, o, d, closest, t)) return;
-    const uint32_t prio = tris[i].prio;
-    if (t < closest || best < 0 || prio > best_prio) { closest = t; best = i; best_prio = prio; }
-}
 __device__ __forceinline__ void consider_hit(const SrtTri* __restrict__ tris, int i, V3 o, V3 d, float& closest, int& best, uint32_t& best_prio) {
     float t;
     if (!tri_test(tris + i, o, d, closest, t)) return;
@@ -281,52 +263,241 @@ __device__ __forceinline__ int closest_hit_flat(const SceneRef& sc, V3 o, V3 d, 
     return best;
 }
 
-// One step of the LBVH walk: fetch `node` (both child boxes live in the parent: 4 x 16-B loads), test the
-// two boxes, test leaf children on the spot, continue with the nearer internal child and stack the farther.
-// Returns false when the walk is over.
-__device__ __forceinline__ bool lbvh_step(const SceneRef& sc, V3 o, V3 d, V3 inv, int& node, int& sp, int* __restrict__ stack, float& closest, int& best,
-                                          uint32_t& best_prio, uint32_t* visits) {
-    const float ix = inv.x, iy = inv.y, iz = inv.z;
-    const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
-    if (visits) visits[0]++;
-    const float4 b0 = np[0], b1 = np[1], b2 = np[2];
-    const int4 ch = *reinterpret_cast<const int4*>(np + 3);
-    // slabs; a NaN direction makes every comparison below false -> both children are visited,
-    // every triangle test then fails (NaN t), i.e. the path misses exactly like the reference (Q1)
-    float t0x = (b0.x - o.x) * ix, t1x = (b0.y - o.x) * ix;
-    float t0y = (b0.z - o.y) * iy, t1y = (b0.w - o.y) * iy;
-    float t0z = (b2.x - o.z) * iz, t1z = (b2.y - o.z) * iz;
-    float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-    float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-    t0x = (b1.x - o.x) * ix; t1x = (b1.y - o.x) * ix;
-    t0y = (b1.z - o.y) * iy; t1y = (b1.w - o.y) * iy;
-    t0z = (b2.z - o.z) * iz; t1z = (b2.w - o.z) * iz;
-    float n1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-    float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-    // conservative: one-sided slack on both ends so rounding can only add candidates
-    bool h0 = !(n0 * 0.9999995f > fminf(f0 * 1.0000005f, closest));
-    bool h1 = !(n1 * 0.9999995f > fminf(f1 * 1.0000005f, closest));
-    int c0 = ch.x, c1 = ch.y;
-    if (h0 && h1 && n1 < n0) {  // visit the nearer child first
-        const int tc = c0; c0 = c1; c1 = tc;
-    } else if (!h0) {
-        c0 = c1; h0 = h1; h1 = false;
-    }
-    // c0 = first child to process (if h0), c1 = second (if h1)
-    int next = -1;
-    if (h0) {
-        if (c0 < 0) { if (visits) visits[1]++; consider_leaf(sc.tris, ~c0, o, d, closest, best, best_prio); }
-        else next = c0;
-    }
-    if (h1) {
-        if (c1 < 0) { if (visits) visits[1]++; consider_leaf(sc.tris, ~c1, o, d, closest, best, best_prio); }
-        else if (next < 0) next = c1;
-        else stack[sp++] = c1;
-    }
-    if (next >= 0) { node = next; return true; }
-    if (sp == 0) return false;
-    node = stack[--sp];
+// tri::hit on a triangle whose three vectors are already in registers (the walk below loads them next to the node)
+__device__ __forceinline__ bool tri_test_q(float4 q0, float4 q1, float4 q2, V3 o, V3 d, float closest, float& t_out) {
+    const float denom = plane_denom(q0, d);
+    if (fabsf(denom) < 1e-8f) return false;
+    const float t = plane_num(q0, o) / denom;
+    if (!(0.0f <= t && t <= closest)) return false;
+    const uint32_t bits = __float_as_uint(q2.z);
+    const float px = o.x + t * d.x, py = o.y + t * d.y, pz = o.z + t * d.z;
+    const float pw = sel3(px, py, pz, SRT_TRI_WAX(bits)), ph = sel3(px, py, pz, SRT_TRI_HAX(bits));
+    const float a1 = (pw - q1.z) * (q1.y - q1.w) - (q1.x - q1.z) * (ph - q1.w);
+    const float a2 = (pw - q2.x) * (q1.w - q2.y) - (q1.z - q2.x) * (ph - q2.y);
+    const float a3 = (pw - q1.x) * (q2.y - q1.y) - (q2.x - q1.x) * (ph - q1.y);
+    const bool inside = SRT_TRI_CW(bits) ? (a1 >= 0.f && a2 >= 0.f && a3 >= 0.f) : (a1 <= 0.f && a2 <= 0.f && a3 <= 0.f);
+    if (!inside) return false;
+    t_out = t;
     return true;
+}
+
+// ---- the LBVH walk: 32-byte grid nodes, deferred and warp-batched leaf tests, stack in shared memory ----
+// A lane carries an internal node to open (`node`, -1 = none), one leaf whose triangle is still to be tested (`pend`,
+// -1 = none) and a stack of further entries (>= 0 internal node, < 0 leaf = ~triangle) whose top lives in a register:
+// a pop hands out the register and issues the load of the entry below, which nobody waits for before the next pop.
+// One step = (1) a lane without a node takes the top of its stack; (2) lanes with a node load its 32 B (both child
+// boxes live in the parent: one LDG.256), test the two boxes and route the hit children -- the nearer internal one is
+// the next node, the farther goes on the stack, a leaf becomes the pending triangle (or goes on the stack when one is
+// pending already); (3) pending triangles are tested TOGETHER: only when SRT_LEAF_BATCH lanes of the warp have one, or
+// when a lane has nothing else left to do -- tested on the spot, 2.5 of 32 lanes ran the exact triangle arithmetic (ncu).
+// The closest hit does not depend on the order of the tests (equal t: the highest `prio` wins), so the answer equals
+// the plain near-first walk's; deferring only tests boxes against a `closest` that is a few steps old (more visits,
+// never fewer).  Returns false when the lane's walk is over.  `lanes` = the lanes that call this step together.
+#define SRT_STACK_EMPTY 0x7fffffff
+#ifndef SRT_STACK_SMEM
+#define SRT_STACK_SMEM 24  // stack entries per thread in shared memory (k_trace_rays: 24 KB per block of 256)
+#endif
+#ifndef SRT_LEAF_BATCH
+#define SRT_LEAF_BATCH 8
+#endif
+struct Walk {
+    int node, pend, top, sp;
+    float closest;
+    int best;
+    uint32_t best_prio;
+};
+// The ray in the grid space of the node boxes (srt_types.h): origin g(o) + 2^23, snapped to the integer lattice by that very
+// addition (error <= half a cell, inside the boxes' three-cell margin), and 1 / (d / cell).  2^23 + q is the float whose low
+// mantissa bits are the 16-bit coordinate q, so a box plane becomes a float with ONE byte permute (no int -> float
+// conversions) and `plane - origin` is an exact integer difference; the slab parameters are those of the world-space ray.
+// Origins far outside the grid make the snap a relative error (<= 1.2e-7 of t), which the slack on the slab interval covers.
+struct GridRay { V3 om, inv; };
+__device__ __forceinline__ GridRay grid_ray(const SceneRef& sc, V3 o, V3 d) {
+    const float4 G = __ldg(sc.grid);
+    GridRay g;
+    const float shift = SRT_GRID_OFFSET + 8388608.0f;
+    g.om = mk((o.x - G.x) * G.w + shift, (o.y - G.y) * G.w + shift, (o.z - G.z) * G.w + shift);
+    g.inv = mk(1.0f / (d.x * G.w), 1.0f / (d.y * G.w), 1.0f / (d.z * G.w));
+    return g;
+}
+__device__ __forceinline__ float grid_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }  // 2^23 + (w & 0xffff)
+__device__ __forceinline__ float grid_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }  // 2^23 + (w >> 16)
+__device__ __forceinline__ void walk_reset(Walk& w, bool active) {
+    w.node = active ? 0 : -1; w.pend = -1; w.top = SRT_STACK_EMPTY; w.sp = 0;
+    w.closest = FLT_MAX; w.best = -1; w.best_prio = 0;
+}
+// The entries below the cached top: the first SRT_STACK_SMEM of a lane live in shared memory, entry k of thread t at
+// word k * blockDim + t -- every lane in its own bank whatever its depth, so a push or pop of a whole warp is one
+// wavefront (the same stack in local memory: one L1 wavefront per distinct depth, next to the node fetches) -- deeper
+// entries (trees over heavily duplicated Morton codes) spill to local memory.  sm == null: local memory only.
+struct StackRef {
+    int* sm;        // this thread's column of the shared-memory stack (null: local memory only)
+    int* lm;        // local-memory overflow
+    uint32_t stride;
+};
+__device__ __forceinline__ void walk_push(Walk& w, const StackRef& st, int e) {
+    if (w.top != SRT_STACK_EMPTY) {
+        if (st.sm && w.sp < SRT_STACK_SMEM) st.sm[w.sp * st.stride] = w.top;
+        else st.lm[st.sm ? w.sp - SRT_STACK_SMEM : w.sp] = w.top;
+        w.sp++;
+    }
+    w.top = e;
+}
+__device__ __forceinline__ int walk_pop(Walk& w, const StackRef& st) {
+    const int e = w.top;
+    w.top = SRT_STACK_EMPTY;
+    if (w.sp > 0) {
+        --w.sp;
+        if (st.sm && w.sp < SRT_STACK_SMEM) w.top = st.sm[w.sp * st.stride];
+        else w.top = st.lm[st.sm ? w.sp - SRT_STACK_SMEM : w.sp];
+    }
+    return e;
+}
+__device__ __forceinline__ bool lbvh_step(const SceneRef& sc, V3 o, V3 d, const GridRay& g, Walk& w, const StackRef& stack, uint32_t lanes, uint32_t* visits) {
+    if (w.node < 0 && w.top != SRT_STACK_EMPTY) {
+        if (w.top >= 0) w.node = walk_pop(w, stack);
+        else if (w.pend < 0) w.pend = ~walk_pop(w, stack);
+    }
+    if (w.node >= 0) {
+        uint32_t c0x, c0y, c0z, c1x, c1y, c1z;
+        int4 ch;
+        if (sc.nodes_global) {  // one 32-byte sector, one request
+            asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=r"(c0x), "=r"(c0y), "=r"(c0z), "=r"(c1x), "=r"(c1y), "=r"(c1z), "=r"(ch.x), "=r"(ch.y) : "l"(sc.nodes + w.node));
+        } else {
+            const uint4* np = reinterpret_cast<const uint4*>(sc.nodes + w.node);
+            const uint4 a = np[0], b = np[1];
+            c0x = a.x; c0y = a.y; c0z = a.z; c1x = a.w; c1y = b.x; c1z = b.y; ch.x = (int)b.z; ch.y = (int)b.w;
+        }
+        const float ox = g.om.x, oy = g.om.y, oz = g.om.z, ix = g.inv.x, iy = g.inv.y, iz = g.inv.z;
+        if (visits) visits[0]++;
+        // slabs; a NaN direction makes every comparison below false -> both children are visited,
+        // every triangle test then fails (NaN t), i.e. the path misses exactly like the reference (Q1)
+        float t0x = (grid_lo(c0x) - ox) * ix, t1x = (grid_hi(c0x) - ox) * ix;
+        float t0y = (grid_lo(c0y) - oy) * iy, t1y = (grid_hi(c0y) - oy) * iy;
+        float t0z = (grid_lo(c0z) - oz) * iz, t1z = (grid_hi(c0z) - oz) * iz;
+        float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+        float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+        t0x = (grid_lo(c1x) - ox) * ix; t1x = (grid_hi(c1x) - ox) * ix;
+        t0y = (grid_lo(c1y) - oy) * iy; t1y = (grid_hi(c1y) - oy) * iy;
+        t0z = (grid_lo(c1z) - oz) * iz; t1z = (grid_hi(c1z) - oz) * iz;
+        float n1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+        float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+        // conservative: one-sided slack on both ends so rounding can only add candidates
+        // (the relative slack also covers origins far outside the grid, whose lattice snap is relative, not half a cell)
+        bool h0 = !(n0 * 0.999999f > fminf(f0 * 1.000001f, w.closest));
+        bool h1 = !(n1 * 0.999999f > fminf(f1 * 1.000001f, w.closest));
+        int c0 = ch.x, c1 = ch.y;
+        if (h0 && h1 && n1 < n0) {  // the nearer child first
+            const int tc = c0; c0 = c1; c1 = tc;
+        } else if (!h0) {
+            c0 = c1; h0 = h1; h1 = false;
+        }
+        int next = -1;
+        if (h0) {
+            if (c0 >= 0) next = c0;
+            else if (w.pend < 0) w.pend = ~c0;
+            else walk_push(w, stack, c0);
+        }
+        if (h1) {
+            if (c1 >= 0 && next < 0) next = c1;
+            else if (c1 < 0 && w.pend < 0) w.pend = ~c1;
+            else walk_push(w, stack, c1);
+        }
+        w.node = next;
+    }
+    const bool has = w.pend >= 0;
+    const bool stuck = has && w.node < 0 && (w.top == SRT_STACK_EMPTY || w.top < 0);  // only a triangle test gets this lane any further
+    const uint32_t waiting = __ballot_sync(lanes, has);
+    if (__popc(waiting) >= SRT_LEAF_BATCH || __any_sync(lanes, stuck)) {
+        if (has) {
+            if (visits) visits[1]++;
+            const float4* tp = reinterpret_cast<const float4*>(sc.tris + w.pend);
+            const float4 q0 = tp[0], q1 = tp[1], q2 = tp[2];
+            float t;
+            if (tri_test_q(q0, q1, q2, o, d, w.closest, t)) {
+                const uint32_t prio = __float_as_uint(q2.w);
+                if (t < w.closest || w.best < 0 || prio > w.best_prio) { w.closest = t; w.best = w.pend; w.best_prio = prio; }
+            }
+            w.pend = -1;
+        }
+    }
+    return (w.node >= 0) | (w.pend >= 0) | (w.top != SRT_STACK_EMPTY);
+}
+
+// The same walk for ONE lane on its own (the renderer's closest_hit: the lanes of a wavefront task each walk their own ray
+// to the end, there is no warp to batch leaf tests with, and what counts is the latency of a step): the loads of the
+// node and of the pending triangle's plane are issued together up front, so their latencies overlap instead of adding
+// up; the triangle is tested first, then the boxes against the updated `closest`.  Measured on whole renders of the
+// 1M-triangle soup: +10 % over testing a leaf where it is found.
+__device__ __forceinline__ bool lbvh_step_single(const SceneRef& sc, V3 o, V3 d, const GridRay& g, Walk& w, const StackRef& stack, uint32_t* visits) {
+    const bool has_node = w.node >= 0, has_leaf = w.pend >= 0;
+    // unconditional loads (node 0 / triangle 0 stand in for "none": both are hot in L1)
+    uint32_t c0x, c0y, c0z, c1x, c1y, c1z;
+    int4 ch;
+    const SrtNode* nptr = sc.nodes + (has_node ? w.node : 0);
+    if (sc.nodes_global) {
+        asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(c0x), "=r"(c0y), "=r"(c0z), "=r"(c1x), "=r"(c1y), "=r"(c1z), "=r"(ch.x), "=r"(ch.y) : "l"(nptr));
+    } else {
+        const uint4* np = reinterpret_cast<const uint4*>(nptr);
+        const uint4 a = np[0], b = np[1];
+        c0x = a.x; c0y = a.y; c0z = a.z; c1x = a.w; c1y = b.x; c1z = b.y; ch.x = (int)b.z; ch.y = (int)b.w;
+    }
+    const float4* tp = reinterpret_cast<const float4*>(sc.tris + (has_leaf ? w.pend : 0));
+    const float4 q0 = tp[0];
+    if (has_leaf) {
+        if (visits) visits[1]++;
+        const float denom = plane_denom(q0, d);
+        const float tq = plane_num(q0, o) / denom;
+        if (fabsf(denom) >= 1e-8f && 0.0f <= tq && tq <= w.closest) {  // the plane part of tri::hit passes: now the other 32 B
+            const float4 q1 = tp[1], q2 = tp[2];
+            float t;
+            if (tri_test_q(q0, q1, q2, o, d, w.closest, t)) {
+                const uint32_t prio = __float_as_uint(q2.w);
+                if (t < w.closest || w.best < 0 || prio > w.best_prio) { w.closest = t; w.best = w.pend; w.best_prio = prio; }
+            }
+        }
+    }
+    w.pend = -1;
+    int next = -1;
+    if (has_node) {
+        if (visits) visits[0]++;
+        const float ox = g.om.x, oy = g.om.y, oz = g.om.z, ix = g.inv.x, iy = g.inv.y, iz = g.inv.z;
+        float t0x = (grid_lo(c0x) - ox) * ix, t1x = (grid_hi(c0x) - ox) * ix;
+        float t0y = (grid_lo(c0y) - oy) * iy, t1y = (grid_hi(c0y) - oy) * iy;
+        float t0z = (grid_lo(c0z) - oz) * iz, t1z = (grid_hi(c0z) - oz) * iz;
+        float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+        float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+        t0x = (grid_lo(c1x) - ox) * ix; t1x = (grid_hi(c1x) - ox) * ix;
+        t0y = (grid_lo(c1y) - oy) * iy; t1y = (grid_hi(c1y) - oy) * iy;
+        t0z = (grid_lo(c1z) - oz) * iz; t1z = (grid_hi(c1z) - oz) * iz;
+        float n1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+        float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+        bool h0 = !(n0 * 0.999999f > fminf(f0 * 1.000001f, w.closest));
+        bool h1 = !(n1 * 0.999999f > fminf(f1 * 1.000001f, w.closest));
+        int c0 = ch.x, c1 = ch.y;
+        if (h0 && h1 && n1 < n0) {
+            const int tc = c0; c0 = c1; c1 = tc;
+        } else if (!h0) {
+            c0 = c1; h0 = h1; h1 = false;
+        }
+        if (h0) {
+            if (c0 < 0) w.pend = ~c0;
+            else next = c0;
+        }
+        if (h1) {
+            if (c1 < 0 && w.pend < 0) w.pend = ~c1;
+            else if (c1 >= 0 && next < 0) next = c1;
+            else walk_push(w, stack, c1);
+        }
+    }
+    if (next < 0 && w.top != SRT_STACK_EMPTY) {
+        if (w.top >= 0) next = walk_pop(w, stack);
+        else if (w.pend < 0) w.pend = ~walk_pop(w, stack);
+    }
+    w.node = next;
+    return (next >= 0) | (w.pend >= 0) | (w.top != SRT_STACK_EMPTY);
 }
 
 // closest hit over the LBVH: both child boxes live in the parent node (4 x 16-B loads),
@@ -346,13 +517,15 @@ __device__ __forceinline__ int closest_hit(const SceneRef& sc, V3 o, V3 d, float
         if (tri_test(sc.tris, o, d, closest, t)) { t_hit = t; return 0; }
         return -1;
     }
-    const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    int stack[64];
-    int sp = 0;
-    int node = 0;
-    while (lbvh_step(sc, o, d, inv, node, sp, stack, closest, best, best_prio, visits)) {}
-    t_hit = closest;
-    return best;
+    const GridRay g = grid_ray(sc, o, d);
+    int local_stack[64];
+    StackRef stack;
+    stack.sm = nullptr; stack.lm = local_stack; stack.stride = 0;
+    Walk w;
+    walk_reset(w, true);
+    while (lbvh_step_single(sc, o, d, g, w, stack, visits)) {}
+    t_hit = w.closest;
+    return w.best;
 }
 
 // ------------------------------------------------------------------------------ path state
@@ -581,7 +754,7 @@ __device__ __forceinline__ SceneRef load_scene(const WaveParams& P, unsigned cha
     SceneRef sc;
     sc.n_tris = P.n_tris;
     if (!SMEM) {
-        sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.flat_guard = 0.f; sc.flat_tol = 0.f; sc.mats = P.mats; sc.cie = P.cie; sc.bg = P.bg;
+        sc.nodes = P.nodes; sc.grid = P.grid; sc.nodes_global = true; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.flat_guard = 0.f; sc.flat_tol = 0.f; sc.mats = P.mats; sc.cie = P.cie; sc.bg = P.bg;
         return sc;
     }
     // layout: [nodes | pre-test records (flat scenes)] | tris | mats | cie | bg
@@ -600,6 +773,7 @@ __device__ __forceinline__ SceneRef load_scene(const WaveParams& P, unsigned cha
     for (int i = threadIdx.x; i < SRT_NS; i += blockDim.x) f[3 * SRT_NS + i] = P.bg[i];
     __syncthreads();
     sc.nodes = FLAT ? nullptr : reinterpret_cast<const SrtNode*>(dst);
+    sc.grid = P.grid; sc.nodes_global = false;
     sc.units = FLAT ? reinterpret_cast<const SrtFlatUnit*>(dst) : nullptr;
     sc.n_units = FLAT ? P.n_units : 0;
     sc.flat_guard = P.flat_guard; sc.flat_tol = P.flat_tol;
@@ -698,7 +872,7 @@ __global__ void __launch_bounds__(256) k_prior_cost(WaveParams P) {
         const V3 o = mk(cam.center[0], cam.center[1], cam.center[2]);
         const V3 d = ((mk(cam.p00[0], cam.p00[1], cam.p00[2]) + ((float)(P.off_x + ci) * du)) + ((float)(P.off_y + cj) * dv)) - o;
         SceneRef sc;
-        sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.flat_guard = 0.f; sc.flat_tol = 0.f; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
+        sc.nodes = P.nodes; sc.grid = P.grid; sc.nodes_global = true; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.flat_guard = 0.f; sc.flat_tol = 0.f; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
         float t;
         const int tri = closest_hit<false>(sc, o, d, t);
         c = 1;
@@ -995,23 +1169,27 @@ __global__ void k_resolve_slice(const float* __restrict__ acc, size_t plane, siz
 }
 
 // Standalone closest-hit queries (BASELINE.json configs[3]); the scene stays in global memory.
-// Persistent warps with ray refill: rays of one warp end after very different numbers of node visits
-// (ncu on 1M incoherent rays: 7.8 of 32 lanes active with one ray per thread), so lanes that are done
-// fetch the next unprocessed rays from a global counter instead of idling until the warp's longest ray
-// ends.  Every active lane processes exactly one BVH node per loop iteration.
+// Persistent warps with ray refill: rays of one warp end after very different numbers of node visits (ncu on 1M incoherent
+// rays: 7.8 of 32 lanes active with one ray per thread), so lanes that are done fetch the next unprocessed rays from a
+// global counter instead of idling until the warp's longest ray ends.  Every lane takes one step per loop iteration.
 #define SRT_NO_RAY 0xFFFFFFFFu
 template <bool COUNT>
 __global__ void __launch_bounds__(SRT_BLOCK, SRT_TRACE_MIN_BLOCKS) k_trace_rays(WaveParams P, uint32_t n, const float* __restrict__ o, const float* __restrict__ d,
                                                           const uint32_t* __restrict__ sorted_idx, float* __restrict__ t_out,
                                                           int32_t* __restrict__ tri_out, unsigned long long* counters, uint32_t* next_ray) {
     SceneRef sc;
-    sc.nodes = P.nodes; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.flat_guard = 0.f; sc.flat_tol = 0.f; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
+    sc.nodes = P.nodes; sc.grid = P.grid; sc.nodes_global = true; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.flat_guard = 0.f; sc.flat_tol = 0.f; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
     const uint32_t lane = threadIdx.x & 31;
-    int stack[64];
-    int sp = 0, node = 0, best = -1;
-    uint32_t ray = SRT_NO_RAY, best_prio = 0;
-    float closest = FLT_MAX;
-    V3 ro = mk(0, 0, 0), rd = mk(0, 0, 0), inv = mk(0, 0, 0);
+    __shared__ int shared_stack[SRT_STACK_SMEM * SRT_BLOCK];
+    int local_stack[64 - SRT_STACK_SMEM];
+    StackRef stack;
+    stack.sm = shared_stack + threadIdx.x; stack.lm = local_stack; stack.stride = SRT_BLOCK;
+    Walk w;
+    walk_reset(w, false);
+    uint32_t ray = SRT_NO_RAY;
+    V3 ro = mk(0, 0, 0), rd = mk(0, 0, 0);
+    GridRay g;
+    g.om = g.inv = mk(0, 0, 0);
     uint32_t visits[2] = {0, 0};
     bool exhausted = false;
     while (true) {
@@ -1027,19 +1205,20 @@ __global__ void __launch_bounds__(SRT_BLOCK, SRT_TRACE_MIN_BLOCKS) k_trace_rays(
                 ray = mine;
                 ro = mk(o[3ull * mine], o[3ull * mine + 1], o[3ull * mine + 2]);
                 rd = mk(d[3ull * mine], d[3ull * mine + 1], d[3ull * mine + 2]);
-                inv = mk(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
-                closest = FLT_MAX; best = -1; best_prio = 0; sp = 0; node = 0;
+                g = grid_ray(sc, ro, rd);
+                walk_reset(w, true);
                 // same early answers as closest_hit: empty scene, NaN ray (Q1), single triangle
                 bool done = sc.n_tris <= 0 || !(rd.x == rd.x && rd.y == rd.y && rd.z == rd.z && ro.x == ro.x && ro.y == ro.y && ro.z == ro.z);
                 if (!done && sc.n_tris == 1) {
                     float t;
-                    if (tri_test(sc.tris, ro, rd, closest, t)) { closest = t; best = 0; }
+                    if (tri_test(sc.tris, ro, rd, w.closest, t)) { w.closest = t; w.best = 0; }
                     done = true;
                 }
                 if (done) {
-                    t_out[mine] = best >= 0 ? closest : -1.0f;
-                    tri_out[mine] = best >= 0 ? (int32_t)sorted_idx[best] : -1;
+                    t_out[mine] = w.best >= 0 ? w.closest : -1.0f;
+                    tri_out[mine] = w.best >= 0 ? (int32_t)sorted_idx[w.best] : -1;
                     ray = SRT_NO_RAY;
+                    walk_reset(w, false);
                 }
             }
         }
@@ -1047,12 +1226,11 @@ __global__ void __launch_bounds__(SRT_BLOCK, SRT_TRACE_MIN_BLOCKS) k_trace_rays(
             if (exhausted) break;
             continue;
         }
-        if (ray != SRT_NO_RAY) {
-            if (!lbvh_step(sc, ro, rd, inv, node, sp, stack, closest, best, best_prio, COUNT ? visits : nullptr)) {
-                t_out[ray] = best >= 0 ? closest : -1.0f;
-                tri_out[ray] = best >= 0 ? (int32_t)sorted_idx[best] : -1;
-                ray = SRT_NO_RAY;
-            }
+        // every lane takes the step (the leaf batches are a warp's decision); a lane without a ray has an empty walk
+        if (!lbvh_step(sc, ro, rd, g, w, stack, 0xffffffffu, COUNT ? visits : nullptr) && ray != SRT_NO_RAY) {
+            t_out[ray] = w.best >= 0 ? w.closest : -1.0f;
+            tri_out[ray] = w.best >= 0 ? (int32_t)sorted_idx[w.best] : -1;
+            ray = SRT_NO_RAY;
         }
     }
     if (COUNT) { atomicAdd(counters, (unsigned long long)visits[0]); atomicAdd(counters + 1, (unsigned long long)visits[1]); }

@@ -8,7 +8,7 @@
 #define SRT_BLOCK 256
 #define SRT_REFILL_LANES 8  // k_trace_rays fetches new rays once this many lanes of a warp are idle
 #ifndef SRT_TRACE_MIN_BLOCKS
-#define SRT_TRACE_MIN_BLOCKS 6   // resident blocks per SM of k_trace_rays (the walk is bound by memory latency: warps in flight are what hides it)
+#define SRT_TRACE_MIN_BLOCKS 5   // resident blocks per SM of k_trace_rays (the walk is bound by memory latency: warps in flight are what hides it)
 #endif
 #ifndef SRT_WAVE_BLOCK
 #define SRT_WAVE_BLOCK 256      // threads of a persistent wavefront block
@@ -19,6 +19,7 @@ namespace srt {
 struct WaveParams {
     // scene (global memory; small scenes are staged into shared memory by every block)
     const SrtNode* nodes;
+    const float4* grid;  // quantisation grid of the node boxes: lo.xyz, 1 / cell (written by the build)
     const SrtTri* tris;  // leaf order
     const SrtFlatUnit* flat_units;  // wide-leaf pre-test units (mode 2), triangles in flat order follow
     const SrtTri* flat_tris;

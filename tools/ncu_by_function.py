@@ -3,14 +3,14 @@
 trace_impl.cuh.  ncu's own source page needs the original paths; this joins the report's SASS rows with the line table
 nvdisasm prints for the same (unchanged) build of libsrt.so.
 usage: [SRT_NCU_LAUNCH=k] ncu_by_function.py report.ncu-rep mangled_kernel_name [n_lines]   (k-th profiled launch of the report, default the last)"""
-import collections, csv, io, pathlib, re, subprocess, sys, tempfile
+import collections, csv, io, os, pathlib, re, subprocess, sys, tempfile
 
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 rep, kernel = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 tmp = pathlib.Path(tempfile.mkdtemp())
 subprocess.run(["cuobjdump", "-xelf", "all", str(ROOT / "cuda-spectral-ray-tracer_b200" / "libsrt.so")], cwd=tmp, check=True, capture_output=True)
-cubin = [p for p in tmp.iterdir() if p.name.startswith("trace_fast")][0]
+cubin = [p for p in tmp.iterdir() if p.name.startswith(os.environ.get("SRT_NCU_CUBIN", "trace_fast"))][0]
 dis = subprocess.run(["nvdisasm", "-g", str(cubin)], capture_output=True, text=True).stdout.split("\n")
 start = [i for i, l in enumerate(dis) if l.startswith(".text." + kernel + ":")][0]
 cur, ins = None, []
