@@ -66,6 +66,20 @@ struct alignas(32) SrtNode {
 #define SRT_GRID_CELLS 65529.0f   // 65535 - 2 * margin
 #define SRT_GRID_OFFSET 3.0f     // = margin: the scene box starts at grid coordinate 3, so min - margin >= 0
 
+// ---- 4-wide traversal node, 64 B = two sectors, two LDG.256: the boxes and refs of a binary node's (up to) four grandchildren ----
+// Built from the 32-B binary nodes by one streaming pass (lbvh.cu k_collapse4) under the SAME index as the binary node it
+// collapses, so no numbering is needed: slots = for each child of node i, the child itself when it is a leaf, else the
+// child's two children.  The grid coordinates are copied, not re-quantised.  A step of the walk tests four boxes and
+// descends two levels of the binary tree: half the dependent steps per ray, and the per-step overhead of the walk (stack,
+// leaf batches, ray refill) is paid half as often.
+//   w[3k .. 3k+2] = slot k: (xmin | xmax << 16), (ymin | ymax << 16), (zmin | zmax << 16)
+//   w[12 + k]     = slot k's ref: >= 0 wide node index, < 0 leaf with triangle index ~ref, SRT_WIDE_EMPTY = unused slot
+struct alignas(64) SrtWide {
+    uint32_t box[12];
+    int32_t ref[4];
+};
+#define SRT_WIDE_EMPTY 0x7fffffff
+
 // ---- device material, 400 B: 95-sample spectrum + parameters ------------------------------
 struct alignas(16) SrtMaterial {
     float spec[SRT_NS];

@@ -72,7 +72,8 @@ struct DeviceScene {
     float* block_boxes = nullptr;  // kBoundsBlocks x 6 partial scene boxes
     float4 *node_box_lo = nullptr, *node_box_hi = nullptr;  // (2n-1) each: (xmin,ymin,zmin,-), (xmax,ymax,zmax,-)
     uint32_t* visit = nullptr;    // n-1 refit arrival flags
-    SrtNode* nodes = nullptr;     // n-1 traversal nodes
+    SrtNode* nodes = nullptr;     // n-1 binary nodes (child boxes on the scene grid)
+    SrtWide* wide = nullptr;      // n-1 four-wide traversal nodes, same indices
     SrtTri* tris = nullptr;       // n, LEAF order
     // wide leaf (scenes of <= 32 pre-test units): flat-order triangles + units, built on the host
     SrtFlatUnit* flat_units = nullptr;
@@ -482,6 +483,39 @@ __global__ void __launch_bounds__(256) k_build_tree(int n, const uint32_t* __res
         hi = make_float4(fmaxf(hi.x, ohi.x), fmaxf(hi.y, ohi.y), fmaxf(hi.z, ohi.z), epoch);
     }
 }
+// binary nodes -> 4-wide traversal nodes (srt_types.h): node i's slots are its leaf children and the children of its internal
+// children.  A left child is numbered `split`, a right child `split + 1`, so the two child nodes of i are one contiguous 64 B.
+__global__ void __launch_bounds__(256) k_collapse4(int n_internal, const SrtNode* __restrict__ nodes, SrtWide* __restrict__ wide) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    const uint4* np = reinterpret_cast<const uint4*>(nodes + i);
+    const uint4 a = __ldg(np), b = __ldg(np + 1);
+    const uint32_t cbox[2][3] = {{a.x, a.y, a.z}, {a.w, b.x, b.y}};
+    const int cref[2] = {(int)b.z, (int)b.w};
+    uint32_t box[12];
+    int ref[4];
+    int s = 0;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        if (cref[c] < 0) {
+            box[3 * s] = cbox[c][0]; box[3 * s + 1] = cbox[c][1]; box[3 * s + 2] = cbox[c][2];
+            ref[s++] = cref[c];
+        } else {
+            const uint4* cp = reinterpret_cast<const uint4*>(nodes + cref[c]);
+            const uint4 ca = __ldg(cp), cb = __ldg(cp + 1);
+            box[3 * s] = ca.x; box[3 * s + 1] = ca.y; box[3 * s + 2] = ca.z;
+            ref[s++] = (int)cb.z;
+            box[3 * s] = ca.w; box[3 * s + 1] = cb.x; box[3 * s + 2] = cb.y;
+            ref[s++] = (int)cb.w;
+        }
+    }
+    for (; s < 4; s++) { box[3 * s] = box[3 * s + 1] = box[3 * s + 2] = 0u; ref[s] = SRT_WIDE_EMPTY; }
+    uint4* wp = reinterpret_cast<uint4*>(wide + i);
+    wp[0] = make_uint4(box[0], box[1], box[2], box[3]);
+    wp[1] = make_uint4(box[4], box[5], box[6], box[7]);
+    wp[2] = make_uint4(box[8], box[9], box[10], box[11]);
+    wp[3] = make_uint4((uint32_t)ref[0], (uint32_t)ref[1], (uint32_t)ref[2], (uint32_t)ref[3]);
+}
 // left / right / parent in the oracle's numbering (internal i, leaf n-1+k), read off the emitted nodes: only dumps need them
 __global__ void __launch_bounds__(256) k_topology(int n, const SrtNode* __restrict__ nodes, int32_t* __restrict__ left, int32_t* __restrict__ right,
                                                   int32_t* __restrict__ parent) {
@@ -541,7 +575,7 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
               dalloc(s->vals[0], n) && dalloc(s->vals[1], n) && dalloc(s->hist, SORT_PASSES * RADIX) &&
               dalloc(s->lookback, (size_t)SORT_PASSES * (s->tiles ? s->tiles : 1) * RADIX) && dalloc(s->tile_counter, SORT_PASSES) &&
               dalloc(s->left, n) && dalloc(s->right, n) && dalloc(s->parent, 2ull * n) && dalloc(s->block_boxes, 6 * kBoundsBlocks) && dalloc(s->node_box_lo, 2ull * n) && dalloc(s->node_box_hi, 2ull * n) && dalloc(s->visit, n) &&
-              dalloc(s->nodes, n) && dalloc(s->tris, n);
+              dalloc(s->nodes, n) && dalloc(s->wide, n) && dalloc(s->tris, n);
     for (auto& e : s->ev) ok = ok && cuda_ok(cudaEventCreate(&e), "cudaEventCreate", __FILE__, __LINE__);
     ok = ok && cuda_ok(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking), "cudaStreamCreate", __FILE__, __LINE__) &&
          cuda_ok(cudaEventCreateWithFlags(&s->ev_sorted, cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__) &&
@@ -580,7 +614,7 @@ void device_scene_destroy(DeviceScene* s) {
     if (s->ev_sorted) cudaEventDestroy(s->ev_sorted);
     if (s->ev_side) cudaEventDestroy(s->ev_side);
     dfree(s->lookback); dfree(s->tile_counter); dfree(s->left); dfree(s->right); dfree(s->parent); dfree(s->node_box_lo); dfree(s->node_box_hi);
-    dfree(s->visit); dfree(s->nodes); dfree(s->tris); dfree(s->flat_units); dfree(s->flat_tris); dfree(s->flat_to_orig);
+    dfree(s->visit); dfree(s->nodes); dfree(s->wide); dfree(s->tris); dfree(s->flat_units); dfree(s->flat_tris); dfree(s->flat_to_orig);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     delete s;
 }
@@ -627,6 +661,7 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
         uint32_t epoch = g_refit_epoch.fetch_add(1u) + 1u;
         if (epoch == 0) epoch = g_refit_epoch.fetch_add(1u) + 1u;
         k_build_tree<<<grid_n, 256, 0, st>>>((int)n, s->keys[0], s->vals[0], s->leaf_boxes, reinterpret_cast<int32_t*>(s->visit), s->node_box_lo, s->node_box_hi, s->nodes, reinterpret_cast<const float4*>(s->scene_box + 8), epoch);
+        if (n > 1) k_collapse4<<<(n - 1 + 255) / 256, 256, 0, st>>>((int)n - 1, s->nodes, s->wide);
         SRT_CUDA(cudaStreamWaitEvent(st, s->ev_side, 0));
         return true;
     };
@@ -634,7 +669,7 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
         SRT_CUDA(cudaEventRecord(s->ev[0], st));
         if (!enqueue()) return false;
         SRT_CUDA(cudaEventRecord(s->ev[4], st));
-        count_launch(4 + SORT_PASSES);  // bounds, morton, passes, permute, tree
+        count_launch(5 + SORT_PASSES);  // bounds, morton, passes, permute, tree, collapse
         SRT_CUDA_LAST();
     }
     SRT_CUDA(cudaEventSynchronize(s->ev[4]));
@@ -679,7 +714,7 @@ bool device_scene_download_lbvh(const DeviceScene* s, LbvhDump& o) {
 }
 
 // accessors for the renderer translation units
-const SrtNode* device_scene_nodes(const DeviceScene* s) { return s->nodes; }
+const SrtWide* device_scene_nodes(const DeviceScene* s) { return s->wide; }
 const float4* device_scene_grid(const DeviceScene* s) { return reinterpret_cast<const float4*>(s->scene_box + 8); }
 const SrtTri* device_scene_tris(const DeviceScene* s) { return s->tris; }
 const SrtFlatUnit* device_scene_flat_units(const DeviceScene* s) { return s->flat_units; }

@@ -14,7 +14,7 @@
 
 namespace srt {
 
-const SrtNode* device_scene_nodes(const DeviceScene* s);
+const SrtWide* device_scene_nodes(const DeviceScene* s);
 const float4* device_scene_grid(const DeviceScene* s);
 const SrtTri* device_scene_tris(const DeviceScene* s);
 const SrtFlatUnit* device_scene_flat_units(const DeviceScene* s);

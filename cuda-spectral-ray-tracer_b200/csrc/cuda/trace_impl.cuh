@@ -78,7 +78,7 @@ __device__ __forceinline__ float rng_range(Rng& s, float lo, float hi) {  // uti
 
 // ------------------------------------------------------------------------------ scene access
 struct SceneRef {
-    const SrtNode* nodes;
+    const SrtWide* nodes;
     const float4* grid;   // quantisation grid of the node boxes (global memory): lo.xyz, 1 / cell
     bool nodes_global;    // nodes in global memory (one LDG.256 per node) or staged in shared memory (two 16-byte loads)
     const SrtTri* tris;
@@ -294,6 +294,9 @@ __device__ __forceinline__ bool tri_test_q(float4 q0, float4 q1, float4 q2, V3 o
 // the plain near-first walk's; deferring only tests boxes against a `closest` that is a few steps old (more visits,
 // never fewer).  Returns false when the lane's walk is over.  `lanes` = the lanes that call this step together.
 #define SRT_STACK_EMPTY 0x7fffffff
+// a 4-wide step stacks up to three entries and descends two binary levels; the binary tree over 30-bit codes + index bits is at
+// most ~54 deep: 3 * 27 + 1 entries
+#define SRT_STACK_MAX 96
 #ifndef SRT_STACK_SMEM
 #define SRT_STACK_SMEM 24  // stack entries per thread in shared memory (k_trace_rays: 24 KB per block of 256)
 #endif
@@ -353,56 +356,81 @@ __device__ __forceinline__ int walk_pop(Walk& w, const StackRef& st) {
     }
     return e;
 }
+// Open a 4-wide node (srt_types.h SrtWide): 64 B as two LDG.256 (two 32-byte sectors of one line), four slab tests.
+// key[k] = entry parameter of slot k's box, +inf when the slot is unused or the box is missed; sorted ascending on return
+// together with the slots' refs (5 compare-exchanges), so that the caller can stack the farther children first.
+// Conservative: one-sided slack on both ends of the slab interval, so rounding can only add candidates (the relative
+// slack also covers origins far outside the grid, whose lattice snap is relative, not half a cell).  A NaN direction never
+// gets here (closest_hit / k_trace_rays answer NaN rays up front); an infinite 1/d leaves +-inf or NaN slab parameters,
+// which fminf / fmaxf order or drop.
+__device__ __forceinline__ void wide_cx(float& ka, int& ra, float& kb, int& rb) {
+    const bool sw = kb < ka;
+    const float k0 = fminf(ka, kb), k1 = fmaxf(ka, kb);
+    const int r0 = sw ? rb : ra, r1 = sw ? ra : rb;
+    ka = k0; kb = k1; ra = r0; rb = r1;
+}
+__device__ __forceinline__ void wide_open(const SceneRef& sc, int node, const GridRay& g, float closest, float key[4], int ref[4]) {
+    uint32_t bx[12];
+    if (sc.nodes_global) {
+        asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(bx[0]), "=r"(bx[1]), "=r"(bx[2]), "=r"(bx[3]), "=r"(bx[4]), "=r"(bx[5]), "=r"(bx[6]), "=r"(bx[7]) : "l"(sc.nodes + node));
+        asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(bx[8]), "=r"(bx[9]), "=r"(bx[10]), "=r"(bx[11]), "=r"(ref[0]), "=r"(ref[1]), "=r"(ref[2]), "=r"(ref[3])
+            : "l"(reinterpret_cast<const char*>(sc.nodes + node) + 32));
+    } else {
+        const uint4* np = reinterpret_cast<const uint4*>(sc.nodes + node);
+        const uint4 a = np[0], b = np[1], c = np[2], e = np[3];
+        bx[0] = a.x; bx[1] = a.y; bx[2] = a.z; bx[3] = a.w; bx[4] = b.x; bx[5] = b.y; bx[6] = b.z; bx[7] = b.w;
+        bx[8] = c.x; bx[9] = c.y; bx[10] = c.z; bx[11] = c.w;
+        ref[0] = (int)e.x; ref[1] = (int)e.y; ref[2] = (int)e.z; ref[3] = (int)e.w;
+    }
+    const float ox = g.om.x, oy = g.om.y, oz = g.om.z, ix = g.inv.x, iy = g.inv.y, iz = g.inv.z;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float t0x = (grid_lo(bx[3 * k]) - ox) * ix, t1x = (grid_hi(bx[3 * k]) - ox) * ix;
+        const float t0y = (grid_lo(bx[3 * k + 1]) - oy) * iy, t1y = (grid_hi(bx[3 * k + 1]) - oy) * iy;
+        const float t0z = (grid_lo(bx[3 * k + 2]) - oz) * iz, t1z = (grid_hi(bx[3 * k + 2]) - oz) * iz;
+        const float nn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+        const float ff = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+        const bool hit = ref[k] != SRT_WIDE_EMPTY && !(nn * 0.999999f > fminf(ff * 1.000001f, closest));
+        key[k] = hit ? nn : INFINITY;
+    }
+    wide_cx(key[0], ref[0], key[1], ref[1]);
+    wide_cx(key[2], ref[2], key[3], ref[3]);
+    wide_cx(key[0], ref[0], key[2], ref[2]);
+    wide_cx(key[1], ref[1], key[3], ref[3]);
+    wide_cx(key[1], ref[1], key[2], ref[2]);
+}
+__device__ __forceinline__ void walk_test_leaf(const SceneRef& sc, V3 o, V3 d, Walk& w, float4 q0, float4 q1, float4 q2) {
+    float t;
+    if (tri_test_q(q0, q1, q2, o, d, w.closest, t)) {
+        const uint32_t prio = __float_as_uint(q2.w);
+        if (t < w.closest || w.best < 0 || prio > w.best_prio) { w.closest = t; w.best = w.pend; w.best_prio = prio; }
+    }
+}
 __device__ __forceinline__ bool lbvh_step(const SceneRef& sc, V3 o, V3 d, const GridRay& g, Walk& w, const StackRef& stack, uint32_t lanes, uint32_t* visits) {
     if (w.node < 0 && w.top != SRT_STACK_EMPTY) {
         if (w.top >= 0) w.node = walk_pop(w, stack);
         else if (w.pend < 0) w.pend = ~walk_pop(w, stack);
     }
     if (w.node >= 0) {
-        uint32_t c0x, c0y, c0z, c1x, c1y, c1z;
-        int4 ch;
-        if (sc.nodes_global) {  // one 32-byte sector, one request
-            asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                : "=r"(c0x), "=r"(c0y), "=r"(c0z), "=r"(c1x), "=r"(c1y), "=r"(c1z), "=r"(ch.x), "=r"(ch.y) : "l"(sc.nodes + w.node));
-        } else {
-            const uint4* np = reinterpret_cast<const uint4*>(sc.nodes + w.node);
-            const uint4 a = np[0], b = np[1];
-            c0x = a.x; c0y = a.y; c0z = a.z; c1x = a.w; c1y = b.x; c1z = b.y; ch.x = (int)b.z; ch.y = (int)b.w;
-        }
-        const float ox = g.om.x, oy = g.om.y, oz = g.om.z, ix = g.inv.x, iy = g.inv.y, iz = g.inv.z;
+        float key[4];
+        int ref[4];
+        wide_open(sc, w.node, g, w.closest, key, ref);
         if (visits) visits[0]++;
-        // slabs; a NaN direction makes every comparison below false -> both children are visited,
-        // every triangle test then fails (NaN t), i.e. the path misses exactly like the reference (Q1)
-        float t0x = (grid_lo(c0x) - ox) * ix, t1x = (grid_hi(c0x) - ox) * ix;
-        float t0y = (grid_lo(c0y) - oy) * iy, t1y = (grid_hi(c0y) - oy) * iy;
-        float t0z = (grid_lo(c0z) - oz) * iz, t1z = (grid_hi(c0z) - oz) * iz;
-        float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-        float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-        t0x = (grid_lo(c1x) - ox) * ix; t1x = (grid_hi(c1x) - ox) * ix;
-        t0y = (grid_lo(c1y) - oy) * iy; t1y = (grid_hi(c1y) - oy) * iy;
-        t0z = (grid_lo(c1z) - oz) * iz; t1z = (grid_hi(c1z) - oz) * iz;
-        float n1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-        float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-        // conservative: one-sided slack on both ends so rounding can only add candidates
-        // (the relative slack also covers origins far outside the grid, whose lattice snap is relative, not half a cell)
-        bool h0 = !(n0 * 0.999999f > fminf(f0 * 1.000001f, w.closest));
-        bool h1 = !(n1 * 0.999999f > fminf(f1 * 1.000001f, w.closest));
-        int c0 = ch.x, c1 = ch.y;
-        if (h0 && h1 && n1 < n0) {  // the nearer child first
-            const int tc = c0; c0 = c1; c1 = tc;
-        } else if (!h0) {
-            c0 = c1; h0 = h1; h1 = false;
+        // the farther children go on the stack first (the nearest of them pops first); the nearest child is the next node
+#pragma unroll
+        for (int k = 3; k >= 1; k--) {
+            if (key[k] < INFINITY) {
+                if (ref[k] < 0 && w.pend < 0) w.pend = ~ref[k];
+                else walk_push(w, stack, ref[k]);
+            }
         }
         int next = -1;
-        if (h0) {
-            if (c0 >= 0) next = c0;
-            else if (w.pend < 0) w.pend = ~c0;
-            else walk_push(w, stack, c0);
-        }
-        if (h1) {
-            if (c1 >= 0 && next < 0) next = c1;
-            else if (c1 < 0 && w.pend < 0) w.pend = ~c1;
-            else walk_push(w, stack, c1);
+        if (key[0] < INFINITY) {
+            if (ref[0] >= 0) next = ref[0];
+            else if (w.pend < 0) w.pend = ~ref[0];
+            else walk_push(w, stack, ref[0]);
         }
         w.node = next;
     }
@@ -414,11 +442,7 @@ __device__ __forceinline__ bool lbvh_step(const SceneRef& sc, V3 o, V3 d, const 
             if (visits) visits[1]++;
             const float4* tp = reinterpret_cast<const float4*>(sc.tris + w.pend);
             const float4 q0 = tp[0], q1 = tp[1], q2 = tp[2];
-            float t;
-            if (tri_test_q(q0, q1, q2, o, d, w.closest, t)) {
-                const uint32_t prio = __float_as_uint(q2.w);
-                if (t < w.closest || w.best < 0 || prio > w.best_prio) { w.closest = t; w.best = w.pend; w.best_prio = prio; }
-            }
+            walk_test_leaf(sc, o, d, w, q0, q1, q2);
             w.pend = -1;
         }
     }
@@ -426,70 +450,43 @@ __device__ __forceinline__ bool lbvh_step(const SceneRef& sc, V3 o, V3 d, const 
 }
 
 // The same walk for ONE lane on its own (the renderer's closest_hit: the lanes of a wavefront task each walk their own ray
-// to the end, there is no warp to batch leaf tests with, and what counts is the latency of a step): the loads of the
-// node and of the pending triangle's plane are issued together up front, so their latencies overlap instead of adding
-// up; the triangle is tested first, then the boxes against the updated `closest`.  Measured on whole renders of the
-// 1M-triangle soup: +10 % over testing a leaf where it is found.
+// to the end, there is no warp to batch leaf tests with, and what counts is the latency of a step): the pending triangle's
+// plane is loaded next to the node, so the two latencies overlap instead of adding up; the triangle is tested first,
+// then the boxes against the updated `closest`.
 __device__ __forceinline__ bool lbvh_step_single(const SceneRef& sc, V3 o, V3 d, const GridRay& g, Walk& w, const StackRef& stack, uint32_t* visits) {
     const bool has_node = w.node >= 0, has_leaf = w.pend >= 0;
-    // unconditional loads (node 0 / triangle 0 stand in for "none": both are hot in L1)
-    uint32_t c0x, c0y, c0z, c1x, c1y, c1z;
-    int4 ch;
-    const SrtNode* nptr = sc.nodes + (has_node ? w.node : 0);
-    if (sc.nodes_global) {
-        asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-            : "=r"(c0x), "=r"(c0y), "=r"(c0z), "=r"(c1x), "=r"(c1y), "=r"(c1z), "=r"(ch.x), "=r"(ch.y) : "l"(nptr));
-    } else {
-        const uint4* np = reinterpret_cast<const uint4*>(nptr);
-        const uint4 a = np[0], b = np[1];
-        c0x = a.x; c0y = a.y; c0z = a.z; c1x = a.w; c1y = b.x; c1z = b.y; ch.x = (int)b.z; ch.y = (int)b.w;
-    }
+    // unconditional load (triangle 0 stands in for "none": hot in L1), issued before the node's
     const float4* tp = reinterpret_cast<const float4*>(sc.tris + (has_leaf ? w.pend : 0));
     const float4 q0 = tp[0];
+    float key[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    int ref[4] = {SRT_WIDE_EMPTY, SRT_WIDE_EMPTY, SRT_WIDE_EMPTY, SRT_WIDE_EMPTY};
+    float closest_for_boxes = w.closest;
     if (has_leaf) {
         if (visits) visits[1]++;
         const float denom = plane_denom(q0, d);
         const float tq = plane_num(q0, o) / denom;
         if (fabsf(denom) >= 1e-8f && 0.0f <= tq && tq <= w.closest) {  // the plane part of tri::hit passes: now the other 32 B
             const float4 q1 = tp[1], q2 = tp[2];
-            float t;
-            if (tri_test_q(q0, q1, q2, o, d, w.closest, t)) {
-                const uint32_t prio = __float_as_uint(q2.w);
-                if (t < w.closest || w.best < 0 || prio > w.best_prio) { w.closest = t; w.best = w.pend; w.best_prio = prio; }
-            }
+            walk_test_leaf(sc, o, d, w, q0, q1, q2);
         }
+        closest_for_boxes = w.closest;
     }
     w.pend = -1;
     int next = -1;
     if (has_node) {
         if (visits) visits[0]++;
-        const float ox = g.om.x, oy = g.om.y, oz = g.om.z, ix = g.inv.x, iy = g.inv.y, iz = g.inv.z;
-        float t0x = (grid_lo(c0x) - ox) * ix, t1x = (grid_hi(c0x) - ox) * ix;
-        float t0y = (grid_lo(c0y) - oy) * iy, t1y = (grid_hi(c0y) - oy) * iy;
-        float t0z = (grid_lo(c0z) - oz) * iz, t1z = (grid_hi(c0z) - oz) * iz;
-        float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-        float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-        t0x = (grid_lo(c1x) - ox) * ix; t1x = (grid_hi(c1x) - ox) * ix;
-        t0y = (grid_lo(c1y) - oy) * iy; t1y = (grid_hi(c1y) - oy) * iy;
-        t0z = (grid_lo(c1z) - oz) * iz; t1z = (grid_hi(c1z) - oz) * iz;
-        float n1 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-        float f1 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-        bool h0 = !(n0 * 0.999999f > fminf(f0 * 1.000001f, w.closest));
-        bool h1 = !(n1 * 0.999999f > fminf(f1 * 1.000001f, w.closest));
-        int c0 = ch.x, c1 = ch.y;
-        if (h0 && h1 && n1 < n0) {
-            const int tc = c0; c0 = c1; c1 = tc;
-        } else if (!h0) {
-            c0 = c1; h0 = h1; h1 = false;
+        wide_open(sc, w.node, g, closest_for_boxes, key, ref);
+#pragma unroll
+        for (int k = 3; k >= 1; k--) {
+            if (key[k] < INFINITY) {
+                if (ref[k] < 0 && w.pend < 0) w.pend = ~ref[k];
+                else walk_push(w, stack, ref[k]);
+            }
         }
-        if (h0) {
-            if (c0 < 0) w.pend = ~c0;
-            else next = c0;
-        }
-        if (h1) {
-            if (c1 < 0 && w.pend < 0) w.pend = ~c1;
-            else if (c1 >= 0 && next < 0) next = c1;
-            else walk_push(w, stack, c1);
+        if (key[0] < INFINITY) {
+            if (ref[0] >= 0) next = ref[0];
+            else if (w.pend < 0) w.pend = ~ref[0];
+            else walk_push(w, stack, ref[0]);
         }
     }
     if (next < 0 && w.top != SRT_STACK_EMPTY) {
@@ -500,8 +497,7 @@ __device__ __forceinline__ bool lbvh_step_single(const SceneRef& sc, V3 o, V3 d,
     return (next >= 0) | (w.pend >= 0) | (w.top != SRT_STACK_EMPTY);
 }
 
-// closest hit over the LBVH: both child boxes live in the parent node (4 x 16-B loads),
-// near child first, far child pushed.  Returns leaf-order triangle index or -1.
+// closest hit over the LBVH (4-wide traversal nodes), nearest child first, the others stacked far to near.  Returns leaf-order triangle index or -1.
 template <bool FLAT>
 __device__ __forceinline__ int closest_hit(const SceneRef& sc, V3 o, V3 d, float& t_hit, uint32_t* visits = nullptr) {
     float closest = FLT_MAX;
@@ -518,7 +514,7 @@ __device__ __forceinline__ int closest_hit(const SceneRef& sc, V3 o, V3 d, float
         return -1;
     }
     const GridRay g = grid_ray(sc, o, d);
-    int local_stack[64];
+    int local_stack[SRT_STACK_MAX];
     StackRef stack;
     stack.sm = nullptr; stack.lm = local_stack; stack.stride = 0;
     Walk w;
@@ -760,7 +756,7 @@ __device__ __forceinline__ SceneRef load_scene(const WaveParams& P, unsigned cha
     // layout: [nodes | pre-test records (flat scenes)] | tris | mats | cie | bg
     const int n_nodes = P.n_tris > 1 ? P.n_tris - 1 : 0;
     float4* dst = reinterpret_cast<float4*>(smem);
-    const int v_head = FLAT ? P.n_units * (int)(sizeof(SrtFlatUnit) / 16) : n_nodes * (int)(sizeof(SrtNode) / 16);
+    const int v_head = FLAT ? P.n_units * (int)(sizeof(SrtFlatUnit) / 16) : n_nodes * (int)(sizeof(SrtWide) / 16);
     const float4* head = FLAT ? reinterpret_cast<const float4*>(P.flat_units) : reinterpret_cast<const float4*>(P.nodes);
     const int n_stage_tris = FLAT ? 2 * P.n_units : P.n_tris;  // flat order: two triangle slots per unit
     const float4* tri_src = FLAT ? reinterpret_cast<const float4*>(P.flat_tris) : reinterpret_cast<const float4*>(P.tris);
@@ -772,7 +768,7 @@ __device__ __forceinline__ SceneRef load_scene(const WaveParams& P, unsigned cha
     for (int i = threadIdx.x; i < 3 * SRT_NS; i += blockDim.x) f[i] = P.cie[i];
     for (int i = threadIdx.x; i < SRT_NS; i += blockDim.x) f[3 * SRT_NS + i] = P.bg[i];
     __syncthreads();
-    sc.nodes = FLAT ? nullptr : reinterpret_cast<const SrtNode*>(dst);
+    sc.nodes = FLAT ? nullptr : reinterpret_cast<const SrtWide*>(dst);
     sc.grid = P.grid; sc.nodes_global = false;
     sc.units = FLAT ? reinterpret_cast<const SrtFlatUnit*>(dst) : nullptr;
     sc.n_units = FLAT ? P.n_units : 0;
@@ -1181,7 +1177,7 @@ __global__ void __launch_bounds__(SRT_BLOCK, SRT_TRACE_MIN_BLOCKS) k_trace_rays(
     sc.nodes = P.nodes; sc.grid = P.grid; sc.nodes_global = true; sc.tris = P.tris; sc.units = nullptr; sc.n_units = 0; sc.flat_guard = 0.f; sc.flat_tol = 0.f; sc.mats = P.mats; sc.cie = nullptr; sc.bg = nullptr; sc.n_tris = P.n_tris;
     const uint32_t lane = threadIdx.x & 31;
     __shared__ int shared_stack[SRT_STACK_SMEM * SRT_BLOCK];
-    int local_stack[64 - SRT_STACK_SMEM];
+    int local_stack[SRT_STACK_MAX - SRT_STACK_SMEM];
     StackRef stack;
     stack.sm = shared_stack + threadIdx.x; stack.lm = local_stack; stack.stride = SRT_BLOCK;
     Walk w;
@@ -1256,7 +1252,7 @@ __global__ void __launch_bounds__(SRT_BLOCK) k_trace_rays_flat(WaveParams P, uin
 // 2: scene staged in shared memory, <= 64 triangles, wide-leaf closest hit (no tree walk)
 static size_t scene_smem_bytes(const WaveParams& P, int mode) {
     const size_t n_nodes = P.n_tris > 1 ? P.n_tris - 1 : 0;
-    const size_t head = mode == 2 ? (size_t)P.n_units * sizeof(SrtFlatUnit) : n_nodes * sizeof(SrtNode);
+    const size_t head = mode == 2 ? (size_t)P.n_units * sizeof(SrtFlatUnit) : n_nodes * sizeof(SrtWide);
     return head + (size_t)(mode == 2 ? 2 * P.n_units : P.n_tris) * sizeof(SrtTri) + (size_t)P.n_mats * sizeof(SrtMaterial) + 4 * SRT_NS * sizeof(float);
 }
 #define SRT_DISPATCH(KERNEL, MODE, GRID, SMEMB, ST, ...)                                  \

@@ -18,7 +18,7 @@ namespace srt {
 
 struct WaveParams {
     // scene (global memory; small scenes are staged into shared memory by every block)
-    const SrtNode* nodes;
+    const SrtWide* nodes;  // four-wide traversal nodes
     const float4* grid;  // quantisation grid of the node boxes: lo.xyz, 1 / cell (written by the build)
     const SrtTri* tris;  // leaf order
     const SrtFlatUnit* flat_units;  // wide-leaf pre-test units (mode 2), triangles in flat order follow

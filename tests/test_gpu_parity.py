@@ -215,6 +215,54 @@ def test_trace_rays_vs_bruteforce(srt):
             assert tri[k] == -1
 
 
+def test_grid_nodes_adversarial_rays(srt):
+    """The walk's traversal nodes store child boxes on a 16-bit scene grid and snap the ray origin to that grid's lattice
+    (csrc/common/srt_types.h, trace_impl.cuh grid_ray).  A stored box must never lose a triangle the exact test accepts:
+    origins far outside the scene (the lattice snap turns from half a cell into a relative error), axis-parallel rays
+    (infinite slab parameters), origins on lattice points and on the scene box, rays grazing along box planes, tiny soups
+    whose triangles are far apart in grid cells -- every answer bit-equal to brute force over all triangles."""
+    rs = np.random.RandomState(11)
+    for n in (2000, 20000):
+        sg = srt.Scene(soup=n, seed=5)
+        sc = oracle.Scene(soup=n, seed=5)
+        f, _ = sc.tris()
+        lo = f[:, [13, 15, 17]].min(0); hi = f[:, [14, 16, 18]].max(0)
+        ext = float((hi - lo).max()); cell = ext / 65529.0
+        O, D = [], []
+        tgt = (lo + rs.rand(60, 3) * (hi - lo)).astype(np.float32)
+        # far origins aimed into the soup.  Not farther than 300 extents: beyond that the reference's own float hit point is off
+        # by more than a triangle's thickness in its projection plane and tri::hit accepts points that miss the triangle's box
+        # by whole units (seen at 3000 extents) -- no box-pruned traversal, the reference's bvh::hit included, returns those
+        for scale in (3.0, 30.0, 300.0):
+            dirs = rs.randn(60, 3); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+            o = tgt - dirs * ext * scale
+            O.append(o); D.append(tgt - o)
+        for ax in range(3):  # axis-parallel rays from outside and inside
+            o = (lo + rs.rand(40, 3) * (hi - lo)); d = np.zeros((40, 3)); d[:, ax] = rs.choice([-1.0, 1.0], 40)
+            O.append(o); D.append(d)
+            o2 = o.copy(); o2[:, ax] = lo[ax] - 10.0; d2 = np.zeros((40, 3)); d2[:, ax] = 1.0
+            O.append(o2); D.append(d2)
+        k = rs.randint(0, 65529, (60, 3))  # origins exactly on lattice points, random directions
+        O.append(lo + k * cell); D.append(rs.randn(60, 3))
+        o = lo + rs.rand(60, 3) * (hi - lo)  # origins on the scene box, directions along its faces
+        ax = rs.randint(0, 3, 60); o[np.arange(60), ax] = np.where(rs.rand(60) < 0.5, lo[ax], hi[ax])
+        d = rs.randn(60, 3); d[np.arange(60), ax] *= 1e-6
+        O.append(o); D.append(d)
+        v = f[rs.randint(0, n - 2, 60)]  # rays through triangle vertices (box corners of leaves), grazing
+        O.append(v[:, 0:3] - rs.randn(60, 3) * 40.0); D.append(v[:, 0:3] - O[-1])
+        o = np.concatenate(O).astype(np.float32); d = np.concatenate(D).astype(np.float32)
+        t, tri, ms = sg.trace_rays(o, d)
+        hits = 0
+        for i in range(o.shape[0]):
+            h, out, idx = sc.brute_hit(o[i], d[i])
+            if h:
+                hits += 1
+                assert tri[i] >= 0 and np.float32(out[1]) == t[i], (n, i, out[1], t[i], idx, tri[i])
+            else:
+                assert tri[i] == -1, (n, i, t[i], tri[i])
+        assert hits > 0.3 * o.shape[0]
+
+
 def test_full_size_properties(srt):
     """BASELINE.json configs[1] size (1920x1080) at reduced spp: size-independent properties --
     the black margin outside the box stays exactly zero, the image mean matches the oracle's
