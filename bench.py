@@ -476,11 +476,11 @@ def main():
             o2 = (o[hit] + tt[hit, None] * d[hit] + 1e-3 * d2).astype(np.float32)
             _, _, ms2, v2 = soup.trace_rays(o2, d2, counted=True)
 
-            def walk_roofline(visits, ms, key):  # 32 B per node visit + 48 B per triangle test
-                ach = (32.0 * visits[0] + 48.0 * visits[1]) / (ms * 1e-3) / 1e9
+            def walk_roofline(visits, ms, key):  # 32 B per binary node visit + 48 B per triangle test; a 4-wide node = 64 B
+                ach = (64.0 * visits[0] + 48.0 * visits[1]) / (ms * 1e-3) / 1e9
                 return {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": profile_traffic("lbvh_%s/%s" % (tag, key)), "peak_source": hbm_src,
                         "frac_of_l2": ach / l2_peak, "l2_peak": l2_peak, "l2_peak_source": "measured in this run (srt_measure_l2_read_gbs: all SMs stream a 32 MiB buffer resident in L2)",
-                        "note": "algorithmic bytes; a scene whose nodes + triangles fit the 126 MB L2 is served from L2: compare `traffic` (DRAM bytes, ncu) and frac_of_l2"}
+                        "algorithmic_bytes": "64 B x wide-node visits + 48 B x triangle tests", "note": "algorithmic bytes; a scene whose nodes + triangles fit the 126 MB L2 is served from L2: compare `traffic` (DRAM bytes, ncu) and frac_of_l2"}
             out["scene_bytes"] = n_tris * (64 + 48)
             out["trace"] = {"primary_rays_per_s": d.shape[0] / (ms1 * 1e-3), "secondary_rays_per_s": d2.shape[0] / (ms2 * 1e-3), "primary_hit_fraction": float(hit.mean()),
                             "primary_nodes_per_ray": v1[0] / d.shape[0], "primary_tris_per_ray": v1[1] / d.shape[0],

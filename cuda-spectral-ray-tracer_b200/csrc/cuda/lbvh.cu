@@ -490,31 +490,27 @@ __global__ void __launch_bounds__(256) k_collapse4(int n_internal, const SrtNode
     if (i >= n_internal) return;
     const uint4* np = reinterpret_cast<const uint4*>(nodes + i);
     const uint4 a = __ldg(np), b = __ldg(np + 1);
-    const uint32_t cbox[2][3] = {{a.x, a.y, a.z}, {a.w, b.x, b.y}};
-    const int cref[2] = {(int)b.z, (int)b.w};
-    uint32_t box[12];
-    int ref[4];
-    int s = 0;
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-        if (cref[c] < 0) {
-            box[3 * s] = cbox[c][0]; box[3 * s + 1] = cbox[c][1]; box[3 * s + 2] = cbox[c][2];
-            ref[s++] = cref[c];
-        } else {
-            const uint4* cp = reinterpret_cast<const uint4*>(nodes + cref[c]);
-            const uint4 ca = __ldg(cp), cb = __ldg(cp + 1);
-            box[3 * s] = ca.x; box[3 * s + 1] = ca.y; box[3 * s + 2] = ca.z;
-            ref[s++] = (int)cb.z;
-            box[3 * s] = ca.w; box[3 * s + 1] = cb.x; box[3 * s + 2] = cb.y;
-            ref[s++] = (int)cb.w;
-        }
-    }
-    for (; s < 4; s++) { box[3 * s] = box[3 * s + 1] = box[3 * s + 2] = 0u; ref[s] = SRT_WIDE_EMPTY; }
+    const int r0 = (int)b.z, r1 = (int)b.w;
+    // both children's nodes at once (node 0 stands in for a leaf child): no dependent second round trip, no indexed arrays
+    const uint4* p0 = reinterpret_cast<const uint4*>(nodes + (r0 >= 0 ? r0 : 0));
+    const uint4* p1 = reinterpret_cast<const uint4*>(nodes + (r1 >= 0 ? r1 : 0));
+    const uint4 a0 = __ldg(p0), b0 = __ldg(p0 + 1), a1 = __ldg(p1), b1 = __ldg(p1 + 1);
+    struct Slot { uint32_t x, y, z; int ref; };
+    const Slot none = {0u, 0u, 0u, SRT_WIDE_EMPTY};
+    // child 0 gives A0 (and A1 when it is internal), child 1 gives B0 (and B1)
+    const bool in0 = r0 >= 0, in1 = r1 >= 0;
+    const Slot A0 = in0 ? Slot{a0.x, a0.y, a0.z, (int)b0.z} : Slot{a.x, a.y, a.z, r0};
+    const Slot A1 = {a0.w, b0.x, b0.y, (int)b0.w};
+    const Slot B0 = in1 ? Slot{a1.x, a1.y, a1.z, (int)b1.z} : Slot{a.w, b.x, b.y, r1};
+    const Slot B1 = {a1.w, b1.x, b1.y, (int)b1.w};
+    const Slot s1 = in0 ? A1 : B0;
+    const Slot s2 = in0 ? B0 : (in1 ? B1 : none);
+    const Slot s3 = (in0 && in1) ? B1 : none;
     uint4* wp = reinterpret_cast<uint4*>(wide + i);
-    wp[0] = make_uint4(box[0], box[1], box[2], box[3]);
-    wp[1] = make_uint4(box[4], box[5], box[6], box[7]);
-    wp[2] = make_uint4(box[8], box[9], box[10], box[11]);
-    wp[3] = make_uint4((uint32_t)ref[0], (uint32_t)ref[1], (uint32_t)ref[2], (uint32_t)ref[3]);
+    wp[0] = make_uint4(A0.x, A0.y, A0.z, s1.x);
+    wp[1] = make_uint4(s1.y, s1.z, s2.x, s2.y);
+    wp[2] = make_uint4(s2.z, s3.x, s3.y, s3.z);
+    wp[3] = make_uint4((uint32_t)A0.ref, (uint32_t)s1.ref, (uint32_t)s2.ref, (uint32_t)s3.ref);
 }
 // left / right / parent in the oracle's numbering (internal i, leaf n-1+k), read off the emitted nodes: only dumps need them
 __global__ void __launch_bounds__(256) k_topology(int n, const SrtNode* __restrict__ nodes, int32_t* __restrict__ left, int32_t* __restrict__ right,
@@ -656,11 +652,11 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
         SRT_CUDA(cudaStreamWaitEvent(s->side, s->ev_sorted, 0));
         k_permute_tris<<<(3 * n + 255) / 256, 256, 0, s->side>>>(n, s->vals[0], reinterpret_cast<const float4*>(s->tris_in), reinterpret_cast<float4*>(s->tris));
         SRT_CUDA(cudaEventRecord(s->ev_side, s->side));
-        SRT_CUDA(cudaEventRecord(s->ev[3], st));  // (no separate hierarchy phase any more: ms_out[3] stays ~0)
         // process-wide counter: an epoch is never used twice, and the box arrays were zeroed when the scene was created (epoch 0 is never handed out)
         uint32_t epoch = g_refit_epoch.fetch_add(1u) + 1u;
         if (epoch == 0) epoch = g_refit_epoch.fetch_add(1u) + 1u;
         k_build_tree<<<grid_n, 256, 0, st>>>((int)n, s->keys[0], s->vals[0], s->leaf_boxes, reinterpret_cast<int32_t*>(s->visit), s->node_box_lo, s->node_box_hi, s->nodes, reinterpret_cast<const float4*>(s->scene_box + 8), epoch);
+        SRT_CUDA(cudaEventRecord(s->ev[3], st));  // ms_out[3] = hierarchy + refit + binary nodes, ms_out[4] = the 4-wide traversal copy
         if (n > 1) k_collapse4<<<(n - 1 + 255) / 256, 256, 0, st>>>((int)n - 1, s->nodes, s->wide);
         SRT_CUDA(cudaStreamWaitEvent(st, s->ev_side, 0));
         return true;

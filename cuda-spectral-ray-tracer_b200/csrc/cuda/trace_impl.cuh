@@ -437,6 +437,8 @@ __device__ __forceinline__ bool lbvh_step(const SceneRef& sc, V3 o, V3 d, const 
     const bool has = w.pend >= 0;
     const bool stuck = has && w.node < 0 && (w.top == SRT_STACK_EMPTY || w.top < 0);  // only a triangle test gets this lane any further
     const uint32_t waiting = __ballot_sync(lanes, has);
+    // (measured and dropped: letting up to 3 / 6 stuck lanes wait for company, and testing the leaves stacked right below the
+    // pending one in the same batch: 1.37 -> 1.26-1.31 G incoherent rays/s)
     if (__popc(waiting) >= SRT_LEAF_BATCH || __any_sync(lanes, stuck)) {
         if (has) {
             if (visits) visits[1]++;

@@ -279,7 +279,7 @@ class Scene:
     def rebuild_lbvh(self, repeats=1):
         ms = np.zeros(5, np.float32)
         _check(lib().srt_scene_rebuild_lbvh(self.h, repeats, ms.ctypes.data))
-        return dict(total=float(ms[0]), bounds_morton=float(ms[1]), sort=float(ms[2]), hierarchy=float(ms[3]), refit_emit=float(ms[4]))
+        return dict(total=float(ms[0]), bounds_morton=float(ms[1]), sort=float(ms[2]), tree=float(ms[3]), collapse=float(ms[4]))
 
     def trace_rays(self, o, d, counted=False):
         o = np.ascontiguousarray(o, np.float32); d = np.ascontiguousarray(d, np.float32)

@@ -140,7 +140,7 @@ int srt_scene_get_materials(const srt_scene*, float* mats_f, int32_t* mats_i);
 int srt_scene_get_lbvh(const srt_scene*, uint32_t* codes, uint32_t* sorted_idx, int32_t* left, int32_t* right,
                        int32_t* parent, float* node_boxes, float* scene_box);
 /* rebuilds the LBVH `repeats` times on device-resident triangles and returns the per-stage
- * CUDA-event times of the LAST build in ms: [total, bounds+morton, sort, 0 (no separate hierarchy phase), tree = hierarchy+refit+emit] */
+ * CUDA-event times of the LAST build in ms: [total, bounds+morton, sort, tree = hierarchy+refit+binary nodes, collapse = the 4-wide traversal nodes] */
 int srt_scene_rebuild_lbvh(srt_scene*, int repeats, float ms_out[5]);
 /* closest-hit queries through the device BVH (BASELINE.json configs[3] traversal rays/s):
  * o,d: n*3 floats; t_out[n] (-1 on miss... see tri_out), tri_out[n] = triangle index or -1.
