@@ -46,9 +46,9 @@ struct alignas(16) SrtFlatUnit {
 };
 #define SRT_FLAT_MAX_UNITS 32
 
-// ---- device BVH node, 32 B = ONE 32-byte sector, one LDG.256 (both child boxes live in the parent) ----
-// The walk is bound by the L1 / L2 traffic of divergent node fetches (tools/micro/gather_probe.cu: 64-B records as 4 x LDG.128
-// gather at 96 G records/s on a B200, 32-B records as one LDG.256 at 250 G), so the traversal copy of a node stores its child
+// ---- binary BVH node, 32 B = one 32-byte sector (both child boxes live in the parent); the walk reads the 4-wide nodes below ----
+// Divergent node fetches cost by the sector and by the request (tools/micro/gather_probe.cu: 64-B records as 4 x LDG.128 gather
+// at 96 G records/s on a B200, as 2 x LDG.256 at 119 G, 32-B records as one LDG.256 at 250 G), so a node stores its child
 // boxes on a uniform 16-bit grid over the scene box (cell = largest extent / 65529, grid coordinate g(x) = (x - lo) / cell + 3):
 //   w0..w2 = child 0: (xmin | xmax << 16), (ymin | ymax << 16), (zmin | zmax << 16)      w3..w5 = child 1, same
 //   w6, w7 = child0, child1: >= 0 internal node index, < 0 leaf with triangle index ~child

@@ -8,9 +8,11 @@
 //              stable => equal codes stay in triangle-index order
 //   tree     : hierarchy AND refit in one bottom-up kernel, one thread per leaf: a finished subtree [a, b] picks its parent by
 //              comparing the key differences at its two ends (the split with the longer common prefix is the nearer ancestor),
-//              the second subtree to arrive at a split owns both child boxes, unions them and emits the 32-B traversal node (child boxes on the 16-bit scene grid)
-//              under the node's Karras index (no fences: published boxes carry the build's epoch).  There is no separate
-//              top-down split search; left / right / parent arrays are derived from the nodes only when a caller dumps them
+//              the second subtree to arrive at a split owns both child boxes, unions them and emits the 32-B binary node (child
+//              boxes on the 16-bit scene grid, srt_types.h) under the node's Karras index (no fences: published boxes carry the
+//              build's epoch).  There is no separate top-down split search; left / right / parent arrays are derived from the
+//              nodes only when a caller dumps them
+//   collapse : binary nodes -> the 4-wide traversal nodes the walk reads (one streaming pass, same indices)
 //   permute  : triangles to leaf order -- a pure gather, on a second stream next to the tree kernel
 //
 // Specification and bit-exactness oracle: oracle/lbvh_oracle.c.  The reference

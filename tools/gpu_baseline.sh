@@ -22,16 +22,16 @@ timeout 300 $CMD > $O/${TAG}_plain_wave.log 2>&1 &&
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_wavefront -s 2 -c 2 -f -o $O/${TAG}_k_wavefront $CMD > $O/${TAG}_ncu_wave.log 2>&1
 echo "wave ncu rc=$?"
 cat $O/${TAG}_plain_wave.log
-# LBVH build at 1M: the eight launches of one warm build
+# LBVH build at 1M: the nine launches of one warm build
 CMD="python tools/lbvh_only.py"
 timeout 300 $CMD > $O/${TAG}_plain_lbvh.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -s 16 -c 8 -f -o $O/${TAG}_lbvh_1m $CMD > $O/${TAG}_ncu_lbvh.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -s 18 -c 9 -f -o $O/${TAG}_lbvh_1m $CMD > $O/${TAG}_ncu_lbvh.log 2>&1
 echo "lbvh ncu rc=$?"
 cat $O/${TAG}_plain_lbvh.log
 # soup queries of the bench (primary + secondary rays at 1M and 10M): DRAM traffic per launch
 CMD="python tools/lbvh_probe.py"
 timeout 300 $CMD > $O/${TAG}_plain_trace.log 2>&1 &&
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum --clock-control none -k regex:'k_trace_rays|k_bounds|k_morton|k_onesweep|k_permute|k_build_tree' -c 200 --csv --log-file $O/${TAG}_soup_traffic.csv $CMD > $O/${TAG}_ncu_trace.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum --clock-control none -k regex:'k_trace_rays|k_bounds|k_morton|k_onesweep|k_permute|k_build_tree|k_collapse4' -c 200 --csv --log-file $O/${TAG}_soup_traffic.csv $CMD > $O/${TAG}_ncu_trace.log 2>&1
 echo "trace ncu rc=$?"
 cat $O/${TAG}_plain_trace.log
 ls -la $O | tail -30
