@@ -54,6 +54,10 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per tile
 constexpr int SORT_WARPS = SORT_THREADS / 32;
+#ifndef SRT_SORT_LOOKBACK
+#define SRT_SORT_LOOKBACK 4
+#endif
+constexpr int SORT_LOOKBACK = SRT_SORT_LOOKBACK;  // predecessor status words read per round of the decoupled look-back
 
 struct DeviceScene {
     uint32_t n = 0, n_mats = 0;
@@ -300,13 +304,23 @@ __global__ void __launch_bounds__(SORT_THREADS) k_onesweep(const uint32_t* __res
         if (tile > 0) *lb = LB_LOCAL | local_count;
         uint32_t excl = 0;
         if (tile > 0) {
+            // the status words of SORT_LOOKBACK predecessors are read together (independent loads, one L2 round trip) and then
+            // consumed in order: with all tiles of a pass resident at once the walk is many tiles long, and one load per
+            // iteration made it a chain of L2 latencies
             int t = (int)tile - 1;
-            while (true) {
-                const uint32_t s = lookback[(size_t)t * RADIX + d];
-                const uint32_t flag = s & ~LB_MASK;
-                if (flag == LB_INCL) { excl += s & LB_MASK; break; }
-                if (flag == LB_LOCAL) { excl += s & LB_MASK; t--; }
-                // flag empty: the earlier tile has not published yet; poll again
+            bool done = false;
+            while (!done) {
+                uint32_t sw[SORT_LOOKBACK];
+#pragma unroll
+                for (int j = 0; j < SORT_LOOKBACK; j++) sw[j] = lookback[(size_t)max(t - j, 0) * RADIX + d];
+#pragma unroll
+                for (int j = 0; j < SORT_LOOKBACK; j++) {
+                    if (done || t < 0) break;   // (t < 0 cannot happen: tile 0 always publishes an inclusive prefix)
+                    const uint32_t flag = sw[j] & ~LB_MASK;
+                    if (flag == LB_INCL) { excl += sw[j] & LB_MASK; done = true; }
+                    else if (flag == LB_LOCAL) { excl += sw[j] & LB_MASK; t--; }
+                    else break;  // not published yet: poll again from this tile
+                }
             }
         }
         __threadfence();
