@@ -6,7 +6,9 @@
 #include "../common/srt_types.h"
 
 #define SRT_BLOCK 256
+#ifndef SRT_REFILL_LANES
 #define SRT_REFILL_LANES 8  // k_trace_rays fetches new rays once this many lanes of a warp are idle
+#endif
 #ifndef SRT_TRACE_MIN_BLOCKS
 #define SRT_TRACE_MIN_BLOCKS 5   // resident blocks per SM of k_trace_rays (48 registers; 4 and 6 blocks measured: -1 % / -6 %)
 #endif

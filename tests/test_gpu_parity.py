@@ -263,6 +263,33 @@ def test_grid_nodes_adversarial_rays(srt):
         assert hits > 0.3 * o.shape[0]
 
 
+def test_trace_rays_full_size_soup_vs_bruteforce(srt):
+    """BASELINE configs[3] size: closest-hit queries through the 4-wide grid nodes of the 1M-triangle soup (triangles a few grid
+    cells wide, a 40-level tree) against brute force over all triangles -- camera rays, incoherent rays from inside, rays from outside"""
+    n = 1 << 20
+    sg = srt.Scene(soup=n, seed=1984)
+    sc = oracle.Scene(soup=n, seed=1984)
+    rs = np.random.RandomState(5)
+    cam = sg.camera(1920, 1080).as_array()
+    px = rs.randint(0, 1920, 80); py = rs.randint(0, 1080, 80)
+    d0 = (cam[8:11][None, :] + px[:, None] * cam[2:5][None, :] + py[:, None] * cam[5:8][None, :] - cam[12:15][None, :])
+    o0 = np.tile(cam[12:15], (80, 1))
+    o1 = rs.rand(80, 3) * 555; d1 = rs.randn(80, 3)
+    tgt = rs.rand(40, 3) * 555; dirs = rs.randn(40, 3); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    o2 = tgt - dirs * 5000.0; d2 = dirs
+    o = np.concatenate([o0, o1, o2]).astype(np.float32); d = np.concatenate([d0, d1, d2]).astype(np.float32)
+    t, tri, ms = sg.trace_rays(o, d)
+    hits = 0
+    for i in range(o.shape[0]):
+        h, out, idx = sc.brute_hit(o[i], d[i])
+        if h:
+            hits += 1
+            assert tri[i] >= 0 and np.float32(out[1]) == t[i], (i, out[1], t[i], idx, tri[i])
+        else:
+            assert tri[i] == -1, (i, t[i], tri[i])
+    assert hits > 100
+
+
 def test_full_size_properties(srt):
     """BASELINE.json configs[1] size (1920x1080) at reduced spp: size-independent properties --
     the black margin outside the box stays exactly zero, the image mean matches the oracle's
