@@ -46,39 +46,28 @@ struct alignas(16) SrtFlatUnit {
 };
 #define SRT_FLAT_MAX_UNITS 32
 
-// ---- binary BVH node, 32 B = one 32-byte sector (both child boxes live in the parent); the walk reads the 4-wide nodes below ----
+// ---- 4-wide traversal node, 64 B = two 32-byte sectors, two LDG.256: the boxes and refs of a binary node's (up to) four grandchildren ----
 // Divergent node fetches cost by the sector and by the request (tools/micro/gather_probe.cu: 64-B records as 4 x LDG.128 gather
-// at 96 G records/s on a B200, as 2 x LDG.256 at 119 G, 32-B records as one LDG.256 at 250 G), so a node stores its child
-// boxes on a uniform 16-bit grid over the scene box (cell = largest extent / 65529, grid coordinate g(x) = (x - lo) / cell + 3):
-//   w0..w2 = child 0: (xmin | xmax << 16), (ymin | ymax << 16), (zmin | zmax << 16)      w3..w5 = child 1, same
-//   w6, w7 = child0, child1: >= 0 internal node index, < 0 leaf with triangle index ~child
-// min = floor(g) - 3, max = ceil(g) + 3: three cells of margin on every side.  The walk's roundings (csrc/cuda/trace_impl.cuh
-// grid_ray: the origin snaps to the grid's integer lattice, <= 0.5 cell; one more rounding of origin / direction, <= 1 cell;
-// build and transform, < 0.05) stay inside that margin, so a stored box always contains, for the walk's arithmetic, the
-// exact float box the reference's closest hit is defined on.  The exact boxes (Karras artefacts, bit-exact vs the oracle) live in
-// node_box_lo / node_box_hi and never enter the walk.
-struct alignas(32) SrtNode {
-    uint32_t c0x, c0y, c0z;
-    uint32_t c1x, c1y, c1z;
-    int32_t child0, child1;
-};
-#define SRT_GRID_MARGIN 3
-#define SRT_GRID_CELLS 65529.0f   // 65535 - 2 * margin
-#define SRT_GRID_OFFSET 3.0f     // = margin: the scene box starts at grid coordinate 3, so min - margin >= 0
-
-// ---- 4-wide traversal node, 64 B = two sectors, two LDG.256: the boxes and refs of a binary node's (up to) four grandchildren ----
-// Built from the 32-B binary nodes by one streaming pass (lbvh.cu k_collapse4) under the SAME index as the binary node it
-// collapses, so no numbering is needed: slots = for each child of node i, the child itself when it is a leaf, else the
-// child's two children.  The grid coordinates are copied, not re-quantised.  A step of the walk tests four boxes and
-// descends two levels of the binary tree: half the dependent steps per ray, and the per-step overhead of the walk (stack,
-// leaf batches, ray refill) is paid half as often.
+// at 96 G records/s on a B200, as 2 x LDG.256 at 119 G, 32-B records as one LDG.256 at 250 G), and a walk pays its per-step
+// overhead (stack, leaf batches, ray refill) once per node it opens.  So the walk does not read binary nodes with float boxes
+// (64 B for two children): one streaming pass after the bottom-up build (lbvh.cu k_collapse4) writes, under the SAME index as the
+// binary node it collapses, slots = for each child of node i, the child itself when it is a leaf, else the child's two children;
+// a step of the walk tests four boxes and descends two levels of the binary tree.
 //   w[3k .. 3k+2] = slot k: (xmin | xmax << 16), (ymin | ymax << 16), (zmin | zmax << 16)
 //   w[12 + k]     = slot k's ref: >= 0 wide node index, < 0 leaf with triangle index ~ref, SRT_WIDE_EMPTY = unused slot
+// Boxes live on a uniform 16-bit grid over the scene box (cell = largest extent / 65529, grid coordinate g(x) = (x - lo) / cell + 3),
+// min = floor(g) - 3, max = ceil(g) + 3: three cells of margin on every side.  The walk's roundings (csrc/cuda/trace_impl.cuh
+// grid_ray: the origin snaps to the grid's integer lattice, <= 0.5 cell; build and transform, < 0.05) stay inside that margin,
+// so a stored box always contains, for the walk's arithmetic, the exact float box the reference's closest hit is defined on.
+// The exact boxes (Karras artefacts, bit-exact vs the oracle) live in DeviceScene::node_box and never enter the walk.
 struct alignas(64) SrtWide {
     uint32_t box[12];
     int32_t ref[4];
 };
 #define SRT_WIDE_EMPTY 0x7fffffff
+#define SRT_GRID_MARGIN 3
+#define SRT_GRID_CELLS 65529.0f   // 65535 - 2 * margin
+#define SRT_GRID_OFFSET 3.0f     // = margin: the scene box starts at grid coordinate 3, so min - margin >= 0
 
 // ---- device material, 400 B: 95-sample spectrum + parameters ------------------------------
 struct alignas(16) SrtMaterial {

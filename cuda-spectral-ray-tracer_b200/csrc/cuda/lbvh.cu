@@ -8,11 +8,11 @@
 //              stable => equal codes stay in triangle-index order
 //   tree     : hierarchy AND refit in one bottom-up kernel, one thread per leaf: a finished subtree [a, b] picks its parent by
 //              comparing the key differences at its two ends (the split with the longer common prefix is the nearer ancestor),
-//              the second subtree to arrive at a split owns both child boxes, unions them and emits the 32-B binary node (child
-//              boxes on the 16-bit scene grid, srt_types.h) under the node's Karras index (no fences: published boxes carry the
-//              build's epoch).  There is no separate top-down split search; left / right / parent arrays are derived from the
-//              nodes only when a caller dumps them
-//   collapse : binary nodes -> the 4-wide traversal nodes the walk reads (one streaming pass, same indices)
+//              the second subtree to arrive at a split unions both child boxes and records the node's children and box under
+//              the node's Karras index (no fences: published boxes carry the build's epoch).  There is no separate top-down
+//              split search; left / right / parent arrays are derived from the children only when a caller dumps them
+//   collapse : the 4-wide traversal nodes the walk reads (srt_types.h): one streaming pass, same indices, child boxes quantised
+//              to the 16-bit scene grid with all lanes at work
 //   permute  : triangles to leaf order -- a pure gather, on a second stream next to the tree kernel
 //
 // Specification and bit-exactness oracle: oracle/lbvh_oracle.c.  The reference
@@ -76,9 +76,9 @@ struct DeviceScene {
     uint32_t* tile_counter = nullptr;  // SORT_PASSES dynamic tile ids
     int32_t *left = nullptr, *right = nullptr, *parent = nullptr;
     float* block_boxes = nullptr;  // kBoundsBlocks x 6 partial scene boxes
-    float4 *node_box_lo = nullptr, *node_box_hi = nullptr;  // (2n-1) each: (xmin,ymin,zmin,-), (xmax,ymax,zmax,-)
+    float4* node_box = nullptr;   // 2 x (2n-1): node i at [2i] = (xmin,ymin,zmin,epoch), [2i+1] = (xmax,ymax,zmax,epoch): one 32-byte sector per box
     uint32_t* visit = nullptr;    // n-1 refit arrival flags
-    SrtNode* nodes = nullptr;     // n-1 binary nodes (child boxes on the scene grid)
+    int2* children = nullptr;     // n-1 (left, right) per Karras node number: >= 0 internal number, < 0 leaf ~k
     SrtWide* wide = nullptr;      // n-1 four-wide traversal nodes, same indices
     SrtTri* tris = nullptr;       // n, LEAF order
     // wide leaf (scenes of <= 32 pre-test units): flat-order triangles + units, built on the host
@@ -450,34 +450,26 @@ __device__ __forceinline__ unsigned long long split_delta(const uint32_t* __rest
     return ((unsigned long long)(__ldg(keys + i) ^ __ldg(keys + i + 1)) << 32) | (uint32_t)(i ^ (i + 1));
 }
 __global__ void __launch_bounds__(256) k_build_tree(int n, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ sorted_idx,
-                                                    const float4* __restrict__ leaf_boxes, int32_t* other, float4* node_box_lo, float4* node_box_hi,
-                                                    SrtNode* __restrict__ nodes, const float4* __restrict__ grid, uint32_t epoch_bits) {
+                                                    const float4* __restrict__ leaf_boxes, int32_t* other, float4* node_box, int2* __restrict__ children,
+                                                    uint32_t epoch_bits) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const float4 G = __ldg(grid);
     const uint32_t src = sorted_idx[k];
     float4 lo = leaf_boxes[2ull * src], hi = leaf_boxes[2ull * src + 1];
     const float epoch = __uint_as_float(epoch_bits);  // only ever compared as bits
     lo.w = hi.w = epoch;
-    node_box_lo[n - 1 + k] = lo;
-    node_box_hi[n - 1 + k] = hi;
+    node_box[2 * (n - 1 + k)] = lo;
+    node_box[2 * (n - 1 + k) + 1] = hi;
     int a = k, b = k, split = -1;          // the subtree this thread carries: leaves [a, b], split between its children (-1: a leaf)
-    float4 llo, lhi, rlo, rhi;             // its children's boxes
-    llo = lhi = rlo = rhi = lo;
     while (true) {
         const bool root = a == 0 && b == n - 1;
         const bool is_left = root ? false : (a == 0 ? true : (b == n - 1 ? false : split_delta(keys, b) < split_delta(keys, a - 1)));
-        if (split >= 0) {  // an internal node: now that its number is known, emit it and publish its box
+        if (split >= 0) {  // an internal node: now that its number is known, record its children and publish its box
             const int self = root ? 0 : (is_left ? b : a);
             const int L = a == split ? n - 1 + split : split, R = b == split + 1 ? n - 1 + split + 1 : split + 1;
-            SrtNode nd;
-            nd.c0x = grid_pack(llo.x, lhi.x, G.x, G.w); nd.c0y = grid_pack(llo.y, lhi.y, G.y, G.w); nd.c0z = grid_pack(llo.z, lhi.z, G.z, G.w);
-            nd.c1x = grid_pack(rlo.x, rhi.x, G.x, G.w); nd.c1y = grid_pack(rlo.y, rhi.y, G.y, G.w); nd.c1z = grid_pack(rlo.z, rhi.z, G.z, G.w);
-            nd.child0 = L >= n - 1 ? ~(L - (n - 1)) : L;
-            nd.child1 = R >= n - 1 ? ~(R - (n - 1)) : R;
-            nodes[self] = nd;
-            node_box_lo[self] = lo;
-            node_box_hi[self] = hi;
+            children[self] = make_int2(L >= n - 1 ? ~(L - (n - 1)) : L, R >= n - 1 ? ~(R - (n - 1)) : R);
+            node_box[2 * self] = lo;
+            node_box[2 * self + 1] = hi;
         }
         if (root) return;
         const int p = is_left ? b : a - 1;  // the parent's split
@@ -489,52 +481,52 @@ __global__ void __launch_bounds__(256) k_build_tree(int n, const uint32_t* __res
         const int sib = is_left ? (far == b + 1 ? n - 1 + far : b + 1) : (far == a - 1 ? n - 1 + far : a - 1);
         float4 olo, ohi;
         do {
-            olo = ld_volatile_f4(node_box_lo + sib);
-            ohi = ld_volatile_f4(node_box_hi + sib);
+            olo = ld_volatile_f4(node_box + 2 * sib);
+            ohi = ld_volatile_f4(node_box + 2 * sib + 1);
         } while (__float_as_uint(olo.w) != epoch_bits || __float_as_uint(ohi.w) != epoch_bits);
-        if (is_left) { llo = lo; lhi = hi; rlo = olo; rhi = ohi; b = far; }
-        else { llo = olo; lhi = ohi; rlo = lo; rhi = hi; a = far; }
+        if (is_left) b = far;
+        else a = far;
         split = p;
         lo = make_float4(fminf(lo.x, olo.x), fminf(lo.y, olo.y), fminf(lo.z, olo.z), epoch);
         hi = make_float4(fmaxf(hi.x, ohi.x), fmaxf(hi.y, ohi.y), fmaxf(hi.z, ohi.z), epoch);
     }
 }
-// binary nodes -> 4-wide traversal nodes (srt_types.h): node i's slots are its leaf children and the children of its internal
-// children.  A left child is numbered `split`, a right child `split + 1`, so the two child nodes of i are one contiguous 64 B.
-__global__ void __launch_bounds__(256) k_collapse4(int n_internal, const SrtNode* __restrict__ nodes, SrtWide* __restrict__ wide) {
+// The 4-wide traversal nodes (srt_types.h), one thread per node: the slots of node i are its leaf children and the children of its
+// internal children.  The grid quantisation happens HERE, with all 32 lanes at work, not in the finisher of k_build_tree, where 3 - 6
+// lanes of a warp are left (the tree kernel: 0.111 -> 0.09 ms at 1M triangles).  A left child is numbered `split`, a right child
+// `split + 1`, so the two children of a node -- refs and boxes -- are neighbours in memory.
+__device__ __forceinline__ uint4 wide_slot(const float4* __restrict__ node_box, int n, int ref, float4 G) {
+    const int number = ref >= 0 ? ref : n - 1 + ~ref;
+    const float4 lo = __ldg(node_box + 2 * number), hi = __ldg(node_box + 2 * number + 1);
+    return make_uint4(grid_pack(lo.x, hi.x, G.x, G.w), grid_pack(lo.y, hi.y, G.y, G.w), grid_pack(lo.z, hi.z, G.z, G.w), (uint32_t)ref);
+}
+__global__ void __launch_bounds__(256) k_collapse4(int n, const int2* __restrict__ children, const float4* __restrict__ node_box,
+                                                   const float4* __restrict__ grid, SrtWide* __restrict__ wide) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_internal) return;
-    const uint4* np = reinterpret_cast<const uint4*>(nodes + i);
-    const uint4 a = __ldg(np), b = __ldg(np + 1);
-    const int r0 = (int)b.z, r1 = (int)b.w;
-    // both children's nodes at once (node 0 stands in for a leaf child): no dependent second round trip, no indexed arrays
-    const uint4* p0 = reinterpret_cast<const uint4*>(nodes + (r0 >= 0 ? r0 : 0));
-    const uint4* p1 = reinterpret_cast<const uint4*>(nodes + (r1 >= 0 ? r1 : 0));
-    const uint4 a0 = __ldg(p0), b0 = __ldg(p0 + 1), a1 = __ldg(p1), b1 = __ldg(p1 + 1);
-    struct Slot { uint32_t x, y, z; int ref; };
-    const Slot none = {0u, 0u, 0u, SRT_WIDE_EMPTY};
-    // child 0 gives A0 (and A1 when it is internal), child 1 gives B0 (and B1)
-    const bool in0 = r0 >= 0, in1 = r1 >= 0;
-    const Slot A0 = in0 ? Slot{a0.x, a0.y, a0.z, (int)b0.z} : Slot{a.x, a.y, a.z, r0};
-    const Slot A1 = {a0.w, b0.x, b0.y, (int)b0.w};
-    const Slot B0 = in1 ? Slot{a1.x, a1.y, a1.z, (int)b1.z} : Slot{a.w, b.x, b.y, r1};
-    const Slot B1 = {a1.w, b1.x, b1.y, (int)b1.w};
-    const Slot s1 = in0 ? A1 : B0;
-    const Slot s2 = in0 ? B0 : (in1 ? B1 : none);
-    const Slot s3 = (in0 && in1) ? B1 : none;
+    if (i >= n - 1) return;
+    const float4 G = __ldg(grid);
+    const int2 c = __ldg(children + i);
+    // the children's own children (node 0 stands in for a leaf child: no dependent branch before the loads are out)
+    const int2 g0 = __ldg(children + (c.x >= 0 ? c.x : 0)), g1 = __ldg(children + (c.y >= 0 ? c.y : 0));
+    const bool in0 = c.x >= 0, in1 = c.y >= 0;
+    const int r0 = in0 ? g0.x : c.x, r1 = in0 ? g0.y : (in1 ? g1.x : c.y), r2 = in0 ? (in1 ? g1.x : c.y) : (in1 ? g1.y : SRT_WIDE_EMPTY),
+              r3 = (in0 && in1) ? g1.y : SRT_WIDE_EMPTY;
+    const uint4 none = make_uint4(0u, 0u, 0u, (uint32_t)SRT_WIDE_EMPTY);
+    const uint4 s0 = wide_slot(node_box, n, r0, G), s1 = wide_slot(node_box, n, r1, G);
+    const uint4 s2 = r2 != SRT_WIDE_EMPTY ? wide_slot(node_box, n, r2, G) : none, s3 = r3 != SRT_WIDE_EMPTY ? wide_slot(node_box, n, r3, G) : none;
     uint4* wp = reinterpret_cast<uint4*>(wide + i);
-    wp[0] = make_uint4(A0.x, A0.y, A0.z, s1.x);
+    wp[0] = make_uint4(s0.x, s0.y, s0.z, s1.x);
     wp[1] = make_uint4(s1.y, s1.z, s2.x, s2.y);
     wp[2] = make_uint4(s2.z, s3.x, s3.y, s3.z);
-    wp[3] = make_uint4((uint32_t)A0.ref, (uint32_t)s1.ref, (uint32_t)s2.ref, (uint32_t)s3.ref);
+    wp[3] = make_uint4(s0.w, s1.w, s2.w, s3.w);
 }
 // left / right / parent in the oracle's numbering (internal i, leaf n-1+k), read off the emitted nodes: only dumps need them
-__global__ void __launch_bounds__(256) k_topology(int n, const SrtNode* __restrict__ nodes, int32_t* __restrict__ left, int32_t* __restrict__ right,
+__global__ void __launch_bounds__(256) k_topology(int n, const int2* __restrict__ children, int32_t* __restrict__ left, int32_t* __restrict__ right,
                                                   int32_t* __restrict__ parent) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) parent[0] = -1;
     if (i >= n - 1) return;
-    const int c0 = nodes[i].child0, c1 = nodes[i].child1;
+    const int c0 = children[i].x, c1 = children[i].y;
     const int L = c0 < 0 ? n - 1 + ~c0 : c0, R = c1 < 0 ? n - 1 + ~c1 : c1;
     left[i] = L;
     right[i] = R;
@@ -586,15 +578,14 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
               dalloc(s->centroids, 3ull * n) && dalloc(s->scene_box, 12) && dalloc(s->codes, n) && dalloc(s->keys[0], n) && dalloc(s->keys[1], n) &&
               dalloc(s->vals[0], n) && dalloc(s->vals[1], n) && dalloc(s->hist, SORT_PASSES * RADIX) &&
               dalloc(s->lookback, (size_t)SORT_PASSES * (s->tiles ? s->tiles : 1) * RADIX) && dalloc(s->tile_counter, SORT_PASSES) &&
-              dalloc(s->left, n) && dalloc(s->right, n) && dalloc(s->parent, 2ull * n) && dalloc(s->block_boxes, 6 * kBoundsBlocks) && dalloc(s->node_box_lo, 2ull * n) && dalloc(s->node_box_hi, 2ull * n) && dalloc(s->visit, n) &&
-              dalloc(s->nodes, n) && dalloc(s->wide, n) && dalloc(s->tris, n);
+              dalloc(s->left, n) && dalloc(s->right, n) && dalloc(s->parent, 2ull * n) && dalloc(s->block_boxes, 6 * kBoundsBlocks) && dalloc(s->node_box, 4ull * n) && dalloc(s->visit, n) &&
+              dalloc(s->children, n) && dalloc(s->wide, n) && dalloc(s->tris, n);
     for (auto& e : s->ev) ok = ok && cuda_ok(cudaEventCreate(&e), "cudaEventCreate", __FILE__, __LINE__);
     ok = ok && cuda_ok(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking), "cudaStreamCreate", __FILE__, __LINE__) &&
          cuda_ok(cudaEventCreateWithFlags(&s->ev_sorted, cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__) &&
          cuda_ok(cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__);
     // pooled blocks carry whatever their last owner wrote: the refit tells published boxes by an epoch in their fourth lane
-    if (ok) ok = cuda_ok(cudaMemset(s->node_box_lo, 0, 2ull * std::max(n, 1u) * sizeof(float4)), "clear node boxes", __FILE__, __LINE__) &&
-                 cuda_ok(cudaMemset(s->node_box_hi, 0, 2ull * std::max(n, 1u) * sizeof(float4)), "clear node boxes", __FILE__, __LINE__);
+    if (ok) ok = cuda_ok(cudaMemset(s->node_box, 0, 4ull * std::max(n, 1u) * sizeof(float4)), "clear node boxes", __FILE__, __LINE__);
     if (ok && n) {
         ok = cuda_ok(cudaMemcpy(s->verts, verts.data(), verts.size() * sizeof(float), cudaMemcpyHostToDevice), "upload verts", __FILE__, __LINE__) &&
              cuda_ok(cudaMemcpy(s->tris_in, packed.data(), packed.size() * sizeof(SrtTri), cudaMemcpyHostToDevice), "upload tris", __FILE__, __LINE__);
@@ -625,8 +616,8 @@ void device_scene_destroy(DeviceScene* s) {
     if (s->side) cudaStreamDestroy(s->side);
     if (s->ev_sorted) cudaEventDestroy(s->ev_sorted);
     if (s->ev_side) cudaEventDestroy(s->ev_side);
-    dfree(s->lookback); dfree(s->tile_counter); dfree(s->left); dfree(s->right); dfree(s->parent); dfree(s->node_box_lo); dfree(s->node_box_hi);
-    dfree(s->visit); dfree(s->nodes); dfree(s->wide); dfree(s->tris); dfree(s->flat_units); dfree(s->flat_tris); dfree(s->flat_to_orig);
+    dfree(s->lookback); dfree(s->tile_counter); dfree(s->left); dfree(s->right); dfree(s->parent); dfree(s->node_box);
+    dfree(s->visit); dfree(s->children); dfree(s->wide); dfree(s->tris); dfree(s->flat_units); dfree(s->flat_tris); dfree(s->flat_to_orig);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     delete s;
 }
@@ -676,14 +667,14 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
         // process-wide counter: an epoch is never used twice, and the box arrays were zeroed when the scene was created (epoch 0 is never handed out)
         uint32_t epoch = g_refit_epoch.fetch_add(1u) + 1u;
         if (epoch == 0) epoch = g_refit_epoch.fetch_add(1u) + 1u;
-        k_build_tree<<<grid_n, 256, 0, st>>>((int)n, s->keys[0], s->vals[0], s->leaf_boxes, reinterpret_cast<int32_t*>(s->visit), s->node_box_lo, s->node_box_hi, s->nodes, reinterpret_cast<const float4*>(s->scene_box + 8), epoch);
+        k_build_tree<<<grid_n, 256, 0, st>>>((int)n, s->keys[0], s->vals[0], s->leaf_boxes, reinterpret_cast<int32_t*>(s->visit), s->node_box, s->children, epoch);
         if (SRT_PERMUTE_MODE == 2) {  // enqueued after the tree kernel: its blocks fill what the climb leaves idle
             SRT_CUDA(cudaStreamWaitEvent(s->side, s->ev_sorted, 0));
             k_permute_tris<<<(3 * n + 255) / 256, 256, 0, s->side>>>(n, s->vals[0], reinterpret_cast<const float4*>(s->tris_in), reinterpret_cast<float4*>(s->tris));
             SRT_CUDA(cudaEventRecord(s->ev_side, s->side));
         }
         SRT_CUDA(cudaEventRecord(s->ev[3], st));  // ms_out[3] = hierarchy + refit + binary nodes, ms_out[4] = the 4-wide traversal copy
-        if (n > 1) k_collapse4<<<(n - 1 + 255) / 256, 256, 0, st>>>((int)n - 1, s->nodes, s->wide);
+        if (n > 1) k_collapse4<<<(n - 1 + 255) / 256, 256, 0, st>>>((int)n, s->children, s->node_box, reinterpret_cast<const float4*>(s->scene_box + 8), s->wide);
         if (SRT_PERMUTE_MODE == 1) k_permute_tris<<<(3 * n + 255) / 256, 256, 0, st>>>(n, s->vals[0], reinterpret_cast<const float4*>(s->tris_in), reinterpret_cast<float4*>(s->tris));
         else SRT_CUDA(cudaStreamWaitEvent(st, s->ev_side, 0));
         return true;
@@ -712,7 +703,7 @@ bool device_scene_download_lbvh(const DeviceScene* s, LbvhDump& o) {
     o.codes.resize(n); o.sorted_idx.resize(n); o.left.resize(n > 0 ? n - 1 : 0); o.right.resize(n > 0 ? n - 1 : 0);
     o.parent.resize(n ? 2 * n - 1 : 0); o.node_boxes.resize(n ? 6ull * (2 * n - 1) : 0);
     if (!n) return true;
-    if (n > 1) k_topology<<<(n + 255) / 256, 256, 0, s->stream>>>((int)n, s->nodes, s->left, s->right, s->parent);
+    if (n > 1) k_topology<<<(n + 255) / 256, 256, 0, s->stream>>>((int)n, s->children, s->left, s->right, s->parent);
     else SRT_CUDA(cudaMemsetAsync(s->parent, 0xFF, sizeof(int32_t), s->stream));
     count_launch();
     SRT_CUDA(cudaStreamSynchronize(s->stream));
@@ -724,12 +715,12 @@ bool device_scene_download_lbvh(const DeviceScene* s, LbvhDump& o) {
     }
     SRT_CUDA(cudaMemcpy(o.parent.data(), s->parent, (2 * n - 1) * 4, cudaMemcpyDeviceToHost));
     {
-        std::vector<float4> lo(2 * n - 1), hi(2 * n - 1);
-        SRT_CUDA(cudaMemcpy(lo.data(), s->node_box_lo, lo.size() * sizeof(float4), cudaMemcpyDeviceToHost));
-        SRT_CUDA(cudaMemcpy(hi.data(), s->node_box_hi, hi.size() * sizeof(float4), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < lo.size(); i++) {
+        std::vector<float4> box(2 * (2 * (size_t)n - 1));
+        SRT_CUDA(cudaMemcpy(box.data(), s->node_box, box.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < box.size() / 2; i++) {
             float* b = o.node_boxes.data() + 6 * i;
-            b[0] = lo[i].x; b[1] = hi[i].x; b[2] = lo[i].y; b[3] = hi[i].y; b[4] = lo[i].z; b[5] = hi[i].z;
+            const float4 lo = box[2 * i], hi = box[2 * i + 1];
+            b[0] = lo.x; b[1] = hi.x; b[2] = lo.y; b[3] = hi.y; b[4] = lo.z; b[5] = hi.z;
         }
     }
     SRT_CUDA(cudaMemcpy(o.scene_box, s->scene_box, 24, cudaMemcpyDeviceToHost));
