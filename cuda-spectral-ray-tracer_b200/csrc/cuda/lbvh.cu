@@ -658,29 +658,18 @@ bool device_scene_build_lbvh(DeviceScene* s, int repeats, float ms_out[5]) {
                                                          s->hist + p * RADIX, s->lookback + (size_t)p * s->tiles * RADIX, s->tile_counter + p);
         }
         SRT_CUDA(cudaEventRecord(s->ev[2], st));
-#ifndef SRT_PERMUTE_MODE
-#define SRT_PERMUTE_MODE 0
-#endif
         // the triangle permutation only needs the sorted order: second stream, next to hierarchy + refit
         SRT_CUDA(cudaEventRecord(s->ev_sorted, st));
-        if (SRT_PERMUTE_MODE == 0) {
-            SRT_CUDA(cudaStreamWaitEvent(s->side, s->ev_sorted, 0));
-            k_permute_tris<<<(3 * n + 255) / 256, 256, 0, s->side>>>(n, s->vals[0], reinterpret_cast<const float4*>(s->tris_in), reinterpret_cast<float4*>(s->tris));
-            SRT_CUDA(cudaEventRecord(s->ev_side, s->side));
-        }
+        SRT_CUDA(cudaStreamWaitEvent(s->side, s->ev_sorted, 0));
+        k_permute_tris<<<(3 * n + 255) / 256, 256, 0, s->side>>>(n, s->vals[0], reinterpret_cast<const float4*>(s->tris_in), reinterpret_cast<float4*>(s->tris));
+        SRT_CUDA(cudaEventRecord(s->ev_side, s->side));
         // process-wide counter: an epoch is never used twice, and the box arrays were zeroed when the scene was created (epoch 0 is never handed out)
         uint32_t epoch = g_refit_epoch.fetch_add(1u) + 1u;
         if (epoch == 0) epoch = g_refit_epoch.fetch_add(1u) + 1u;
         k_build_tree<<<grid_n, 256, 0, st>>>((int)n, s->keys[0], s->vals[0], s->leaf_boxes, reinterpret_cast<int32_t*>(s->visit), s->node_box, s->children, epoch);
-        if (SRT_PERMUTE_MODE == 2) {  // enqueued after the tree kernel: its blocks fill what the climb leaves idle
-            SRT_CUDA(cudaStreamWaitEvent(s->side, s->ev_sorted, 0));
-            k_permute_tris<<<(3 * n + 255) / 256, 256, 0, s->side>>>(n, s->vals[0], reinterpret_cast<const float4*>(s->tris_in), reinterpret_cast<float4*>(s->tris));
-            SRT_CUDA(cudaEventRecord(s->ev_side, s->side));
-        }
-        SRT_CUDA(cudaEventRecord(s->ev[3], st));  // ms_out[3] = hierarchy + refit + binary nodes, ms_out[4] = the 4-wide traversal copy
+        SRT_CUDA(cudaEventRecord(s->ev[3], st));  // ms_out[3] = hierarchy + refit, ms_out[4] = the 4-wide traversal nodes (+ what is left of the permutation)
         if (n > 1) k_collapse4<<<(n - 1 + 255) / 256, 256, 0, st>>>((int)n, s->children, s->node_box, reinterpret_cast<const float4*>(s->scene_box + 8), s->wide);
-        if (SRT_PERMUTE_MODE == 1) k_permute_tris<<<(3 * n + 255) / 256, 256, 0, st>>>(n, s->vals[0], reinterpret_cast<const float4*>(s->tris_in), reinterpret_cast<float4*>(s->tris));
-        else SRT_CUDA(cudaStreamWaitEvent(st, s->ev_side, 0));
+        SRT_CUDA(cudaStreamWaitEvent(st, s->ev_side, 0));
         return true;
     };
     for (int rep = 0; rep < repeats; rep++) {
