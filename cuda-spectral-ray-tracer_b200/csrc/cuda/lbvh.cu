@@ -437,7 +437,7 @@ const uint32_t* pixel_order_build(PixelOrder* o, const uint32_t* cost, uint32_t 
 // a child box on the 16-bit scene grid, SRT_GRID_MARGIN cells of margin (srt_types.h); min in the low half, max in the high half
 __device__ __forceinline__ uint32_t grid_pack(float mn, float mx, float lo, float inv_cell) {
     const float gl = (mn - lo) * inv_cell + SRT_GRID_OFFSET, gh = (mx - lo) * inv_cell + SRT_GRID_OFFSET;
-    const int ql = max((int)floorf(gl) - SRT_GRID_MARGIN, 0), qh = min((int)ceilf(gh) + SRT_GRID_MARGIN, 65535);
+    const int ql = max(__float2int_rd(gl) - SRT_GRID_MARGIN, 0), qh = min(__float2int_ru(gh) + SRT_GRID_MARGIN, 65535);  // floor / ceil in the conversion
     return (uint32_t)ql | ((uint32_t)qh << 16);
 }
 __device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
