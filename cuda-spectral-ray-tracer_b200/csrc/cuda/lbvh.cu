@@ -235,7 +235,8 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                            uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
                                                            const uint32_t* __restrict__ digit_count, volatile uint32_t* lookback,
-                                                           uint32_t* tile_counter) {
+                                                           uint32_t* tile_counter, int rounds) {
+    // rounds = keys per thread actually used (<= SORT_ITEMS): the host cuts a small sort into one equal tile per SM
     constexpr int WARPS = THREADS / 32, TILE = THREADS * SORT_ITEMS;  // THREADS >= RADIX: the per-digit steps are done by the first RADIX threads
     __shared__ uint32_t s_warp_hist[WARPS][RADIX];  // per-warp digit counts -> per-warp exclusive offsets
     __shared__ uint32_t s_tile_off[RADIX];               // exclusive offset of each digit inside the sorted tile
@@ -265,19 +266,21 @@ __global__ void __launch_bounds__(THREADS) k_onesweep(const uint32_t* __restrict
     if (tid < RADIX)
         for (int w = 0; w < warp; w++) digit_base += s_dtot[w];
     const uint32_t tile = s_tile;
-    const uint32_t tile_base = tile * TILE;
-    // warp-striped load: warp w owns [w*512, (w+1)*512), item i of lane l = w*512 + i*32 + l
+    const uint32_t tile_keys = (uint32_t)(THREADS * rounds), tile_base = tile * tile_keys;
+    // warp-striped load: warp w owns rounds * 32 consecutive keys, item i of lane l = w * rounds * 32 + i * 32 + l
     uint32_t key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
-        const uint32_t g = tile_base + warp * (SORT_ITEMS * 32) + i * 32 + lane;
-        key[i] = g < n ? keys_in[g] : 0xFFFFFFFFu;
-        val[i] = g < n ? vals_in[g] : 0u;
+        const uint32_t g = tile_base + warp * (rounds * 32) + i * 32 + lane;
+        const bool valid = i < rounds && g < n;
+        key[i] = valid ? keys_in[g] : 0xFFFFFFFFu;
+        val[i] = valid ? vals_in[g] : 0u;
     }
     // stable rank of every key among equal digits of its warp (items in order, lanes in order)
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
-        const uint32_t g = tile_base + warp * (SORT_ITEMS * 32) + i * 32 + lane;
+        if (i >= rounds) break;  // (uniform)
+        const uint32_t g = tile_base + warp * (rounds * 32) + i * 32 + lane;
         const bool valid = g < n;
         const uint32_t digit = (key[i] >> shift) & (RADIX - 1);
         const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : (RADIX + lane));
@@ -353,8 +356,8 @@ __global__ void __launch_bounds__(THREADS) k_onesweep(const uint32_t* __restrict
     // scatter into shared memory in sorted order
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
-        const uint32_t g = tile_base + warp * (SORT_ITEMS * 32) + i * 32 + lane;
-        if (g < n) {
+        const uint32_t g = tile_base + warp * (rounds * 32) + i * 32 + lane;
+        if (i < rounds && g < n) {
             const uint32_t digit = (key[i] >> shift) & (RADIX - 1);
             const uint32_t pos = s_tile_off[digit] + s_warp_hist[warp][digit] + rank[i];
             s_keys[pos] = key[i];
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(THREADS) k_onesweep(const uint32_t* __restrict
     }
     __syncthreads();
     // coalesced write-out: consecutive threads write consecutive addresses inside each digit run
-    const uint32_t count = min((uint32_t)TILE, n - tile_base);
+    const uint32_t count = min(tile_keys, n - tile_base);
     for (uint32_t j = tid; j < count; j += THREADS) {
         const uint32_t k = s_keys[j];
         const uint32_t digit = (k >> shift) & (RADIX - 1);
@@ -389,11 +392,18 @@ static int sm_count();
 // the tiles, half the look-back, one block's fixed costs per SM -- 1M keys: 24.5 -> 22.5 us per pass; 10M keys are faster on the
 // 4096-key tiles (0.51 vs 0.60 ms: three resident blocks per SM instead of one).
 static int sort_threads_for(uint32_t n) { return (n + 512 * SORT_ITEMS - 1) / (512 * SORT_ITEMS) <= (uint32_t)sm_count() ? 512 : 256; }
-static uint32_t sort_tiles_for(uint32_t n) { const uint32_t tile = (uint32_t)sort_threads_for(n) * SORT_ITEMS; return (n + tile - 1) / tile; }
+// keys per thread: SORT_ITEMS, or -- small sorts -- as few as give every SM one tile (1M keys: 14 x 512 = 7168 keys, 147 tiles)
+static int sort_rounds_for(uint32_t n) {
+    if (sort_threads_for(n) != 512) return SORT_ITEMS;
+    const uint32_t per_sm = (n + (uint32_t)sm_count() - 1) / (uint32_t)sm_count();
+    return (int)std::min<uint32_t>(SORT_ITEMS, std::max<uint32_t>(1u, (per_sm + 511u) / 512u));
+}
+static uint32_t sort_tiles_for(uint32_t n) { const uint32_t tile = (uint32_t)(sort_threads_for(n) * sort_rounds_for(n)); return (n + tile - 1) / tile; }
 static void launch_onesweep(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, uint32_t n, int shift,
                             const uint32_t* digit_count, uint32_t* lookback, uint32_t* tile_counter, cudaStream_t st) {
-    if (sort_threads_for(n) == 512) k_onesweep<512><<<sort_tiles_for(n), 512, sort_smem(512), st>>>(keys_in, vals_in, keys_out, vals_out, n, shift, digit_count, lookback, tile_counter);
-    else k_onesweep<256><<<sort_tiles_for(n), 256, sort_smem(256), st>>>(keys_in, vals_in, keys_out, vals_out, n, shift, digit_count, lookback, tile_counter);
+    const int rounds = sort_rounds_for(n);
+    if (sort_threads_for(n) == 512) k_onesweep<512><<<sort_tiles_for(n), 512, sort_smem(512), st>>>(keys_in, vals_in, keys_out, vals_out, n, shift, digit_count, lookback, tile_counter, rounds);
+    else k_onesweep<256><<<sort_tiles_for(n), 256, sort_smem(256), st>>>(keys_in, vals_in, keys_out, vals_out, n, shift, digit_count, lookback, tile_counter, rounds);
 }
 
 // ---- pixel order of the wavefront renderer (renderer.cu) -------------------------------------
@@ -427,7 +437,7 @@ struct PixelOrder {
 PixelOrder* pixel_order_create(uint32_t max_slots) {
     auto* o = new PixelOrder();
     o->cap = max_slots ? max_slots : 1;
-    o->tiles = (o->cap + SORT_TILE - 1) / SORT_TILE;
+    o->tiles = std::max<uint32_t>((o->cap + SORT_TILE - 1) / SORT_TILE, (uint32_t)sm_count() + 1u);
     bool ok = true;
     for (int k = 0; k < 2; k++) ok = ok && device_pool_alloc((void**)&o->keys[k], o->cap * sizeof(uint32_t)) && device_pool_alloc((void**)&o->vals[k], o->cap * sizeof(uint32_t));
     ok = ok && device_pool_alloc((void**)&o->small, ((size_t)RADIX + 64 + (size_t)o->tiles * RADIX) * sizeof(uint32_t));
@@ -443,7 +453,7 @@ void pixel_order_destroy(PixelOrder* o) {
 // enqueues the sort on `st`; the returned device array (n entries, owned slots first) is valid until the next call
 const uint32_t* pixel_order_build(PixelOrder* o, const uint32_t* cost, uint32_t n, uint32_t samples, cudaStream_t st) {
     if (!o || n == 0 || n > o->cap || samples == 0) return nullptr;
-    const uint32_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const uint32_t tiles = std::max<uint32_t>((n + SORT_TILE - 1) / SORT_TILE, sort_tiles_for(n));  // status words to clear
     uint32_t* hist = o->small;
     uint32_t* ticket = o->small + RADIX;
     uint32_t* lookback = o->small + RADIX + 64;
@@ -604,7 +614,7 @@ DeviceScene* device_scene_create(const std::vector<HostTri>& tris, const std::ve
         const uint32_t mt = tris[i].mat < mats.size() ? mats[tris[i].mat].type : SRT_LAMBERTIAN;
         packed[i] = tris[i].pack(mt, prio[i]);
     }
-    s->tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    s->tiles = std::max<uint32_t>((n + SORT_TILE - 1) / SORT_TILE, (uint32_t)sm_count() + 1u);  // look-back words: small sorts run one (smaller) tile per SM
     bool ok = dalloc(s->verts, 9ull * n) && dalloc(s->tris_in, n) && dalloc(s->mats, mats.size()) && dalloc(s->leaf_boxes, 2ull * n) &&
               dalloc(s->centroids, 3ull * n) && dalloc(s->scene_box, 12) && dalloc(s->codes, n) && dalloc(s->keys[0], n) && dalloc(s->keys[1], n) &&
               dalloc(s->vals[0], n) && dalloc(s->vals[1], n) && dalloc(s->hist, SORT_PASSES * RADIX) &&
