@@ -160,6 +160,7 @@ struct DeviceRenderer {
     size_t chunk_px = 0;
     // optional per-kernel timing: event pairs tagged with a category (0 pixel order, 1 k_wavefront, 2 k_megakernel, 3 other)
     std::vector<cudaEvent_t> ev_pool;
+    std::vector<cudaEvent_t> band_ev;  // one per row band of a pipelined whole-frame resolve
     std::vector<int> ev_tag;
     size_t ev_used = 0;
     double cat_ms[4] = {0, 0, 0, 0};
@@ -213,6 +214,7 @@ void device_renderer_destroy(DeviceRenderer* r) {
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
     for (cudaEvent_t e : r->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : r->band_ev) cudaEventDestroy(e);
     delete r;
 }
 
@@ -546,7 +548,8 @@ bool device_renderer_render_chunk(DeviceRenderer* r, unsigned off_x, unsigned of
 }
 
 // frame_buffer holds 0..255 as float (frame_buffer.cuh:6-44): widen `count` bytes per channel into the caller's planes
-static void widen_rows(const unsigned char* stage, size_t stage_plane, float* const dst[3], unsigned off_x, unsigned off_y, unsigned w, unsigned h, unsigned img_w) {
+static void widen_rows(const unsigned char* stage, size_t stage_plane, float* const dst[3], unsigned off_x, unsigned off_y, unsigned w, unsigned h, unsigned img_w,
+                       bool one_thread = false) {
     auto widen = [&](unsigned y0, unsigned y1) {
         for (int c = 0; c < 3; c++) {
             if (!dst[c]) continue;
@@ -557,7 +560,7 @@ static void widen_rows(const unsigned char* stage, size_t stage_plane, float* co
             }
         }
     };
-    if ((size_t)w * h >= (1u << 18)) {  // big regions: the 4x wider float planes are written by several host threads, one band of rows each
+    if (!one_thread && (size_t)w * h >= (1u << 18)) {  // big regions: the 4x wider float planes are written by several host threads, one band of rows each
         const unsigned nt = std::max(1u, std::min({8u, std::thread::hardware_concurrency(), h}));
         std::vector<std::thread> pool;
         for (unsigned k = 1; k < nt; k++) pool.emplace_back(widen, (unsigned)((uint64_t)h * k / nt), (unsigned)((uint64_t)h * (k + 1) / nt));
@@ -576,12 +579,45 @@ bool device_renderer_resolve(DeviceRenderer* r, unsigned off_x, unsigned off_y, 
     if (n == 0) return true;
     std::lock_guard<std::mutex> lock(r->stage_mu);
     if (!ensure_staging(r, 3 * n, 3 * n)) return false;  // a whole-image resolve after a chunked / reduced render grows the buffers once
+    float* const dst[3] = {fr, fg, fb};
+    // Big regions (a whole frame) go out as a pipeline of row bands: tonemap + D2H of band k+1 run while a host thread widens band k
+    // into the caller's float planes, so the frame costs one band's copy plus one band's widening after the last tonemap instead
+    // of the whole copy followed by the whole widening.
+    const unsigned nb = n >= (1u << 18) ? std::max(1u, std::min({8u, std::thread::hardware_concurrency(), h})) : 1u;
+    if (nb > 1) {
+        while (r->band_ev.size() < nb) {
+            cudaEvent_t e = nullptr;
+            SRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            r->band_ev.push_back(e);
+        }
+        auto row0 = [&](unsigned b) { return (unsigned)((uint64_t)h * b / nb); };
+        for (unsigned b = 0; b < nb; b++) {  // band b: rows [y0, y1), three byte planes of w * (y1 - y0) at byte 3 * w * y0 of both stagings
+            const unsigned y0 = row0(b), y1 = row0(b + 1);
+            const size_t at = (size_t)3 * w * y0, bytes = (size_t)3 * w * (y1 - y0);
+            T.resolve(r->P.acc, r->P.plane, r->P.img_w, off_x, off_y + y0, w, y1 - y0, r->P.spp, r->d_rgb + at, r->stream);
+            r->launches++; count_launch();
+            SRT_CUDA_LAST();
+            SRT_CUDA(cudaMemcpyAsync(r->h_stage + at, r->d_rgb + at, bytes, cudaMemcpyDeviceToHost, r->stream));
+            SRT_CUDA(cudaEventRecord(r->band_ev[b], r->stream));
+        }
+        std::atomic<int> failed{0};
+        auto band = [&](unsigned b) {
+            const unsigned y0 = row0(b), y1 = row0(b + 1);
+            if (cudaSetDevice(r->device) != cudaSuccess || cudaEventSynchronize(r->band_ev[b]) != cudaSuccess) { failed = 1; return; }
+            widen_rows(r->h_stage + (size_t)3 * w * y0, (size_t)w * (y1 - y0), dst, off_x, off_y + y0, w, y1 - y0, img_w, true);
+        };
+        std::vector<std::thread> pool;
+        for (unsigned b = 1; b < nb; b++) pool.emplace_back(band, b);
+        band(0);
+        for (std::thread& th : pool) th.join();
+        if (failed) { cudaGetLastError(); set_error("film read-back failed (band event)"); return false; }
+        return true;
+    }
     T.resolve(r->P.acc, r->P.plane, r->P.img_w, off_x, off_y, w, h, r->P.spp, r->d_rgb, r->stream);
     r->launches++; count_launch();
     SRT_CUDA_LAST();
     SRT_CUDA(cudaMemcpyAsync(r->h_stage, r->d_rgb, 3 * n, cudaMemcpyDeviceToHost, r->stream));
     SRT_CUDA(cudaStreamSynchronize(r->stream));
-    float* const dst[3] = {fr, fg, fb};
     widen_rows(r->h_stage, n, dst, off_x, off_y, w, h, img_w);
     return true;
 }
@@ -614,19 +650,27 @@ bool device_renderer_exchange_film(DeviceRenderer* r, float* fr, float* fg, floa
     if (tr.on) { cudaStreamSynchronize(st); tr.mark("slice tonemap"); }
     if (!comm_gather_bytes(c, r->d_rgb, r->d_gather, 3 * cnt, st)) return false;
     if (tr.on) { cudaStreamSynchronize(st); tr.mark("gather"); }
-    if (rank == 0) SRT_CUDA(cudaMemcpyAsync(r->h_stage, r->d_gather, world * 3 * cnt, cudaMemcpyDeviceToHost, st));
+    // rank 0 copies the gathered bytes to the host slice by slice; the host thread that widens slice k waits for that copy only
+    const bool threaded = rank == 0 && npx >= (1u << 18) && world > 1;
+    if (rank == 0) {
+        while (threaded && r->band_ev.size() < world) {
+            cudaEvent_t e = nullptr;
+            SRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            r->band_ev.push_back(e);
+        }
+        for (size_t k = 0; k < world; k++) {
+            SRT_CUDA(cudaMemcpyAsync(r->h_stage + k * 3 * cnt, r->d_gather + k * 3 * cnt, 3 * cnt, cudaMemcpyDeviceToHost, st));
+            if (threaded) SRT_CUDA(cudaEventRecord(r->band_ev[k], st));
+        }
+    }
     SRT_CUDA(cudaEventRecord(r->ex2, st));
-    SRT_CUDA(cudaEventSynchronize(r->ex2));
-    float ms = 0;
-    SRT_CUDA(cudaEventElapsedTime(&ms, r->ex0, r->ex1));
-    r->exchange_ms += ms;
-    SRT_CUDA(cudaEventElapsedTime(&ms, r->ex1, r->ex2));
-    r->film_out_ms += ms;
+    if (!threaded) SRT_CUDA(cudaEventSynchronize(r->ex2));
     r->exchanged = true;
-    tr.mark("d2h");
+    std::atomic<int> failed{0};
     if (rank == 0) {  // slices are runs of the raster: widen them as one-row regions
         float* const planes[3] = {fr, fg, fb};
         auto widen = [&](size_t k) {
+            if (threaded && (cudaSetDevice(r->device) != cudaSuccess || cudaEventSynchronize(r->band_ev[k]) != cudaSuccess)) { failed = 1; return; }
             const size_t f = k * cnt;
             if (f >= npx) return;
             const size_t n = std::min(cnt, npx - f);
@@ -637,7 +681,7 @@ bool device_renderer_exchange_film(DeviceRenderer* r, float* fr, float* fg, floa
                 widen_u8_to_f32(src, o, n);
             }
         };
-        if (npx >= (1u << 18) && world > 1) {
+        if (threaded) {
             std::vector<std::thread> pool;
             for (size_t k = 1; k < world; k++) pool.emplace_back(widen, k);
             widen(0);
@@ -646,6 +690,14 @@ bool device_renderer_exchange_film(DeviceRenderer* r, float* fr, float* fg, floa
             for (size_t k = 0; k < world; k++) widen(k);
         }
     }
+    if (threaded) SRT_CUDA(cudaEventSynchronize(r->ex2));
+    if (failed) { cudaGetLastError(); set_error("film read-back failed (slice event)"); return false; }
+    float ms = 0;
+    SRT_CUDA(cudaEventElapsedTime(&ms, r->ex0, r->ex1));
+    r->exchange_ms += ms;
+    SRT_CUDA(cudaEventElapsedTime(&ms, r->ex1, r->ex2));
+    r->film_out_ms += ms;
+    tr.mark("d2h + widen");
     return true;
 }
 
