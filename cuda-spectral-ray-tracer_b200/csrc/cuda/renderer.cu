@@ -606,7 +606,7 @@ bool device_renderer_resolve(DeviceRenderer* r, unsigned off_x, unsigned off_y, 
             if (cudaSetDevice(r->device) != cudaSuccess || cudaEventSynchronize(r->band_ev[b]) != cudaSuccess) { failed = 1; return; }
             widen_rows(r->h_stage + (size_t)3 * w * y0, (size_t)w * (y1 - y0), dst, off_x, off_y + y0, w, y1 - y0, img_w, true);
         };
-        std::vector<std::thread> pool;
+        std::vector<std::thread> pool;  // (a persistent worker pool instead of eight threads per frame: measured, no gain)
         for (unsigned b = 1; b < nb; b++) pool.emplace_back(band, b);
         band(0);
         for (std::thread& th : pool) th.join();
@@ -669,21 +669,24 @@ bool device_renderer_exchange_film(DeviceRenderer* r, float* fr, float* fg, floa
     std::atomic<int> failed{0};
     if (rank == 0) {  // slices are runs of the raster: widen them as one-row regions
         float* const planes[3] = {fr, fg, fb};
-        auto widen = [&](size_t k) {
+        // a slice is widened by `parts` host threads (about eight in all, whatever the world size), each waiting for its slice's copy
+        const size_t parts = threaded ? std::max<size_t>(1, 8 / world) : 1;
+        auto widen = [&](size_t job) {
+            const size_t k = job / parts, part = job % parts;
             if (threaded && (cudaSetDevice(r->device) != cudaSuccess || cudaEventSynchronize(r->band_ev[k]) != cudaSuccess)) { failed = 1; return; }
             const size_t f = k * cnt;
             if (f >= npx) return;
-            const size_t n = std::min(cnt, npx - f);
+            const size_t n = std::min(cnt, npx - f), a = n * part / parts, b = n * (part + 1) / parts;
             for (int ch = 0; ch < 3; ch++) {
                 if (!planes[ch]) continue;
                 const unsigned char* src = r->h_stage + (k * 3 + ch) * cnt;
                 float* o = planes[ch] + f;
-                widen_u8_to_f32(src, o, n);
+                widen_u8_to_f32(src + a, o + a, b - a);
             }
         };
         if (threaded) {
             std::vector<std::thread> pool;
-            for (size_t k = 1; k < world; k++) pool.emplace_back(widen, k);
+            for (size_t j = 1; j < world * parts; j++) pool.emplace_back(widen, j);
             widen(0);
             for (std::thread& th : pool) th.join();
         } else {

@@ -694,6 +694,19 @@ def test_whole_image_resolve_after_small_chunks(srt):
     assert np.array_equal(fb.rgb(), chunked)
 
 
+def test_banded_whole_frame_readback_vs_oracle(srt):
+    """frames of >= 2^18 pixels leave the device as a pipeline of row bands (tonemap + D2H of band k+1 while a host thread widens
+    band k, renderer.cu device_renderer_resolve): the sRGB planes must equal the oracle's tonemap of the same XYZ film, byte for
+    byte, at a height that does not divide into the bands evenly"""
+    w, h, spp = 1024, 517, 2
+    rgb, xyz, _ = srt.render(scene_id=1, w=w, h=h, spp=spp, bounce=10, strict=True)
+    orgb, oxyz = oracle.render(oracle.Scene(1), oracle.camera(w, h), spp, 10)
+    same = (xyz.view(np.uint32) == oxyz.view(np.uint32)).all(axis=0)
+    assert same.mean() >= 0.99999
+    assert np.array_equal(rgb[:, same], orgb[:, same])
+    assert rgb.min() >= 0 and rgb.max() <= 255 and float(rgb.std()) > 1.0
+
+
 def test_full_bench_size_bitwise_vs_oracle(srt):
     """The whole bench workload (BASELINE configs[1]: Cornell 1920x1080, 64 spp, depth 10; 435 M rays) in strict FP mode
     against the CPU oracle (which equals the real reference host build on this frame bit for bit, checked in the
