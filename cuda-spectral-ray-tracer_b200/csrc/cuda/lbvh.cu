@@ -55,8 +55,14 @@ constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per tile
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr size_t sort_smem(int threads) { return 2ull * threads * SORT_ITEMS * sizeof(uint32_t); }  // dynamic shared memory of k_onesweep (the sorted tile)
+#ifndef SRT_SORT_BALLOT
+#define SRT_SORT_BALLOT 1
+#endif
 #ifndef SRT_SORT_LOOKBACK
 #define SRT_SORT_LOOKBACK 4
+#endif
+#ifndef SRT_SORT_LOOKBACK_512
+#define SRT_SORT_LOOKBACK_512 4  // the one-tile-per-SM kernel of small sorts: all tiles run at once, every walk is long
 #endif
 constexpr int SORT_LOOKBACK = SRT_SORT_LOOKBACK;  // predecessor status words read per round of the decoupled look-back
 
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(256) k_morton_hist(const float* __restrict__ c
 constexpr uint32_t LB_LOCAL = 1u << 30, LB_INCL = 2u << 30, LB_MASK = (1u << 30) - 1;
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1) k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                            uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
                                                            const uint32_t* __restrict__ digit_count, volatile uint32_t* lookback,
                                                            uint32_t* tile_counter, int rounds) {
@@ -247,6 +253,7 @@ __global__ void __launch_bounds__(THREADS) k_onesweep(const uint32_t* __restrict
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_dtot[RADIX / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);  // dynamic tile id: earlier tiles are always already running (first: its round trip overlaps the digit scan)
     // global base of every digit = exclusive scan of the pass' 256 digit counts: every block does the tiny scan itself
     uint32_t digit_base = 0;
     if (tid < RADIX) {
@@ -260,7 +267,6 @@ __global__ void __launch_bounds__(THREADS) k_onesweep(const uint32_t* __restrict
         if (lane == 31) s_dtot[warp] = inc;
         digit_base = inc - c;  // + the totals of the warps before, added after the first barrier below
     }
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);  // dynamic tile id: earlier tiles are always already running
     for (int i = tid; i < WARPS * RADIX; i += THREADS) (&s_warp_hist[0][0])[i] = 0;
     __syncthreads();
     if (tid < RADIX)
@@ -283,7 +289,20 @@ __global__ void __launch_bounds__(THREADS) k_onesweep(const uint32_t* __restrict
         const uint32_t g = tile_base + warp * (rounds * 32) + i * 32 + lane;
         const bool valid = g < n;
         const uint32_t digit = (key[i] >> shift) & (RADIX - 1);
+#if SRT_SORT_BALLOT
+        // lanes with the same digit, from one ballot per digit bit: constant time, where MATCH.ANY takes one step per distinct value
+        // in the warp (~30 of 32 for the digits of Morton codes)
+        uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int b = 0; b < RADIX_BITS; b++) {
+            const bool bit = (digit >> b) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? bal : ~bal;
+        }
+        if (!valid) peers = 1u << lane;
+#else
         const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : (RADIX + lane));
+#endif
         const uint32_t before = __popc(peers & ((1u << lane) - 1));
         uint32_t base = 0;
         if (valid && before == 0) {  // leader of the peer group bumps the warp counter
@@ -315,14 +334,15 @@ __global__ void __launch_bounds__(THREADS) k_onesweep(const uint32_t* __restrict
             // the status words of SORT_LOOKBACK predecessors are read together (independent loads, one L2 round trip) and then
             // consumed in order: with all tiles of a pass resident at once the walk is many tiles long, and one load per
             // iteration made it a chain of L2 latencies
+            constexpr int LB = THREADS == 512 ? SRT_SORT_LOOKBACK_512 : SORT_LOOKBACK;
             int t = (int)tile - 1;
             bool done = false;
             while (!done) {
-                uint32_t sw[SORT_LOOKBACK];
+                uint32_t sw[LB];
 #pragma unroll
-                for (int j = 0; j < SORT_LOOKBACK; j++) sw[j] = lookback[(size_t)max(t - j, 0) * RADIX + d];
+                for (int j = 0; j < LB; j++) sw[j] = lookback[(size_t)max(t - j, 0) * RADIX + d];
 #pragma unroll
-                for (int j = 0; j < SORT_LOOKBACK; j++) {
+                for (int j = 0; j < LB; j++) {
                     if (done || t < 0) break;   // (t < 0 cannot happen: tile 0 always publishes an inclusive prefix)
                     const uint32_t flag = sw[j] & ~LB_MASK;
                     if (flag == LB_INCL) { excl += sw[j] & LB_MASK; done = true; }
