@@ -804,16 +804,8 @@ __device__ __forceinline__ uint32_t ref_thread_index(const WaveParams& P, uint32
 // the same queue find each other with one __match_any_sync, the first lane of every group reserves the group's room with
 // one shared-memory atomicAdd (up to four addresses in one instruction), lanes write at base + rank-in-group.
 // which = 0..3 (regenerate, lambertian, metallic, dielectric), or 4 = this lane pushes nothing.
-#ifndef SRT_PUSH_BALLOT
-#define SRT_PUSH_BALLOT 0
-#endif
 __device__ __forceinline__ void queue_push_all(uint16_t* __restrict__ q, uint32_t S, int* counters, uint32_t which, uint32_t local_slot) {
-#if SRT_PUSH_BALLOT
-    const uint32_t b0 = __ballot_sync(0xffffffffu, which & 1u), b1 = __ballot_sync(0xffffffffu, which & 2u), b2 = __ballot_sync(0xffffffffu, which & 4u);
-    const uint32_t peers = ((which & 1u) ? b0 : ~b0) & ((which & 2u) ? b1 : ~b1) & ((which & 4u) ? b2 : ~b2);
-#else
     const uint32_t peers = __match_any_sync(0xffffffffu, which);
-#endif
     const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
     int base = 0;
     if (lane == leader && which < 4u) base = atomicAdd(counters + which, __popc(peers));
